@@ -1,0 +1,680 @@
+"""Host-side data model of the B200 backend.
+
+These classes mirror, attribute for attribute, the objects GemPy's bridge builds for
+``gempy_engine.compute_model`` and the objects GemPy reads back from the returned
+``Solutions`` (reference call site: gempy/API/compute_API.py:68-73; builders:
+gempy/modules/data_manipulation/_engine_factory.py:26-56,71-104; consumers:
+gempy/core/data/geo_model.py:100-127, gempy/modules/mesh_extranction/marching_cubes.py:27-47).
+The engine package itself is not vendored in the reference tree, so the names below are the
+ones the reference *uses*, not a copy of any source file.
+
+Everything here is plain numpy on the host.  Device memory is owned by torch tensors inside
+``gempy_b200.engine.compute`` and only materialised into these containers at the end of a
+compute call.
+"""
+from __future__ import annotations
+
+import enum
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+
+# --------------------------------------------------------------------------- enums
+class AvailableBackends(enum.Enum):
+    """Backend selector carried by ``GemPyEngineConfig.backend``
+    (gempy/core/data/gempy_engine_config.py:11).  ``numpy`` / ``PYTORCH`` / ``legacy`` are the
+    reference's members (gempy/API/compute_API.py:42, test/test_api/test_backends.py:55);
+    ``B200`` is the member this backend adds."""
+    numpy = enum.auto()
+    PYTORCH = enum.auto()
+    legacy = enum.auto()
+    B200 = enum.auto()
+
+
+class AvailableKernelFunctions(enum.Enum):
+    cubic = 0
+    exponential = 1
+    matern_5_2 = 2
+
+
+class StackRelationType(enum.Enum):
+    """Encodings follow the serialization goldens (ERODE=1, FAULT=3;
+    test/test_modules/test_faults/*.verify/fault.approved.txt)."""
+    ERODE = 1
+    ONLAP = 2
+    FAULT = 3
+    BASEMENT = 4
+
+
+class BlockSolutionType(enum.Enum):
+    """RawArraysSolution.BlockSolutionType (gempy/core/data/geo_model.py:324-339)."""
+    NONE = 0
+    OCTREE = 1
+    DENSE_GRID = 2
+
+
+class MeshExtractionMaskingOptions(enum.Enum):
+    NOTHING = 1
+    DISJOINT = 2
+    INTERSECT = 3
+    RAW = 4
+
+
+# --------------------------------------------------------------------------- inputs
+@dataclass
+class SurfacePoints:
+    """_engine_factory.py:27-30."""
+    sp_coords: np.ndarray
+    nugget_effect_scalar: np.ndarray | float = 2e-5
+
+    def __post_init__(self):
+        self.sp_coords = np.ascontiguousarray(self.sp_coords, dtype=np.float64).reshape(-1, 3)
+        n = self.sp_coords.shape[0]
+        self.nugget_effect_scalar = np.broadcast_to(
+            np.asarray(self.nugget_effect_scalar, dtype=np.float64), (n,)).copy()
+
+    @property
+    def n_points(self) -> int:
+        return self.sp_coords.shape[0]
+
+
+@dataclass
+class Orientations:
+    """_engine_factory.py:33-37."""
+    dip_positions: np.ndarray
+    dip_gradients: np.ndarray
+    nugget_effect_grad: np.ndarray | float = 0.01
+
+    def __post_init__(self):
+        self.dip_positions = np.ascontiguousarray(self.dip_positions, dtype=np.float64).reshape(-1, 3)
+        self.dip_gradients = np.ascontiguousarray(self.dip_gradients, dtype=np.float64).reshape(-1, 3)
+        n = self.dip_positions.shape[0]
+        self.nugget_effect_grad = np.broadcast_to(
+            np.asarray(self.nugget_effect_grad, dtype=np.float64), (n,)).copy()
+
+    @property
+    def n_items(self) -> int:
+        return self.dip_positions.shape[0]
+
+
+@dataclass
+class RegularGrid:
+    """engine_grid.RegularGrid(orthogonal_extent, regular_grid_shape) (_engine_factory.py:72-75,93-96).
+
+    Cell centres, ``meshgrid(indexing='ij')`` order: x slowest, z fastest
+    (gempy/core/data/grid_modules/regular_grid.py:58-71,191-201).  ``values`` is generated lazily;
+    the CUDA path never needs it for a regular grid (coordinates come from the linear index)."""
+    orthogonal_extent: np.ndarray
+    regular_grid_shape: np.ndarray
+    _values: Optional[np.ndarray] = field(default=None, repr=False)   # explicit centres (octree levels > 0)
+    _dxdydz: Optional[np.ndarray] = field(default=None, repr=False)
+
+    def __post_init__(self):
+        self.orthogonal_extent = np.asarray(self.orthogonal_extent, dtype=np.float64).reshape(6)
+        self.regular_grid_shape = np.asarray(self.regular_grid_shape, dtype=np.int64).reshape(3)
+
+    @classmethod
+    def from_octree_level(cls, xyz_coords_octree: np.ndarray, previous_regular_grid: "RegularGrid",
+                          active_cells=None, left_right=None) -> "RegularGrid":
+        g = cls(previous_regular_grid.orthogonal_extent, previous_regular_grid.regular_grid_shape * 2)
+        g._values = np.ascontiguousarray(xyz_coords_octree, dtype=np.float64)
+        g._dxdydz = previous_regular_grid.dxdydz / 2.0
+        return g
+
+    @property
+    def is_implicit(self) -> bool:
+        return self._values is None
+
+    @property
+    def dxdydz(self) -> np.ndarray:
+        if self._dxdydz is not None:
+            return self._dxdydz
+        e, s = self.orthogonal_extent, self.regular_grid_shape
+        return np.array([(e[1] - e[0]) / s[0], (e[3] - e[2]) / s[1], (e[5] - e[4]) / s[2]])
+
+    @property
+    def resolution(self) -> np.ndarray:
+        return self.regular_grid_shape
+
+    def axis_coords(self):
+        e, s = self.orthogonal_extent, self.regular_grid_shape
+        d = self.dxdydz if self._dxdydz is None else np.array(
+            [(e[1] - e[0]) / s[0], (e[3] - e[2]) / s[1], (e[5] - e[4]) / s[2]])
+        return [np.linspace(e[2 * a] + d[a] / 2, e[2 * a + 1] - d[a] / 2, int(s[a]), dtype=np.float64)
+                for a in range(3)]
+
+    @property
+    def values(self) -> np.ndarray:
+        if self._values is None:
+            g = np.meshgrid(*self.axis_coords(), indexing="ij")
+            self._values = np.vstack([c.ravel() for c in g]).T.astype(np.float64)
+        return self._values
+
+    @property
+    def n_points(self) -> int:
+        if self._values is not None:
+            return self._values.shape[0]
+        return int(np.prod(self.regular_grid_shape))
+
+
+@dataclass
+class GenericGrid:
+    """engine_grid.GenericGrid(values) (_engine_factory.py:76-81)."""
+    values: np.ndarray
+
+    def __post_init__(self):
+        self.values = np.ascontiguousarray(self.values, dtype=np.float64).reshape(-1, 3)
+
+    @property
+    def n_points(self) -> int:
+        return self.values.shape[0]
+
+
+@dataclass
+class CenteredGrid:
+    """engine_grid.CenteredGrid(centers, radius, resolution) (_engine_factory.py:82-87).
+    Geophysics is outside this backend's scope; the class exists so the
+    bridge's constructor call succeeds and ``compute_model`` can reject it explicitly."""
+    centers: np.ndarray
+    radius: np.ndarray
+    resolution: np.ndarray
+
+
+@dataclass
+class EngineGrid:
+    """engine_grid.EngineGrid (_engine_factory.py:97-104).  Evaluation order of the point sets is
+    octree, dense, custom, topography, sections, (geophysics)."""
+    octree_grid: Optional[RegularGrid] = None
+    dense_grid: Optional[RegularGrid] = None
+    topography: Optional[GenericGrid] = None
+    sections: Optional[GenericGrid] = None
+    custom_grid: Optional[GenericGrid] = None
+    geophysics_grid: Optional[CenteredGrid] = None
+
+    _ORDER = ("octree_grid", "dense_grid", "custom_grid", "topography", "sections")
+
+    def parts(self):
+        """[(name, grid)] of the active point sets in evaluation order."""
+        return [(n, getattr(self, n)) for n in self._ORDER if getattr(self, n) is not None]
+
+    def _slice_of(self, name: str) -> slice:
+        start = 0
+        for n, g in self.parts():
+            if n == name:
+                return slice(start, start + g.n_points)
+            start += g.n_points
+        return slice(0, 0)
+
+    octree_grid_slice = property(lambda self: self._slice_of("octree_grid"))
+    dense_grid_slice = property(lambda self: self._slice_of("dense_grid"))
+    custom_grid_slice = property(lambda self: self._slice_of("custom_grid"))
+    topography_slice = property(lambda self: self._slice_of("topography"))
+    sections_slice = property(lambda self: self._slice_of("sections"))
+
+    @property
+    def len_all_grids(self) -> int:
+        return sum(g.n_points for _, g in self.parts())
+
+    @property
+    def values(self) -> np.ndarray:
+        return np.vstack([g.values for _, g in self.parts()]) if self.parts() else np.zeros((0, 3))
+
+    @classmethod
+    def from_xyz_coords(cls, xyz_coords: np.ndarray) -> "EngineGrid":
+        return cls(custom_grid=GenericGrid(xyz_coords))
+
+
+@dataclass
+class InterpolationInput:
+    """InterpolationInput(surface_points, orientations, grid, unit_values, weights)
+    (_engine_factory.py:50-56)."""
+    surface_points: SurfacePoints
+    orientations: Orientations
+    grid: EngineGrid
+    unit_values: Optional[np.ndarray] = None
+    weights: Optional[List[np.ndarray]] = None
+
+    def __post_init__(self):
+        if self.weights is None:
+            self.weights = []
+
+
+# --------------------------------------------------------------------------- descriptor
+@dataclass
+class FaultsData:
+    """Placeholder for finite-fault data (gempy/core/data/structural_group.py:32).  Finite faults
+    are a prototype in the reference (gempy/API/faults_API.py:84-91 raises NotImplementedError);
+    this backend rejects them."""
+    fault_values_everywhere: Optional[np.ndarray] = None
+    fault_values_on_sp: Optional[np.ndarray] = None
+    thickness: Optional[float] = None
+
+    @property
+    def finite_faults_defined(self) -> bool:
+        return self.thickness is not None
+
+
+@dataclass
+class TensorsStructure:
+    number_of_points_per_surface: np.ndarray
+
+    def __post_init__(self):
+        self.number_of_points_per_surface = np.asarray(self.number_of_points_per_surface, dtype=np.int64)
+
+    @property
+    def n_surfaces(self) -> int:
+        return int(self.number_of_points_per_surface.shape[0])
+
+    @property
+    def total_number_sp(self) -> int:
+        return int(self.number_of_points_per_surface.sum())
+
+    @property
+    def reference_sp_position(self) -> np.ndarray:
+        """Index of the reference point of every surface = its first point."""
+        n = self.number_of_points_per_surface
+        return np.concatenate([[0], np.cumsum(n)[:-1]]).astype(np.int64)
+
+
+@dataclass
+class StacksStructure:
+    number_of_points_per_stack: np.ndarray
+    number_of_orientations_per_stack: np.ndarray
+    number_of_surfaces_per_stack: np.ndarray
+    masking_descriptor: Sequence[StackRelationType]
+    faults_relations: Optional[np.ndarray] = None
+    faults_input_data: Optional[List[Optional[FaultsData]]] = None
+
+    def __post_init__(self):
+        self.number_of_points_per_stack = np.asarray(self.number_of_points_per_stack, dtype=np.int64)
+        self.number_of_orientations_per_stack = np.asarray(self.number_of_orientations_per_stack, dtype=np.int64)
+        self.number_of_surfaces_per_stack = np.asarray(self.number_of_surfaces_per_stack, dtype=np.int64)
+        if self.faults_relations is not None:
+            self.faults_relations = np.asarray(self.faults_relations, dtype=bool)
+
+    @property
+    def n_stacks(self) -> int:
+        return int(self.number_of_points_per_stack.shape[0])
+
+
+@dataclass
+class InputDataDescriptor:
+    """InputDataDescriptor.from_structural_frame(structural_frame, making_descriptor,
+    faults_relations, faults_input_data) (gempy/core/data/structural_frame.py:311-316)."""
+    tensors_structure: TensorsStructure
+    stack_structure: StacksStructure
+
+    @classmethod
+    def from_structural_frame(cls, structural_frame, making_descriptor, faults_relations,
+                              faults_input_data=None) -> "InputDataDescriptor":
+        # reads what gempy/core/data/structural_frame.py:333-350 exposes
+        ts = TensorsStructure(np.asarray(structural_frame.number_of_points_per_element))
+        ss = StacksStructure(
+            number_of_points_per_stack=structural_frame.number_of_points_per_group,
+            number_of_orientations_per_stack=structural_frame.number_of_orientations_per_group,
+            number_of_surfaces_per_stack=structural_frame.number_of_elements_per_group,
+            masking_descriptor=list(making_descriptor),
+            faults_relations=faults_relations,
+            faults_input_data=faults_input_data,
+        )
+        return cls(ts, ss)
+
+
+# --------------------------------------------------------------------------- options
+@dataclass
+class KernelOptions:
+    """Defaults pinned by the serialization golden
+    test/test_modules/test_serialize_model.test_generate_horizontal_stratigraphic_model.verify/
+    'Horizontal Stratigraphic Model serialization.approved.txt' (kernel_options block)."""
+    range: float = 1.7
+    c_o: float = 10.0
+    uni_degree: int = 1
+    i_res: float = 4.0
+    gi_res: float = 2.0
+    number_dimensions: int = 3
+    kernel_function: AvailableKernelFunctions = AvailableKernelFunctions.cubic
+    kernel_solver: int = 1                      # 1 = direct dense solve
+    compute_condition_number: bool = False
+    optimizing_condition_number: bool = False
+    condition_number: Optional[float] = None
+
+
+@dataclass
+class EvaluationOptions:
+    """Same golden, evaluation_options block."""
+    _number_octree_levels: int = 1
+    _number_octree_levels_surface: int = 4
+    octree_curvature_threshold: float = -1.0
+    octree_error_threshold: float = 1.0
+    octree_min_level: int = 2
+    mesh_extraction: bool = True
+    mesh_extraction_masking_options: MeshExtractionMaskingOptions = MeshExtractionMaskingOptions.INTERSECT
+    mesh_extraction_fancy: bool = True
+    evaluation_chunk_size: int = 500_000
+    compute_scalar_gradient: bool = False
+    verbose: bool = False
+
+    @property
+    def number_octree_levels(self) -> int:
+        return self._number_octree_levels
+
+    @number_octree_levels.setter
+    def number_octree_levels(self, v: int):
+        self._number_octree_levels = int(v)
+
+    @property
+    def number_octree_levels_surface(self) -> int:
+        return min(self._number_octree_levels_surface, self._number_octree_levels)
+
+    @number_octree_levels_surface.setter
+    def number_octree_levels_surface(self, v: int):
+        self._number_octree_levels_surface = int(v)
+
+
+@dataclass
+class InterpolationOptions:
+    kernel_options: KernelOptions = field(default_factory=KernelOptions)
+    evaluation_options: EvaluationOptions = field(default_factory=EvaluationOptions)
+    sigmoid_slope: float = 5_000_000.0
+    debug: bool = False
+    cache_mode: int = 3
+    cache_model_name: str = ""
+    block_solutions_type: BlockSolutionType = BlockSolutionType.OCTREE
+
+    # constructors the reference calls (gempy/API/initialization_API.py:81-83,
+    # gempy/modules/json_io/json_operations.py:158)
+    @classmethod
+    def from_args(cls, range: float = 1.7, c_o: float = 10.0, uni_degree: int = 1, i_res: float = 4.0,
+                  gi_res: float = 2.0, number_dimensions: int = 3, number_octree_levels: int = 1,
+                  kernel_function: AvailableKernelFunctions = AvailableKernelFunctions.cubic,
+                  mesh_extraction: bool = True, compute_scalar_gradient: bool = False,
+                  sigmoid_slope: float = 5_000_000.0) -> "InterpolationOptions":
+        ko = KernelOptions(range=range, c_o=c_o, uni_degree=uni_degree, i_res=i_res, gi_res=gi_res,
+                           number_dimensions=number_dimensions, kernel_function=kernel_function)
+        eo = EvaluationOptions(_number_octree_levels=number_octree_levels, mesh_extraction=mesh_extraction,
+                               compute_scalar_gradient=compute_scalar_gradient)
+        return cls(kernel_options=ko, evaluation_options=eo, sigmoid_slope=sigmoid_slope)
+
+    @classmethod
+    def init_octree_options(cls, range: float = 1.7, c_o: float = 10.0, refinement: int = 1) -> "InterpolationOptions":
+        return cls.from_args(range=range, c_o=c_o, number_octree_levels=refinement, mesh_extraction=True)
+
+    @classmethod
+    def init_dense_grid_options(cls) -> "InterpolationOptions":
+        o = cls.from_args(number_octree_levels=1, mesh_extraction=False)
+        o.block_solutions_type = BlockSolutionType.DENSE_GRID
+        return o
+
+    # shortcuts the reference's tests/examples touch
+    # (test_custom_grid.py:30, Alesmodel.py:107-145, Moureze.py:151-154)
+    @property
+    def number_octree_levels(self) -> int:
+        return self.evaluation_options.number_octree_levels
+
+    @number_octree_levels.setter
+    def number_octree_levels(self, v: int):
+        self.evaluation_options.number_octree_levels = v
+
+    @property
+    def number_octree_levels_surface(self) -> int:
+        return self.evaluation_options.number_octree_levels_surface
+
+    @number_octree_levels_surface.setter
+    def number_octree_levels_surface(self, v: int):
+        self.evaluation_options.number_octree_levels_surface = v
+
+    @property
+    def mesh_extraction(self) -> bool:
+        return self.evaluation_options.mesh_extraction
+
+    @mesh_extraction.setter
+    def mesh_extraction(self, v: bool):
+        self.evaluation_options.mesh_extraction = bool(v)
+
+    @property
+    def compute_scalar_gradient(self) -> bool:
+        return self.evaluation_options.compute_scalar_gradient
+
+    @compute_scalar_gradient.setter
+    def compute_scalar_gradient(self, v: bool):
+        self.evaluation_options.compute_scalar_gradient = bool(v)
+
+
+# --------------------------------------------------------------------------- transform
+@dataclass
+class Transform:
+    """Minimal input transform: ``x' = (x + position) * scale`` (rotation unsupported, always 0 in
+    the reference's models; gempy/core/data/geo_model.py:135-141,158-168,244-247).
+    The golden JSON pins HORIZONTAL_STRAT to position [-500]*3, scale 6.25e-4."""
+    position: np.ndarray
+    rotation: np.ndarray
+    scale: np.ndarray
+
+    @classmethod
+    def from_input_points(cls, surface_points_xyz: np.ndarray, orientations_xyz: np.ndarray) -> "Transform":
+        pts = np.concatenate([np.asarray(surface_points_xyz).reshape(-1, 3),
+                              np.asarray(orientations_xyz).reshape(-1, 3)], axis=0)
+        mx, mn = pts.max(axis=0), pts.min(axis=0)
+        scaling = 2.0 * np.max(mx - mn)
+        center = (mx + mn) / 2.0
+        f = 1.0 / scaling
+        return cls(position=-center, rotation=np.zeros(3), scale=np.array([f, f, f]))
+
+    def apply(self, points: np.ndarray) -> np.ndarray:
+        return (np.asarray(points, dtype=np.float64) + self.position) * self.scale
+
+    def apply_inverse(self, points: np.ndarray) -> np.ndarray:
+        return np.asarray(points, dtype=np.float64) / self.scale - self.position
+
+    def transform_gradient(self, gradients: np.ndarray) -> np.ndarray:
+        g = np.asarray(gradients, dtype=np.float64)
+        t = g / self.scale                      # inverse-transpose of diag(scale)
+        n0 = np.linalg.norm(g, axis=1)
+        n1 = np.linalg.norm(t, axis=1)
+        n1[n1 == 0] = 1.0
+        return t * (n0 / n1)[:, None]
+
+    def scale_points(self, points: np.ndarray) -> np.ndarray:
+        return np.asarray(points, dtype=np.float64) * self.scale
+
+
+# --------------------------------------------------------------------------- outputs
+@dataclass
+class ExportedFields:
+    """Scalar field (and optional gradient) on [all grid points ++ all surface points of the stack's
+    model]; the ``scalar_field`` view drops the surface-point tail
+    (test/test_model_types/test_example_models_I.py:20-21)."""
+    _scalar_field: np.ndarray
+    _gx_field: Optional[np.ndarray] = None
+    _gy_field: Optional[np.ndarray] = None
+    _gz_field: Optional[np.ndarray] = None
+    _grid_size: int = 0
+    _scalar_field_at_surface_points: Optional[np.ndarray] = None
+
+    @property
+    def scalar_field_everywhere(self) -> np.ndarray:
+        return self._scalar_field
+
+    @property
+    def scalar_field(self) -> np.ndarray:
+        return self._scalar_field[:self._grid_size]
+
+    @property
+    def gx_field(self):
+        return None if self._gx_field is None else self._gx_field[:self._grid_size]
+
+    @property
+    def gy_field(self):
+        return None if self._gy_field is None else self._gy_field[:self._grid_size]
+
+    @property
+    def gz_field(self):
+        return None if self._gz_field is None else self._gz_field[:self._grid_size]
+
+    @property
+    def scalar_field_at_surface_points(self) -> np.ndarray:
+        return self._scalar_field_at_surface_points
+
+
+@dataclass
+class ScalarFieldOutput:
+    weights: np.ndarray
+    grid: EngineGrid
+    exported_fields: ExportedFields
+    values_block: np.ndarray            # (1, n_xyz) activator output on grid ++ surface points
+    stack_relation: StackRelationType
+    mask_components: Optional[np.ndarray] = None
+
+    @property
+    def grid_size(self) -> int:
+        return self.exported_fields._grid_size
+
+
+@dataclass
+class CombinedScalarFieldsOutput:
+    squeezed_mask_array: np.ndarray     # (n_xyz,) bool: where this stack owns the final block
+    final_block: np.ndarray             # (n_xyz,) combined lith block (same for every stack)
+    faults_block: np.ndarray            # (n_xyz,) sum of fault blocks
+    final_exported_fields: Optional[ExportedFields] = None
+
+
+@dataclass
+class InterpOutput:
+    scalar_fields: ScalarFieldOutput
+    combined_scalar_field: Optional[CombinedScalarFieldsOutput] = None
+
+    @property
+    def weights(self):
+        return self.scalar_fields.weights
+
+    @property
+    def grid(self) -> EngineGrid:
+        return self.scalar_fields.grid
+
+    @property
+    def exported_fields(self) -> ExportedFields:
+        return self.scalar_fields.exported_fields
+
+    @property
+    def exported_fields_dense_grid(self) -> ExportedFields:
+        sl = self.grid.dense_grid_slice
+        ef = self.scalar_fields.exported_fields
+        pick = lambda a: None if a is None else a[sl]
+        return ExportedFields(pick(ef._scalar_field), pick(ef._gx_field), pick(ef._gy_field), pick(ef._gz_field),
+                              sl.stop - sl.start, ef._scalar_field_at_surface_points)
+
+    @property
+    def values_block(self) -> np.ndarray:
+        return self.scalar_fields.values_block[:, :self.scalar_fields.grid_size]
+
+    @property
+    def block(self) -> np.ndarray:
+        return self.combined_scalar_field.final_block[:self.scalar_fields.grid_size]
+
+    @property
+    def ids_block(self) -> np.ndarray:
+        return np.rint(self.block)
+
+    @property
+    def faults_block(self) -> np.ndarray:
+        return self.combined_scalar_field.faults_block[:self.scalar_fields.grid_size]
+
+    @property
+    def litho_faults_ids(self) -> np.ndarray:
+        lith = np.rint(self.block)
+        faults = np.rint(self.faults_block)
+        mult = max(int(len(np.unique(lith))), 1)
+        return lith + faults * mult
+
+
+@dataclass
+class OctreeLevel:
+    grid_centers: EngineGrid
+    outputs_centers: List[InterpOutput]
+    grid_corners: Optional[EngineGrid] = None
+    outputs_corners: Optional[List[InterpOutput]] = None
+    marked_voxels: Optional[np.ndarray] = None      # refine mask over this level's voxels
+
+    @property
+    def outputs(self) -> List[InterpOutput]:
+        return self.outputs_centers
+
+    @property
+    def last_output_center(self) -> InterpOutput:
+        return self.outputs_centers[-1]
+
+    @property
+    def number_of_outputs(self) -> int:
+        return len(self.outputs_centers)
+
+    @property
+    def dxdydz(self):
+        return self.grid_centers.octree_grid.dxdydz
+
+
+@dataclass
+class DualContouringData:
+    xyz_on_edge: np.ndarray
+    valid_edges: np.ndarray
+    gradients: Optional[np.ndarray] = None
+
+
+@dataclass
+class DualContouringMesh:
+    vertices: np.ndarray
+    edges: np.ndarray
+    dc_data: Optional[DualContouringData] = None
+
+    @property
+    def vertices_tensor(self):
+        return self.vertices
+
+
+class RawArraysSolution:
+    """Dense arrays GemPy users read after ``compute_model``:
+    lith_block, fault_block, litho_faults_block, scalar_field_matrix, block_matrix, mask_matrix,
+    mask_matrix_squeezed, custom, vertices, edges."""
+    BlockSolutionType = BlockSolutionType
+
+    def __init__(self):
+        self.lith_block = np.empty(0)
+        self.fault_block = np.empty(0)
+        self.litho_faults_block = np.empty(0)
+        self.scalar_field_matrix = np.empty((0, 0))
+        self.block_matrix = np.empty((0, 0))
+        self.mask_matrix = np.empty((0, 0))
+        self.mask_matrix_squeezed = np.empty((0, 0))
+        self.custom = None
+        self.topography = None
+        self.sections = None
+        self.dense_ids = None
+        self.vertices: list = []
+        self.edges: list = []
+
+
+class Solutions:
+    """What ``compute_model`` returns (gempy/API/compute_API.py:68-73) and
+    ``GeoModel.solutions`` consumes (gempy/core/data/geo_model.py:100-127)."""
+
+    def __init__(self, octrees_output: List[OctreeLevel], dc_meshes: Optional[List[DualContouringMesh]] = None,
+                 fw_gravity=None, block_solution_type: BlockSolutionType = BlockSolutionType.OCTREE):
+        self.octrees_output = octrees_output
+        self.dc_meshes = dc_meshes
+        self.gravity = fw_gravity
+        self.block_solution_type = block_solution_type
+        self.scalar_field_at_surface_points: List[float] = []
+        self._ordered_elements: List[np.ndarray] = []
+        for out in octrees_output[0].outputs_centers:
+            sfasp = out.exported_fields.scalar_field_at_surface_points
+            self.scalar_field_at_surface_points.extend(np.asarray(sfasp).tolist())
+            self._ordered_elements.append(np.argsort(sfasp)[::-1])
+        self.raw_arrays: Optional[RawArraysSolution] = None
+
+    @property
+    def root_output(self) -> OctreeLevel:
+        return self.octrees_output[0]
+
+    def meshes_to_unstruct(self):
+        raise NotImplementedError("subsurface export is outside the B200 backend's scope (SURVEY.md §2 row 13)")

@@ -1,0 +1,127 @@
+"""The oracle against the reference's own golden vectors and known answers (CPU only).
+
+Goldens: tests/golden/approved_scalar_fields.json, extracted by tests/golden/make_fixtures.py from
+/root/reference/test/test_model_types/*.approved.txt (test_example_models_I.py:19-88)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from gempy_b200 import examples as ex
+from oracle import gempy_oracle as orc
+
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "approved_scalar_fields.json")))
+
+
+def _verify_scalar_field(levels, with_corners):
+    """Restates _verify_scalar_field (test_example_models_I.py:19-23): stack 0 of the last octree level,
+    every len//50-th value.  When the last level is also the dual-contouring level the engine's array holds
+    centres ++ corners."""
+    last = levels[-1]
+    n1 = last.centers.shape[0]
+    z = last.fields.stacks[0].Z[:n1]
+    if with_corners:
+        z = np.concatenate([z, last.fields_corners.stacks[0].Z[:8 * n1]])
+    return z[::int(len(z) / 50)]
+
+
+@pytest.mark.parametrize("key,build,with_corners", [
+    ("anticline", ex.anticline, False),       # refinement 5, surface level 4 -> last level has no corners
+    ("fault", ex.one_fault, False),           # refinement 6
+    ("combination", ex.combination, True),    # refinement 4 == number_octree_levels_surface
+])
+def test_approved_scalar_fields(key, build, with_corners):
+    m = build()
+    ii, opt, desc = m.args()
+    opt.evaluation_options.mesh_extraction = with_corners
+    levels = orc.interpolate_n_octree_levels(ii, opt, desc)
+    got = _verify_scalar_field(levels, with_corners)
+    want = np.array(GOLD[key])
+    assert got.shape == want.shape == (51,)
+    # the reference's comparator is allclose(rtol=1e-5, atol=1e-5) (test/verify_helper.py:70-101);
+    # the approved file prints 8 significant digits, so 5e-8 is the tightest meaningful bound
+    np.testing.assert_allclose(got, want, rtol=0, atol=5e-8)
+
+
+def test_custom_grid_known_answer():
+    """test/test_modules/test_grids/test_custom_grid.py:24-47."""
+    xyz = np.array([[0, 0, 0], [1000, 0, 0], [0, 1000, 0], [1000, 1000, 0],
+                    [0, 0, 1000], [1000, 0, 1000], [0, 1000, 1000], [1000, 1000, 1000]], dtype=float)
+    m = ex.anticline(custom_xyz=xyz)
+    ii, opt, desc = m.args()
+    f = orc.interpolate_all_fields(ii, opt, desc, ii.grid.custom_grid.values)
+    np.testing.assert_array_equal(f.lith_ids, np.array([3., 3., 3., 3., 1., 1., 1., 1.]))
+
+
+def test_horizontal_plane_and_transform():
+    """Golden JSON pins the input transform of HORIZONTAL_STRAT (position -500, scale 6.25e-4); the kriged
+    field of two horizontal layers is the exact plane Z = gi_res * z'."""
+    m = ex.horizontal_strat()
+    np.testing.assert_allclose(m.transform.position, [-500, -500, -500])
+    np.testing.assert_allclose(m.transform.scale, [0.000625] * 3)
+    ii, opt, desc = m.args()
+    xyz = ii.grid.dense_grid.values
+    f = orc.interpolate_all_fields(ii, opt, desc, xyz, gradient=True)
+    st = f.stacks[0]
+    np.testing.assert_allclose(st.Z[:xyz.shape[0]], 2.0 * xyz[:, 2], atol=1e-12)
+    np.testing.assert_allclose(st.G[:xyz.shape[0]], np.tile([0, 0, 1.0], (xyz.shape[0], 1)), atol=1e-12)
+    ids, counts = np.unique(f.lith_ids, return_counts=True)
+    assert ids.tolist() == [1., 2., 3.] and counts.tolist() == [5000, 2500, 5000]
+
+
+def test_scalar_field_matrix_shape_contract():
+    """test/test_modules/test_outliers.py:51: (n_stacks, n_dense_points)."""
+    m = ex.combination()
+    ii, opt, desc = m.args()
+    c, _ = orc.regular_grid_centers(ii.grid.octree_grid.orthogonal_extent, [10, 5, 5])
+    f = orc.interpolate_all_fields(ii, opt, desc, c)
+    mat = np.stack([s.Z[:f.grid_size] for s in f.stacks])
+    assert mat.shape == (3, 250)
+
+
+def test_interpolant_honours_data():
+    """Mathematical self-check: Z(rest_i) = Z(ref_i) up to the nugget, gradient at the
+    orientations ~ G (engine gradient convention)."""
+    m = ex.synthetic_stress(n_sp_per_surface=40, n_surfaces=3, n_ori=30, resolution=(4, 4, 4))
+    ii, opt, desc = m.args()
+    f = orc.interpolate_all_fields(ii, opt, desc, ii.orientations.dip_positions, gradient=True)
+    st = f.stacks[0]
+    n_o = ii.orientations.n_items
+    zsp = st.Z[n_o:]
+    starts = desc.tensors_structure.reference_sp_position
+    n = desc.tensors_structure.number_of_points_per_surface
+    for s0, k in zip(starts, n):
+        assert np.abs(zsp[s0:s0 + k] - zsp[s0]).max() < 5e-3
+    g = st.G[:n_o]
+    assert np.abs(g - ii.orientations.dip_gradients).max() < 5e-2
+
+
+def test_gradient_matches_finite_difference():
+    """Engine-convention gradient = (1/gi_res) dZ/dx away from the data (regulariser negligible there)."""
+    m = ex.anticline()
+    ii, opt, desc = m.args()
+    rng = np.random.default_rng(0)
+    x = rng.uniform(-0.2, 0.2, size=(20, 3))
+    h = 1e-6
+    f0 = orc.interpolate_all_fields(ii, opt, desc, x, gradient=True).stacks[0]
+    for a in range(3):
+        dx = np.zeros(3); dx[a] = h
+        zp = orc.interpolate_all_fields(ii, opt, desc, x + dx).stacks[0].Z[:20]
+        zm = orc.interpolate_all_fields(ii, opt, desc, x - dx).stacks[0].Z[:20]
+        fd = (zp - zm) / (2 * h) / opt.kernel_options.gi_res
+        np.testing.assert_allclose(f0.G[:20, a], fd, rtol=2e-3, atol=2e-3)
+
+
+def test_dual_contouring_vertices_near_surface():
+    m = ex.anticline(refinement=4)
+    ii, opt, desc = m.args()
+    sol = orc.compute_model(ii, opt, desc)
+    assert sol.meshes is not None and len(sol.meshes) == 2
+    for mesh in sol.meshes:
+        assert mesh.vertices.shape[0] > 50 and mesh.edges.shape[0] > 50
+        f = orc.interpolate_all_fields(ii, opt, desc, mesh.vertices)
+        z = f.stacks[0].Z[:mesh.vertices.shape[0]]
+        iso = f.stacks[0].isovalues[mesh.surface]
+        assert np.abs(z - iso).max() < 0.03        # vertices sit on the isosurface to a fraction of a voxel
+        assert mesh.edges.max() < mesh.vertices.shape[0]
