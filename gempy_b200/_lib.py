@@ -1,0 +1,102 @@
+"""ctypes binding of libgempy_b200.so (the C ABI declared in include/gempy_b200.h).
+
+There is no CPU fallback: if the shared library is missing or fails to load, importing this module's
+``lib()`` raises.  The library is built in-tree by ``gempy_b200/csrc/build.py`` (``__graft_entry__.build()``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgempy_b200.so")
+
+GPB_KERNEL = {"cubic": 0, "exponential": 1, "matern_5_2": 2}
+
+c_double_p = C.c_void_p   # device pointers travel as integers
+c_int_p = C.c_void_p
+
+
+class GpbStack(C.Structure):
+    _fields_ = [
+        ("n_ori", C.c_int), ("n_rest", C.c_int), ("n_surf", C.c_int), ("n_drift", C.c_int),
+        ("n_faults", C.c_int), ("kernel", C.c_int),
+        ("range", C.c_double), ("c_o", C.c_double), ("i_res", C.c_double), ("gi_res", C.c_double),
+        ("ori_pos", C.c_void_p), ("ori_grad", C.c_void_p), ("ori_nugget", C.c_void_p),
+        ("rest", C.c_void_p), ("ref", C.c_void_p), ("sp_nugget", C.c_void_p),
+        ("fault_rest", C.c_void_p), ("fault_ref", C.c_void_p),
+        ("surf_offsets", C.c_void_p), ("ref_unique", C.c_void_p),
+    ]
+
+
+class GpbRegularGrid(C.Structure):
+    _fields_ = [
+        ("x0", C.c_double), ("y0", C.c_double), ("z0", C.c_double),
+        ("dx", C.c_double), ("dy", C.c_double), ("dz", C.c_double),
+        ("nx", C.c_int), ("ny", C.c_int), ("nz", C.c_int),
+    ]
+
+
+# name -> (restype, argtypes); every symbol include/gempy_b200.h declares
+_LL = C.c_longlong
+_P = C.c_void_p
+SIGNATURES = {
+    "gpb_last_error": (C.c_char_p, []),
+    "gpb_version": (C.c_int, []),
+    "gpb_device_info": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "gpb_launch_count": (_LL, []),
+    "gpb_bench_dfma": (C.c_int, [C.c_int, C.POINTER(C.c_double), _P]),
+    "gpb_system_size": (C.c_int, [C.POINTER(GpbStack)]),
+    "gpb_assemble_cov": (C.c_int, [C.POINTER(GpbStack), _P, C.c_int, _P, _P]),
+    "gpb_lu_solve": (C.c_int, [C.c_int, _P, C.c_int, _P, C.c_int, C.c_int, _P, _P, _P]),
+    "gpb_lu_factor": (C.c_int, [C.c_int, _P, C.c_int, _P, _P, _P]),
+    "gpb_lu_apply": (C.c_int, [C.c_int, _P, C.c_int, _P, _P, C.c_int, C.c_int, _P]),
+    "gpb_eval_table_doubles": (_LL, [C.POINTER(GpbStack)]),
+    "gpb_pack_eval_table": (C.c_int, [C.POINTER(GpbStack), _P, _P, _P]),
+    "gpb_eval_regular": (C.c_int, [C.POINTER(GpbStack), _P, C.POINTER(GpbRegularGrid), _LL, _LL, _P, _LL,
+                                   _P, _P, _P, _P, _P]),
+    "gpb_eval_points": (C.c_int, [C.POINTER(GpbStack), _P, _P, _LL, _LL, _P, _LL, _P, _P, _P, _P, _P]),
+    "gpb_activate": (C.c_int, [_P, _LL, _P, _P, C.c_int, C.c_double, _P, _P]),
+    "gpb_min": (C.c_int, [_P, _LL, _P, _P]),
+    "gpb_shift": (C.c_int, [_P, _LL, _P, _P, _P]),
+    "gpb_combine": (C.c_int, [_P, _P, _LL, _LL, C.c_int, C.POINTER(C.c_int), _P, _P, _P, _P, _P, _P, _P]),
+    "gpb_voxel_corners": (C.c_int, [_P, _LL, _LL, C.c_double, C.c_double, C.c_double, _P, _LL, _P]),
+    "gpb_mark_voxels": (C.c_int, [_P, _P, _LL, C.c_int, _P, _P]),
+    "gpb_emit_children": (C.c_int, [_P, _LL, _LL, _P, C.c_double, C.c_double, C.c_double, _P, _LL,
+                                    C.POINTER(_LL), _P]),
+    "gpb_any8": (C.c_int, [_P, _LL, _P, _P]),
+    "gpb_dc_edges": (C.c_int, [_P, _LL, _P, _LL, C.c_double, _P, _P, _P, _P]),
+    "gpb_dc_vertices": (C.c_int, [_P, _P, _P, _LL, C.c_double, _P, _P]),
+}
+
+_lib = None
+
+
+class GpbError(RuntimeError):
+    pass
+
+
+def lib() -> C.CDLL:
+    """Load (once) and return the library.  Raises if it was not built -- no fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise GpbError(f"{LIB_PATH} not found: build it with `python gempy_b200/csrc/build.py` "
+                           "(__graft_entry__.build()); the B200 backend has no CPU fallback")
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)          # AttributeError if the .so lacks a declared symbol
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        msg = lib().gpb_last_error().decode("utf-8", "replace")
+        raise GpbError(f"gempy_b200 error {rc}: {msg}")
+
+
+def launch_count() -> int:
+    return int(lib().gpb_launch_count())

@@ -1,0 +1,108 @@
+// Shared helpers of the gempy_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdint>
+#include "../../include/gempy_b200.h"
+
+// Numerical constants pinned by the reference's approved vectors (see oracle/gempy_oracle.py header).
+#define GPB_REG_EPS  1e-5     // h_u h_v / (r^2 + 1e-5)
+#define GPB_DIST_EPS 1e-10    // r = sqrt(|h|^2 + 1e-10)
+
+extern thread_local char g_gpb_error[512];
+extern long long g_gpb_launches;
+
+int gpb_set_error(int code, const char* fmt, ...);
+
+#define GPB_CHECK_CUDA(expr)                                                                       \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess)                                                                     \
+            return gpb_set_error(GPB_E_CUDA, "%s failed at %s:%d: %s", #expr, __FILE__, __LINE__,  \
+                                 cudaGetErrorString(_e));                                          \
+    } while (0)
+
+#define GPB_LAUNCH_CHECK()                                                                         \
+    do {                                                                                           \
+        ++g_gpb_launches;                                                                          \
+        cudaError_t _e = cudaGetLastError();                                                       \
+        if (_e != cudaSuccess)                                                                     \
+            return gpb_set_error(GPB_E_CUDA, "kernel launch failed at %s:%d: %s", __FILE__,        \
+                                 __LINE__, cudaGetErrorString(_e));                                \
+    } while (0)
+
+#define GPB_REQUIRE(cond, msg)                                                                     \
+    do {                                                                                           \
+        if (!(cond)) return gpb_set_error(GPB_E_INVALID, "%s (%s:%d)", msg, __FILE__, __LINE__);   \
+    } while (0)
+
+static inline long long gpb_round_up(long long v, long long m) { return (v + m - 1) / m * m; }
+
+int gpb_sm_count();
+
+// ---- fast FP64 primitives -------------------------------------------------------------------------
+// MUFU seeds (2^-22) + one third-order correction: error ~ e^3 ~ 1e-20 relative before rounding,
+// with no divergent slow path (arguments are strictly positive, normal numbers on this path).
+__device__ __forceinline__ double gpb_rsqrt_seed(double u) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(u));
+    return y;
+}
+__device__ __forceinline__ double gpb_rcp_seed(double d) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+    return y;
+}
+// sqrt(u), u > 0
+__device__ __forceinline__ double gpb_fast_sqrt(double u) {
+    const double y0 = gpb_rsqrt_seed(u);
+    const double g0 = u * y0;
+    const double e = fma(-g0, y0, 1.0);
+    const double p = fma(0.375, e, 0.5);
+    return fma(g0 * e, p, g0);
+}
+// 1/d, d > 0
+__device__ __forceinline__ double gpb_fast_rcp(double d) {
+    const double y0 = gpb_rcp_seed(d);
+    const double e = fma(-d, y0, 1.0);
+    const double p = fma(e, e, e);
+    return fma(y0, p, y0);
+}
+
+// ---- mbarrier / bulk-copy (TMA) helpers -------------------------------------------------------------
+__device__ __forceinline__ uint32_t gpb_smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void gpb_mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(gpb_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void gpb_fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void gpb_fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void gpb_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(gpb_smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void gpb_mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(gpb_smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP).
+__device__ __forceinline__ void gpb_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     gpb_smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(gpb_smem_u32(bar))
+                 : "memory");
+}

@@ -1,0 +1,429 @@
+// (3) Fused on-the-fly kernel-times-weights evaluation of the scalar field and its gradient.
+//
+// Engine stage replaced: "evaluator" + the evaluation kernels of "kernel_constructor" (SURVEY.md 8a2 row 3),
+// reached from gempy_engine.compute_model (/root/reference/gempy/API/compute_API.py:68-73).  The reference
+// design materialises an (n_data x chunk) kernel matrix per chunk (evaluation_chunk_size = 500000 elements,
+// test/test_modules/test_serialize_model.*.verify/*.approved.txt) and multiplies it by the weights; here the
+// kernel matrix never exists: every CTA streams the packed data-point table through shared memory with 1-D
+// TMA bulk copies (cp.async.bulk + mbarrier, double buffered) and every thread keeps P grid points and their
+// four accumulators (Z, dZ/dx, dZ/dy, dZ/dz) in registers.
+//
+// Roofline: FP64 pipe (DFMA).  Per (point, surface-point source): 23 FP64-pipe instructions + 1 MUFU;
+// per (point, orientation): 33 + 2 MUFU (cubic kernel).  HBM traffic is the output only (32 B / point).
+//
+// Packed table (built by gpb_pack_eval_table), all coordinates divided by the range a:
+//   [ n_sps_pad x {X, Y, Z, W} ]   W = c_o*i_res*w_i for rest points, -c_o*i_res*sum(w) for each reference point
+//   [ n_ori_pad x {X, Y, Z, w'x, w'y, w'z} ]   w' = -(c_o*gi_res/a) * w
+//   [ tail: mu_z[9] (drift, field), mu_g[9] (drift, gradient), scal[6], w_fault[n_faults] ]
+#include "gpb_common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kTileSp = 256;                  // sources per tile: 256 * 32 B = 8 KB
+constexpr int kTileOri = 128;                 // 128 * 48 B = 6 KB
+constexpr int kTileBytes = kTileSp * 32;      // stage buffer size
+constexpr int kTailDoubles = 24;              // mu_z[9] mu_g[9] scal[6]
+
+struct EvalParams {
+    const double* src;       // packed table
+    long long n_sps_pad;
+    long long n_ori_pad;
+    int n_drift;
+    int n_faults;
+    // points
+    gpb_regular_grid grid;   // REGULAR
+    const double* xyz;       // !REGULAR: [3][ld_xyz]
+    long long ld_xyz;
+    long long i0;            // first global index (REGULAR)
+    long long m;             // number of points
+    const double* fault_vals;
+    long long ld_fault;
+    double* Z;
+    double* gx;
+    double* gy;
+    double* gz;
+    double inv_a;
+    double eps_u;            // DIST_EPS / a^2
+    double eps_reg;          // REG_EPS / a^2
+};
+
+// ---- covariance terms in range-normalised units (t = r/a, u = t^2) ------------------------------------
+//   cval : C(r) (cubic: C - 1, the constant cancels because the source weights sum to zero)
+//   kp   : a^2 * C'(r)/r
+//   dd   : a^2 * (C'(r)/r - C''(r))          (numerator of the regularised gradient-gradient term)
+template <int KERNEL>
+__device__ __forceinline__ void cov_sp(double u, double t, double& c, double& kp) {
+    if constexpr (KERNEL == GPB_KERNEL_CUBIC) {
+        // C - 1 = u * (-7 + t * (35/4 + u * (-7/2 + 3/4 u)));  kp = -14 + t * (105/4 + u * (-35/2 + 21/4 u))
+        const double P = fma(u, fma(0.75, u, -3.5), 8.75);
+        const double Q = fma(u, fma(5.25, u, -17.5), 26.25);
+        c = u * fma(t, P, -7.0);
+        kp = fma(t, Q, -14.0);
+    } else if constexpr (KERNEL == GPB_KERNEL_EXPONENTIAL) {
+        const double e = exp(-0.5 * u);
+        c = e;
+        kp = -e;
+    } else {
+        const double s = 2.23606797749978969641 * t;
+        const double e = exp(-s);
+        c = fma(s, fma(s, 1.0 / 3.0, 1.0), 1.0) * e;
+        kp = (-5.0 / 3.0) * (1.0 + s) * e;
+    }
+}
+
+template <int KERNEL>
+__device__ __forceinline__ void cov_ori(double u, double t, double& kp, double& dd) {
+    if constexpr (KERNEL == GPB_KERNEL_CUBIC) {
+        const double Q = fma(u, fma(5.25, u, -17.5), 26.25);
+        kp = fma(t, Q, -14.0);
+        // dd = -(105/4) t (1-u)^2, written as -(s - s u)^2 t with s = sqrt(105/4)
+        const double om = fma(-5.12347538297979853, u, 5.12347538297979853);
+        dd = -(om * om) * t;
+    } else if constexpr (KERNEL == GPB_KERNEL_EXPONENTIAL) {
+        const double e = exp(-0.5 * u);
+        kp = -e;
+        dd = -e * u;
+    } else {
+        const double s = 2.23606797749978969641 * t;
+        const double e = exp(-s);
+        kp = (-5.0 / 3.0) * (1.0 + s) * e;
+        dd = (-5.0 / 3.0) * e * s * s;
+    }
+}
+
+template <int KERNEL, bool GRAD, bool REGULAR, int P>
+__global__ void __launch_bounds__(kThreads, (P <= 2) ? 2 : 1)
+eval_kernel(const EvalParams prm) {
+    __shared__ __align__(128) double stage[2][kTileBytes / 8];
+    __shared__ __align__(8) uint64_t full[2];
+
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        gpb_mbar_init(&full[0], 1);
+        gpb_mbar_init(&full[1], 1);
+        gpb_fence_mbar_init();
+    }
+    __syncthreads();
+
+    const long long n_sp_tiles = prm.n_sps_pad / kTileSp;
+    const long long n_ori_tiles = prm.n_ori_pad / kTileOri;
+    const long long n_tiles = n_sp_tiles + n_ori_tiles;
+    const double* src_ori = prm.src + 4 * prm.n_sps_pad;
+    const double* tail = src_ori + 6 * prm.n_ori_pad;
+
+    const long long chunk = (long long)kThreads * P;
+    const long long n_chunks = (prm.m + chunk - 1) / chunk;
+    unsigned long long gt = 0;   // global tile counter of this CTA (buffer = gt & 1, parity = (gt >> 1) & 1)
+
+    auto issue = [&](long long j, unsigned long long g) {
+        // thread 0 only
+        const int b = (int)(g & 1);
+        if (j < n_sp_tiles) {
+            gpb_mbar_expect_tx(&full[b], kTileSp * 32);
+            gpb_bulk_g2s(stage[b], prm.src + 4 * (long long)kTileSp * j, kTileSp * 32, &full[b]);
+        } else {
+            gpb_mbar_expect_tx(&full[b], kTileOri * 48);
+            gpb_bulk_g2s(stage[b], src_ori + 6 * (long long)kTileOri * (j - n_sp_tiles), kTileOri * 48, &full[b]);
+        }
+    };
+
+    for (long long c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+        // ---- this thread's P points -------------------------------------------------------------------
+        double X[P], Y[P], Zc[P];
+        double accZ[P], hx[P], hy[P], hz[P];
+        long long idx[P];
+#pragma unroll
+        for (int k = 0; k < P; ++k) {
+            idx[k] = c * chunk + (long long)k * kThreads + tid;
+            const long long i = idx[k] < prm.m ? idx[k] : prm.m - 1;     // clamp: tail threads recompute the last point
+            double x, y, z;
+            if constexpr (REGULAR) {
+                const long long gi = prm.i0 + i;
+                const long long nyz = (long long)prm.grid.ny * prm.grid.nz;
+                const long long ix = gi / nyz;
+                const long long rem = gi - ix * nyz;
+                const long long iy = rem / prm.grid.nz;
+                const long long iz = rem - iy * prm.grid.nz;
+                x = fma((double)ix, prm.grid.dx, prm.grid.x0);
+                y = fma((double)iy, prm.grid.dy, prm.grid.y0);
+                z = fma((double)iz, prm.grid.dz, prm.grid.z0);
+            } else {
+                x = prm.xyz[i];
+                y = prm.xyz[prm.ld_xyz + i];
+                z = prm.xyz[2 * prm.ld_xyz + i];
+            }
+            X[k] = x * prm.inv_a;
+            Y[k] = y * prm.inv_a;
+            Zc[k] = z * prm.inv_a;
+            accZ[k] = 0.0; hx[k] = 0.0; hy[k] = 0.0; hz[k] = 0.0;
+        }
+
+        if (tid == 0 && n_tiles > 0) issue(0, gt);
+
+        for (long long j = 0; j < n_tiles; ++j, ++gt) {
+            if (tid == 0 && j + 1 < n_tiles) issue(j + 1, gt + 1);
+            const int b = (int)(gt & 1);
+            gpb_mbar_wait(&full[b], (uint32_t)((gt >> 1) & 1));
+            const double* s = stage[b];
+
+            if (j < n_sp_tiles) {
+                // ---- surface-point sources: {X, Y, Z, W} -----------------------------------------------
+#pragma unroll 2
+                for (int q = 0; q < kTileSp; ++q) {
+                    const double2 a0 = *reinterpret_cast<const double2*>(s + 4 * q);
+                    const double2 a1 = *reinterpret_cast<const double2*>(s + 4 * q + 2);
+#pragma unroll
+                    for (int k = 0; k < P; ++k) {
+                        const double dx = X[k] - a0.x, dy = Y[k] - a0.y, dz = Zc[k] - a1.x;
+                        const double u = fma(dz, dz, fma(dy, dy, fma(dx, dx, prm.eps_u)));
+                        const double t = gpb_fast_sqrt(u);
+                        double cv, kp;
+                        cov_sp<KERNEL>(u, t, cv, kp);
+                        accZ[k] = fma(a1.y, cv, accZ[k]);
+                        if constexpr (GRAD) {
+                            const double g = a1.y * kp;
+                            hx[k] = fma(g, dx, hx[k]);
+                            hy[k] = fma(g, dy, hy[k]);
+                            hz[k] = fma(g, dz, hz[k]);
+                        }
+                    }
+                }
+                if (j == n_sp_tiles - 1) {
+                    if constexpr (GRAD) {
+                        const double r = tail[18];       // gi^2 / i_res : surface-point part into H units
+#pragma unroll
+                        for (int k = 0; k < P; ++k) { hx[k] *= r; hy[k] *= r; hz[k] *= r; }
+                    }
+                }
+            } else {
+                // ---- orientation sources: {X, Y, Z, w'x, w'y, w'z} -------------------------------------
+#pragma unroll 2
+                for (int q = 0; q < kTileOri; ++q) {
+                    const double2 a0 = *reinterpret_cast<const double2*>(s + 6 * q);
+                    const double2 a1 = *reinterpret_cast<const double2*>(s + 6 * q + 2);
+                    const double2 a2 = *reinterpret_cast<const double2*>(s + 6 * q + 4);
+#pragma unroll
+                    for (int k = 0; k < P; ++k) {
+                        const double dx = X[k] - a0.x, dy = Y[k] - a0.y, dz = Zc[k] - a1.x;
+                        const double u = fma(dz, dz, fma(dy, dy, fma(dx, dx, prm.eps_u)));
+                        const double t = gpb_fast_sqrt(u);
+                        double kp, dd;
+                        cov_ori<KERNEL>(u, t, kp, dd);
+                        const double hw = fma(dz, a2.y, fma(dy, a2.x, dx * a1.y));
+                        accZ[k] = fma(kp, hw, accZ[k]);
+                        if constexpr (GRAD) {
+                            const double c1 = -(dd * gpb_fast_rcp(u + prm.eps_reg)) * hw;
+                            hx[k] = fma(c1, dx, fma(kp, a1.y, hx[k]));
+                            hy[k] = fma(c1, dy, fma(kp, a2.x, hy[k]));
+                            hz[k] = fma(c1, dz, fma(kp, a2.y, hz[k]));
+                        }
+                    }
+                }
+            }
+            __syncthreads();     // everyone is done with stage[b] before thread 0 refills it
+        }
+
+        // ---- drift, faults, store -------------------------------------------------------------------------
+        const double inv_agi = tail[19];        // 1 / (a * gi)
+#pragma unroll
+        for (int k = 0; k < P; ++k) {
+            if (idx[k] >= prm.m) continue;
+            double z = accZ[k];
+            double g0 = hx[k] * inv_agi, g1 = hy[k] * inv_agi, g2 = hz[k] * inv_agi;
+            if (prm.n_drift >= 3) {
+                z = fma(tail[0], X[k], fma(tail[1], Y[k], fma(tail[2], Zc[k], z)));
+                if constexpr (GRAD) { g0 += tail[9]; g1 += tail[10]; g2 += tail[11]; }
+            }
+            if (prm.n_drift == 9) {
+                z = fma(tail[3], X[k] * X[k], fma(tail[4], Y[k] * Y[k], fma(tail[5], Zc[k] * Zc[k], z)));
+                z = fma(tail[6], X[k] * Y[k], fma(tail[7], X[k] * Zc[k], fma(tail[8], Y[k] * Zc[k], z)));
+                if constexpr (GRAD) {
+                    g0 += 2.0 * tail[12] * X[k] + tail[15] * Y[k] + tail[16] * Zc[k];
+                    g1 += 2.0 * tail[13] * Y[k] + tail[15] * X[k] + tail[17] * Zc[k];
+                    g2 += 2.0 * tail[14] * Zc[k] + tail[16] * X[k] + tail[17] * Y[k];
+                }
+            }
+            for (int f = 0; f < prm.n_faults; ++f)
+                z = fma(tail[kTailDoubles + f], prm.fault_vals[(long long)f * prm.ld_fault + idx[k]], z);
+            prm.Z[idx[k]] = z;
+            if constexpr (GRAD) {
+                prm.gx[idx[k]] = g0;
+                prm.gy[idx[k]] = g1;
+                prm.gz[idx[k]] = g2;
+            }
+        }
+    }
+}
+
+// ---- packing ----------------------------------------------------------------------------------------------
+struct PackParams {
+    gpb_stack st;
+    const double* w;
+    double* src;
+    long long n_sps_pad, n_ori_pad;
+};
+
+__global__ void pack_kernel(const PackParams p) {
+    const gpb_stack& st = p.st;
+    const double inv_a = 1.0 / st.range;
+    const double cI = st.c_o * st.i_res;
+    const double cG = -(st.c_o * st.gi_res) * inv_a;
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const double* w_g = p.w;
+    const double* w_i = p.w + 3LL * st.n_ori;
+    const double* mu = w_i + st.n_rest;
+    const double* w_f = mu + st.n_drift;
+    const long long n_sps = (long long)st.n_rest + st.n_surf;
+    // surface-point sources
+    for (long long i = tid; i < p.n_sps_pad; i += stride) {
+        double x = 0, y = 0, z = 0, W = 0;
+        if (i < st.n_rest) {
+            x = st.rest[i]; y = st.rest[st.n_rest + i]; z = st.rest[2LL * st.n_rest + i];
+            W = cI * w_i[i];
+        } else if (i < n_sps) {
+            const int s = (int)(i - st.n_rest);
+            x = st.ref_unique[s]; y = st.ref_unique[st.n_surf + s]; z = st.ref_unique[2 * st.n_surf + s];
+            double acc = 0.0;                       // sequential sum: deterministic
+            for (int r = st.surf_offsets[s]; r < st.surf_offsets[s + 1]; ++r) acc += w_i[r];
+            W = -cI * acc;
+        }
+        double* o = p.src + 4 * i;
+        o[0] = x * inv_a; o[1] = y * inv_a; o[2] = z * inv_a; o[3] = W;
+    }
+    // orientation sources
+    double* so = p.src + 4 * p.n_sps_pad;
+    for (long long i = tid; i < p.n_ori_pad; i += stride) {
+        double v[6] = {0, 0, 0, 0, 0, 0};
+        if (i < st.n_ori) {
+            v[0] = st.ori_pos[i] * inv_a; v[1] = st.ori_pos[st.n_ori + i] * inv_a; v[2] = st.ori_pos[2LL * st.n_ori + i] * inv_a;
+            v[3] = cG * w_g[i]; v[4] = cG * w_g[st.n_ori + i]; v[5] = cG * w_g[2LL * st.n_ori + i];
+        }
+        for (int k = 0; k < 6; ++k) so[6 * i + k] = v[k];
+    }
+    // tail
+    double* tl = so + 6 * p.n_ori_pad;
+    if (tid == 0) {
+        const double a = st.range;
+        for (int k = 0; k < kTailDoubles; ++k) tl[k] = 0.0;
+        for (int k = 0; k < st.n_drift; ++k) {
+            const double m = mu[k];
+            // field: gi * mu_k f_k(x), x = a X  ->  linear terms * a, quadratic * a^2
+            tl[k] = st.gi_res * m * (k < 3 ? a : a * a);
+            // gradient: mu_k d f_k / d x   (linear: mu; quadratic: coefficient of X is mu * a)
+            tl[9 + k] = (k < 3) ? m : m * a;
+        }
+        tl[18] = st.gi_res * st.gi_res / st.i_res;
+        tl[19] = 1.0 / (a * st.gi_res);
+        for (int f = 0; f < st.n_faults; ++f) tl[kTailDoubles + f] = w_f[f];
+    }
+}
+
+template <int KERNEL, bool GRAD, bool REGULAR>
+int launch_eval(const EvalParams& prm, cudaStream_t stream) {
+    constexpr int P = GRAD ? 4 : 4;
+    const long long chunk = (long long)kThreads * P;
+    const long long n_chunks = (prm.m + chunk - 1) / chunk;
+    if (n_chunks == 0) return GPB_OK;
+    int occ = 1;
+    GPB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, eval_kernel<KERNEL, GRAD, REGULAR, P>, kThreads, 0));
+    if (occ < 1) occ = 1;
+    long long grid = (long long)gpb_sm_count() * occ;
+    if (grid > n_chunks) grid = n_chunks;
+    eval_kernel<KERNEL, GRAD, REGULAR, P><<<(unsigned)grid, kThreads, 0, stream>>>(prm);
+    GPB_LAUNCH_CHECK();
+    return GPB_OK;
+}
+
+template <bool REGULAR>
+int dispatch_eval(int kernel, bool grad, const EvalParams& prm, cudaStream_t stream) {
+#define GPB_CASE(K)                                                         \
+    case K:                                                                 \
+        return grad ? launch_eval<K, true, REGULAR>(prm, stream) : launch_eval<K, false, REGULAR>(prm, stream);
+    switch (kernel) {
+        GPB_CASE(GPB_KERNEL_CUBIC)
+        GPB_CASE(GPB_KERNEL_EXPONENTIAL)
+        GPB_CASE(GPB_KERNEL_MATERN52)
+        default: return gpb_set_error(GPB_E_INVALID, "unknown kernel function %d", kernel);
+    }
+#undef GPB_CASE
+}
+
+int fill_common(const gpb_stack* st, const double* src, EvalParams& prm) {
+    GPB_REQUIRE(st != nullptr && src != nullptr, "null stack or table");
+    GPB_REQUIRE(st->range > 0, "range must be positive");
+    prm.src = src;
+    prm.n_sps_pad = gpb_round_up((long long)st->n_rest + st->n_surf, kTileSp);
+    prm.n_ori_pad = gpb_round_up(st->n_ori, kTileOri);
+    prm.n_drift = st->n_drift;
+    prm.n_faults = st->n_faults;
+    prm.inv_a = 1.0 / st->range;
+    prm.eps_u = GPB_DIST_EPS / (st->range * st->range);
+    prm.eps_reg = GPB_REG_EPS / (st->range * st->range);
+    return GPB_OK;
+}
+
+}  // namespace
+
+extern "C" long long gpb_eval_table_doubles(const gpb_stack* st) {
+    if (!st) return 0;
+    return 4 * gpb_round_up((long long)st->n_rest + st->n_surf, kTileSp) + 6 * gpb_round_up(st->n_ori, kTileOri) +
+           kTailDoubles + st->n_faults + 8;
+}
+
+extern "C" int gpb_pack_eval_table(const gpb_stack* st, const double* w, double* src, void* stream) {
+    GPB_REQUIRE(st && w && src, "null argument");
+    GPB_REQUIRE(st->n_drift == 0 || st->n_drift == 3 || st->n_drift == 9, "n_drift must be 0, 3 or 9");
+    PackParams p;
+    p.st = *st;
+    p.w = w;
+    p.src = src;
+    p.n_sps_pad = gpb_round_up((long long)st->n_rest + st->n_surf, kTileSp);
+    p.n_ori_pad = gpb_round_up(st->n_ori, kTileOri);
+    const long long work = p.n_sps_pad > p.n_ori_pad ? p.n_sps_pad : p.n_ori_pad;
+    int blocks = (int)((work + 127) / 128);
+    if (blocks < 1) blocks = 1;
+    pack_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(p);
+    GPB_LAUNCH_CHECK();
+    return GPB_OK;
+}
+
+extern "C" int gpb_eval_regular(const gpb_stack* st, const double* src, const gpb_regular_grid* grid, long long i0,
+                                long long i1, const double* fault_vals, long long ld_fault, double* Z, double* gx,
+                                double* gy, double* gz, void* stream) {
+    EvalParams prm{};
+    int rc = fill_common(st, src, prm);
+    if (rc) return rc;
+    GPB_REQUIRE(grid && Z, "null grid or output");
+    GPB_REQUIRE(i0 >= 0 && i1 >= i0 && i1 <= (long long)grid->nx * grid->ny * grid->nz, "bad point range");
+    GPB_REQUIRE((gx == nullptr) == (gy == nullptr) && (gx == nullptr) == (gz == nullptr), "gradient outputs: all or none");
+    GPB_REQUIRE(st->n_faults == 0 || fault_vals != nullptr, "fault values missing");
+    prm.grid = *grid;
+    prm.i0 = i0;
+    prm.m = i1 - i0;
+    prm.fault_vals = fault_vals;
+    prm.ld_fault = ld_fault;
+    prm.Z = Z; prm.gx = gx; prm.gy = gy; prm.gz = gz;
+    return dispatch_eval<true>(st->kernel, gx != nullptr, prm, (cudaStream_t)stream);
+}
+
+extern "C" int gpb_eval_points(const gpb_stack* st, const double* src, const double* xyz, long long ld_xyz, long long m,
+                               const double* fault_vals, long long ld_fault, double* Z, double* gx, double* gy,
+                               double* gz, void* stream) {
+    EvalParams prm{};
+    int rc = fill_common(st, src, prm);
+    if (rc) return rc;
+    GPB_REQUIRE(m >= 0 && ld_xyz >= m, "bad point count");
+    if (m == 0) return GPB_OK;
+    GPB_REQUIRE(xyz && Z, "null points or output");
+    GPB_REQUIRE((gx == nullptr) == (gy == nullptr) && (gx == nullptr) == (gz == nullptr), "gradient outputs: all or none");
+    GPB_REQUIRE(st->n_faults == 0 || fault_vals != nullptr, "fault values missing");
+    prm.xyz = xyz;
+    prm.ld_xyz = ld_xyz;
+    prm.m = m;
+    prm.fault_vals = fault_vals;
+    prm.ld_fault = ld_fault;
+    prm.Z = Z; prm.gx = gx; prm.gy = gy; prm.gz = gz;
+    return dispatch_eval<false>(st->kernel, gx != nullptr, prm, (cudaStream_t)stream);
+}

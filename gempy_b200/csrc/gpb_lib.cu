@@ -1,0 +1,85 @@
+// Library plumbing: error reporting, device query, launch counter.
+#include "gpb_common.cuh"
+#include <cstdarg>
+
+thread_local char g_gpb_error[512] = "";
+long long g_gpb_launches = 0;
+
+int gpb_set_error(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_gpb_error, sizeof(g_gpb_error), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int gpb_sm_count() {
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (cached[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
+
+extern "C" const char* gpb_last_error(void) { return g_gpb_error; }
+extern "C" int gpb_version(void) { return 100; }
+extern "C" long long gpb_launch_count(void) { return g_gpb_launches; }
+
+extern "C" int gpb_device_info(int device, int* sm_count, int* cc_major, int* cc_minor) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n)
+        return gpb_set_error(GPB_E_NODEVICE, "no CUDA device %d (count %d)", device, n);
+    int sm = 0, ma = 0, mi = 0;
+    GPB_CHECK_CUDA(cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, device));
+    GPB_CHECK_CUDA(cudaDeviceGetAttribute(&ma, cudaDevAttrComputeCapabilityMajor, device));
+    GPB_CHECK_CUDA(cudaDeviceGetAttribute(&mi, cudaDevAttrComputeCapabilityMinor, device));
+    if (sm_count) *sm_count = sm;
+    if (cc_major) *cc_major = ma;
+    if (cc_minor) *cc_minor = mi;
+    if (ma != 10) return gpb_set_error(GPB_E_NODEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", device, ma, mi);
+    return GPB_OK;
+}
+
+// ---- FP64 FMA pipe microbenchmark (roofline denominator; MEASURED_PEAKS.json has no FP64 entry) ----------
+__global__ void __launch_bounds__(256) dfma_chain_kernel(double* out, int iters, double a, double b) {
+    double x0 = threadIdx.x * 1e-3, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+            x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+        }
+    }
+    const double s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+    if (s == 123.456) out[0] = s;      // never true: keeps the chain alive
+}
+
+extern "C" int gpb_bench_dfma(int iters, double* tflops_host, void* stream) {
+    GPB_REQUIRE(iters > 0 && tflops_host, "bad arguments");
+    cudaStream_t s = (cudaStream_t)stream;
+    double* d = nullptr;
+    GPB_CHECK_CUDA(cudaMalloc((void**)&d, sizeof(double)));
+    const int blocks = gpb_sm_count() * 8;
+    cudaEvent_t e0, e1;
+    GPB_CHECK_CUDA(cudaEventCreate(&e0));
+    GPB_CHECK_CUDA(cudaEventCreate(&e1));
+    dfma_chain_kernel<<<blocks, 256, 0, s>>>(d, iters / 10 + 1, 0.999999, 1e-9);   // warm-up
+    GPB_LAUNCH_CHECK();
+    GPB_CHECK_CUDA(cudaEventRecord(e0, s));
+    dfma_chain_kernel<<<blocks, 256, 0, s>>>(d, iters, 0.999999, 1e-9);
+    GPB_LAUNCH_CHECK();
+    GPB_CHECK_CUDA(cudaEventRecord(e1, s));
+    GPB_CHECK_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    GPB_CHECK_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    const double flops = 2.0 * 64.0 * (double)iters * 256.0 * (double)blocks;
+    *tflops_host = flops / (ms * 1e-3) / 1e12;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    return GPB_OK;
+}

@@ -1,0 +1,411 @@
+// (2) Dense FP64 solve of the saddle-point system: blocked right-looking LU with partial pivoting.
+//
+// Engine stage replaced: "solver" with kernel_solver = 1 (direct dense solve; the reference calls LAPACK gesv
+// through numpy.linalg.solve) -- SURVEY.md 8a2 row (2); reference call site gempy/API/compute_API.py:68-73.
+//
+// Structure (column-major, in place):
+//   n <= kSmallN : one CTA, whole matrix in shared memory (the reference's example models: n = 8 ... 104).
+//   otherwise, for each panel of kNB columns:
+//     panel_kernel   unblocked partial-pivot LU of the tall panel (pivot search = block reduction)
+//     swap_trsm      row interchanges of the panel applied to the columns right of it + U12 = L11^-1 A12
+//     gemm_kernel    A22 -= L21 * U12 on the FP64 tensor cores (mma.sync m8n8k4 DMMA) -- the one dense contraction
+//   Interchanges are applied LAPACK-style inside a panel and LINPACK-style across panels (columns left of a
+//   panel are never permuted); gpb_lu_apply replays them panel by panel, so factor + apply are self-consistent.
+#include "gpb_common.cuh"
+
+namespace {
+
+constexpr int kNB = 32;          // panel width = K of the trailing update
+constexpr int kSmallN = 160;     // whole-matrix-in-smem path
+
+// =====================================================================================================
+// small systems: one CTA, matrix in shared memory
+// =====================================================================================================
+__global__ void __launch_bounds__(256) lu_small_kernel(int n, double* __restrict__ A, int lda, double* __restrict__ b,
+                                                        int nrhs, int ldb, int* __restrict__ ipiv, int* __restrict__ info,
+                                                        int do_solve) {
+    extern __shared__ double sm[];
+    const int ld = n + 1;                       // padded leading dimension
+    double* S = sm;                             // n x n, column-major, ld
+    __shared__ double red_v[8];
+    __shared__ int red_i[8];
+    __shared__ int piv_s;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int e = tid; e < n * n; e += nt) {
+        const int j = e / n, i = e - j * n;
+        S[j * ld + i] = A[(long long)j * lda + i];
+    }
+    if (tid == 0 && info) *info = 0;
+    __syncthreads();
+    for (int k = 0; k < n; ++k) {
+        // pivot search in column k, rows k..n-1 (first maximum, like idamax)
+        double best = -1.0;
+        int bi = n;
+        for (int i = k + tid; i < n; i += nt) {
+            const double v = fabs(S[k * ld + i]);
+            if (v > best) { best = v; bi = i; }
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_down_sync(0xffffffffu, best, o);
+            const int oi = __shfl_down_sync(0xffffffffu, bi, o);
+            if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+        }
+        if ((tid & 31) == 0) { red_v[tid >> 5] = best; red_i[tid >> 5] = bi; }
+        __syncthreads();
+        if (tid == 0) {
+            for (int w = 1; w < (nt >> 5); ++w)
+                if (red_v[w] > best || (red_v[w] == best && red_i[w] < bi)) { best = red_v[w]; bi = red_i[w]; }
+            piv_s = bi;
+            ipiv[k] = bi;
+            if (best == 0.0 && info && *info == 0) *info = k + 1;
+        }
+        __syncthreads();
+        const int p = piv_s;
+        if (p != k) {
+            for (int j = (k / kNB) * kNB + tid; j < n; j += nt) {     // LINPACK-style across panels
+                const double t = S[j * ld + k];
+                S[j * ld + k] = S[j * ld + p];
+                S[j * ld + p] = t;
+            }
+        }
+        __syncthreads();
+        const double pv = S[k * ld + k];
+        const double inv = pv != 0.0 ? 1.0 / pv : 0.0;
+        for (int i = k + 1 + tid; i < n; i += nt) S[k * ld + i] *= inv;
+        __syncthreads();
+        const int rem = n - k - 1;
+        for (int e = tid; e < rem * rem; e += nt) {
+            const int jj = e / rem, ii = e - jj * rem;
+            const int i = k + 1 + ii, j = k + 1 + jj;
+            S[j * ld + i] = fma(-S[k * ld + i], S[j * ld + k], S[j * ld + i]);
+        }
+        __syncthreads();
+    }
+    for (int e = tid; e < n * n; e += nt) {
+        const int j = e / n, i = e - j * n;
+        A[(long long)j * lda + i] = S[j * ld + i];
+    }
+    if (!do_solve) return;
+    // solve for each right-hand side (one warp per rhs would be enough; systems are tiny)
+    for (int r = 0; r < nrhs; ++r) {
+        double* x = b + (long long)r * ldb;
+        __syncthreads();
+        __shared__ double xs[kSmallN];
+        for (int i = tid; i < n; i += nt) xs[i] = x[i];
+        __syncthreads();
+        for (int k = 0; k < n; ++k) {               // forward, unit lower; swaps replayed panel by panel
+            if (k % kNB == 0) {
+                if (tid == 0) {
+                    const int ke = min(k + kNB, n);
+                    for (int kk = k; kk < ke; ++kk) {
+                        const int p = ipiv[kk];
+                        if (p != kk) { const double t = xs[kk]; xs[kk] = xs[p]; xs[p] = t; }
+                    }
+                }
+                __syncthreads();
+            }
+            const double xk = xs[k];
+            for (int i = k + 1 + tid; i < n; i += nt) xs[i] = fma(-S[k * ld + i], xk, xs[i]);
+            __syncthreads();
+        }
+        for (int k = n - 1; k >= 0; --k) {          // backward
+            if (tid == 0) xs[k] /= S[k * ld + k];
+            __syncthreads();
+            const double xk = xs[k];
+            for (int i = tid; i < k; i += nt) xs[i] = fma(-S[k * ld + i], xk, xs[i]);
+            __syncthreads();
+        }
+        for (int i = tid; i < n; i += nt) x[i] = xs[i];
+    }
+}
+
+// =====================================================================================================
+// blocked path
+// =====================================================================================================
+// Unblocked partial-pivot LU of the panel A[k0:n, k0:k0+jb]; one CTA of 1024 threads, panel in global/L2.
+__global__ void __launch_bounds__(1024) panel_kernel(int n, int k0, int jb, double* __restrict__ A, int lda,
+                                                      int* __restrict__ ipiv, int* __restrict__ info) {
+    __shared__ double red_v[32];
+    __shared__ int red_i[32];
+    __shared__ int piv_s;
+    __shared__ double prow[kNB];
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int j = 0; j < jb; ++j) {
+        const int kj = k0 + j;
+        double* col = A + (long long)kj * lda;
+        double best = -1.0;
+        int bi = n;
+        for (int i = kj + tid; i < n; i += nt) {
+            const double v = fabs(col[i]);
+            if (v > best) { best = v; bi = i; }
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_down_sync(0xffffffffu, best, o);
+            const int oi = __shfl_down_sync(0xffffffffu, bi, o);
+            if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+        }
+        if ((tid & 31) == 0) { red_v[tid >> 5] = best; red_i[tid >> 5] = bi; }
+        __syncthreads();
+        if (tid == 0) {
+            for (int w = 1; w < (nt >> 5); ++w)
+                if (red_v[w] > best || (red_v[w] == best && red_i[w] < bi)) { best = red_v[w]; bi = red_i[w]; }
+            piv_s = bi;
+            ipiv[kj] = bi;
+            if (best == 0.0 && info && *info == 0) *info = kj + 1;
+        }
+        __syncthreads();
+        const int p = piv_s;
+        // swap rows kj <-> p inside the panel and stage the pivot row
+        if (tid < jb) {
+            double* c = A + (long long)(k0 + tid) * lda;
+            const double vp = c[p];
+            if (p != kj) { c[p] = c[kj]; c[kj] = vp; }
+            prow[tid] = vp;
+        }
+        __syncthreads();
+        const double pv = prow[j];
+        const double inv = pv != 0.0 ? 1.0 / pv : 0.0;
+        const int nc = jb - j - 1;
+        for (int i = kj + 1 + tid; i < n; i += nt) {
+            const double l = col[i] * inv;
+            col[i] = l;
+            for (int c = 0; c < nc; ++c) {
+                double* a = A + (long long)(kj + 1 + c) * lda + i;
+                *a = fma(-l, prow[j + 1 + c], *a);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// Apply the panel's interchanges to the columns right of the panel and solve U12 = L11^-1 A12.
+// One CTA handles 64 columns.
+__global__ void __launch_bounds__(256) swap_trsm_kernel(int n, int k0, int jb, double* __restrict__ A, int lda,
+                                                        const int* __restrict__ ipiv) {
+    __shared__ double L[kNB][kNB + 1];
+    __shared__ double T[64][kNB + 1];
+    __shared__ int piv[kNB];
+    const int tid = threadIdx.x;
+    const int c0 = k0 + jb + blockIdx.x * 64;
+    const int ncol = min(64, n - c0);
+    for (int e = tid; e < jb * jb; e += 256) {
+        const int j = e / jb, i = e - j * jb;
+        L[i][j] = A[(long long)(k0 + j) * lda + k0 + i];
+    }
+    if (tid < jb) piv[tid] = ipiv[k0 + tid];
+    __syncthreads();
+    // interchanges: one thread per column, sequential over the panel's pivots
+    if (tid < ncol) {
+        double* c = A + (long long)(c0 + tid) * lda;
+        for (int j = 0; j < jb; ++j) {
+            const int p = piv[j];
+            if (p != k0 + j) { const double t = c[k0 + j]; c[k0 + j] = c[p]; c[p] = t; }
+        }
+    }
+    __syncthreads();
+    for (int e = tid; e < ncol * jb; e += 256) {
+        const int c = e / jb, i = e - c * jb;
+        T[c][i] = A[(long long)(c0 + c) * lda + k0 + i];
+    }
+    __syncthreads();
+    if (tid < ncol) {
+        for (int k = 0; k < jb; ++k) {
+            const double xk = T[tid][k];
+            for (int i = k + 1; i < jb; ++i) T[tid][i] = fma(-L[i][k], xk, T[tid][i]);
+        }
+    }
+    __syncthreads();
+    for (int e = tid; e < ncol * jb; e += 256) {
+        const int c = e / jb, i = e - c * jb;
+        A[(long long)(c0 + c) * lda + k0 + i] = T[c][i];
+    }
+}
+
+// ---- DMMA trailing update: C[M x N] -= Ap[M x K] * Bp[K x N], K = jb <= 32 ---------------------------
+__device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+constexpr int kGM = 64, kGN = 64;       // CTA tile
+constexpr int kLdA = kGM + 8;           // As[k][m]: ld = 8 mod 16 doubles -> 2 wavefronts per fragment load (optimal)
+constexpr int kLdB = kNB + 4;           // Bs[n][k]: ld = 4 mod 16 doubles
+
+__global__ void __launch_bounds__(256) gemm_kernel(int M, int N, int K, const double* __restrict__ Ap, const double* __restrict__ Bp,
+                                                   double* __restrict__ C, int lda) {
+    __shared__ double As[kNB * kLdA];
+    __shared__ double Bs[kGN * kLdB];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int m0 = blockIdx.x * kGM, n0 = blockIdx.y * kGN;
+    // stage A: columns k are contiguous in m
+    for (int e = tid; e < K * kGM; e += 256) {
+        const int k = e / kGM, m = e - k * kGM;
+        As[k * kLdA + m] = (m0 + m < M) ? -Ap[(long long)k * lda + m0 + m] : 0.0;     // negated: C += (-A) B
+    }
+    for (int e = tid; e < kGN * K; e += 256) {
+        const int nn = e / K, k = e - nn * K;
+        Bs[nn * kLdB + k] = (n0 + nn < N) ? Bp[(long long)(n0 + nn) * lda + k] : 0.0;
+    }
+    __syncthreads();
+    // 8 warps: 2 along M (32 rows each) x 4 along N (16 cols each); warp tile 32 x 16 = 4 x 2 m8n8 tiles
+    const int wm = (warp & 1) * 32, wn = (warp >> 1) * 16;
+    const int r = lane >> 2, q = lane & 3;
+    constexpr int NJ = 2;
+    double acc[4][NJ][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            const int gm = m0 + wm + 8 * i + r;
+            const int gn = n0 + wn + 8 * j + 2 * q;
+            acc[i][j][0] = (gm < M && gn < N) ? C[(long long)gn * lda + gm] : 0.0;
+            acc[i][j][1] = (gm < M && gn + 1 < N) ? C[(long long)(gn + 1) * lda + gm] : 0.0;
+        }
+    for (int ks = 0; ks < K; ks += 4) {
+        double a[4], b[NJ];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[i] = As[(ks + q) * kLdA + wm + 8 * i + r];
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) b[j] = Bs[(wn + 8 * j + r) * kLdB + ks + q];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            const int gm = m0 + wm + 8 * i + r;
+            const int gn = n0 + wn + 8 * j + 2 * q;
+            if (gm < M && gn < N) C[(long long)gn * lda + gm] = acc[i][j][0];
+            if (gm < M && gn + 1 < N) C[(long long)(gn + 1) * lda + gm] = acc[i][j][1];
+        }
+}
+
+// ---- triangular solves with the blocked factors (one CTA; panel-by-panel) --------------------------------
+__global__ void __launch_bounds__(1024) apply_kernel(int n, const double* __restrict__ LU, int lda, const int* __restrict__ ipiv,
+                                                      double* __restrict__ b, int nrhs, int ldb) {
+    __shared__ double xs[kNB];
+    __shared__ double D[kNB][kNB + 1];
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int r = 0; r < nrhs; ++r) {
+        double* x = b + (long long)r * ldb;
+        // forward: P, L
+        for (int k0 = 0; k0 < n; k0 += kNB) {
+            const int jb = min(kNB, n - k0);
+            __syncthreads();
+            for (int e = tid; e < jb * jb; e += nt) {
+                const int c = e / jb, i = e - c * jb;
+                D[i][c] = LU[(long long)(k0 + c) * lda + k0 + i];
+            }
+            if (tid == 0) {
+                for (int j = 0; j < jb; ++j) {
+                    const int p = ipiv[k0 + j];
+                    if (p != k0 + j) { const double t = x[k0 + j]; x[k0 + j] = x[p]; x[p] = t; }
+                }
+            }
+            __syncthreads();
+            if (tid < 32) {
+                double v = (tid < jb) ? x[k0 + tid] : 0.0;
+                for (int c = 0; c < jb; ++c) {
+                    const double xc = __shfl_sync(0xffffffffu, v, c);
+                    if (tid > c && tid < jb) v = fma(-D[tid][c], xc, v);
+                }
+                if (tid < jb) { xs[tid] = v; x[k0 + tid] = v; }
+            }
+            __syncthreads();
+            for (int i = k0 + jb + tid; i < n; i += nt) {
+                double v = x[i];
+                for (int c = 0; c < jb; ++c) v = fma(-LU[(long long)(k0 + c) * lda + i], xs[c], v);
+                x[i] = v;
+            }
+        }
+        // backward: U
+        const int last = ((n - 1) / kNB) * kNB;
+        for (int k0 = last; k0 >= 0; k0 -= kNB) {
+            const int jb = min(kNB, n - k0);
+            __syncthreads();
+            for (int e = tid; e < jb * jb; e += nt) {
+                const int c = e / jb, i = e - c * jb;
+                D[i][c] = LU[(long long)(k0 + c) * lda + k0 + i];
+            }
+            __syncthreads();
+            if (tid < 32) {
+                double v = (tid < jb) ? x[k0 + tid] : 0.0;
+                for (int c = jb - 1; c >= 0; --c) {
+                    if (tid == c) v /= D[c][c];
+                    const double xc = __shfl_sync(0xffffffffu, v, c);
+                    if (tid < c) v = fma(-D[tid][c], xc, v);
+                }
+                if (tid < jb) { xs[tid] = v; x[k0 + tid] = v; }
+            }
+            __syncthreads();
+            for (int i = tid; i < k0; i += nt) {
+                double v = x[i];
+                for (int c = 0; c < jb; ++c) v = fma(-LU[(long long)(k0 + c) * lda + i], xs[c], v);
+                x[i] = v;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void zero_info_kernel(int* info) { if (info) *info = 0; }
+
+int factor_blocked(int n, double* A, int lda, int* ipiv, int* info, cudaStream_t s) {
+    zero_info_kernel<<<1, 1, 0, s>>>(info);
+    GPB_LAUNCH_CHECK();
+    for (int k0 = 0; k0 < n; k0 += kNB) {
+        const int jb = (n - k0 < kNB) ? n - k0 : kNB;
+        panel_kernel<<<1, 1024, 0, s>>>(n, k0, jb, A, lda, ipiv, info);
+        GPB_LAUNCH_CHECK();
+        const int nright = n - k0 - jb;
+        if (nright > 0) {
+            swap_trsm_kernel<<<(nright + 63) / 64, 256, 0, s>>>(n, k0, jb, A, lda, ipiv);
+            GPB_LAUNCH_CHECK();
+            const int M = n - k0 - jb;
+            dim3 grid((M + kGM - 1) / kGM, (nright + kGN - 1) / kGN);
+            gemm_kernel<<<grid, 256, 0, s>>>(M, nright, jb, A + (long long)k0 * lda + k0 + jb,
+                                             A + (long long)(k0 + jb) * lda + k0, A + (long long)(k0 + jb) * lda + k0 + jb, lda);
+            GPB_LAUNCH_CHECK();
+        }
+    }
+    return GPB_OK;
+}
+
+int small_path(int n, double* A, int lda, double* b, int nrhs, int ldb, int* ipiv, int* info, int do_solve, cudaStream_t s) {
+    const size_t smem = (size_t)n * (n + 1) * sizeof(double);
+    static bool attr_set = false;
+    if (!attr_set) {
+        GPB_CHECK_CUDA(cudaFuncSetAttribute(lu_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        attr_set = true;
+    }
+    lu_small_kernel<<<1, 256, smem, s>>>(n, A, lda, b, nrhs, ldb, ipiv, info, do_solve);
+    GPB_LAUNCH_CHECK();
+    return GPB_OK;
+}
+
+}  // namespace
+
+extern "C" int gpb_lu_factor(int n, double* A, int lda, int* ipiv, int* info, void* stream) {
+    GPB_REQUIRE(n > 0 && A && ipiv && lda >= n, "bad arguments");
+    if (n <= kSmallN) return small_path(n, A, lda, nullptr, 0, 0, ipiv, info, 0, (cudaStream_t)stream);
+    return factor_blocked(n, A, lda, ipiv, info, (cudaStream_t)stream);
+}
+
+extern "C" int gpb_lu_apply(int n, const double* LU, int lda, const int* ipiv, double* b, int nrhs, int ldb, void* stream) {
+    GPB_REQUIRE(n > 0 && LU && ipiv && b && lda >= n && ldb >= n && nrhs >= 1, "bad arguments");
+    apply_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(n, LU, lda, ipiv, b, nrhs, ldb);
+    GPB_LAUNCH_CHECK();
+    return GPB_OK;
+}
+
+extern "C" int gpb_lu_solve(int n, double* A, int lda, double* b, int nrhs, int ldb, int* ipiv, int* info, void* stream) {
+    GPB_REQUIRE(n > 0 && A && b && ipiv && lda >= n && ldb >= n && nrhs >= 1, "bad arguments");
+    if (n <= kSmallN) return small_path(n, A, lda, b, nrhs, ldb, ipiv, info, 1, (cudaStream_t)stream);
+    int rc = factor_blocked(n, A, lda, ipiv, info, (cudaStream_t)stream);
+    if (rc) return rc;
+    return gpb_lu_apply(n, A, lda, ipiv, b, nrhs, ldb, stream);
+}

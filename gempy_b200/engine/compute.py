@@ -1,0 +1,610 @@
+"""Host side of the B200 backend: ``compute_model`` with the engine's signature.
+
+Mirrors ``gempy_engine.compute_model(interpolation_input, options, data_descriptor, geophysics_input)``
+(the call GemPy makes at /root/reference/gempy/API/compute_API.py:68-73) and returns a ``Solutions`` object
+with the attributes GemPy reads (gempy/core/data/geo_model.py:100-127).  The pipeline per octree level is
+
+    per stack:  ref/rest split -> [assemble covariance -> LU solve | cached weights] -> pack weights
+                -> fused field(+gradient) evaluation on {octree centres, dense, custom, topography, sections,
+                   corners} ++ surface points -> activator
+    all stacks: masks + combination -> lith / fault blocks
+    next level: corner-id refinement test -> child emission
+    finally:    dual contouring on the surface level
+
+Every arithmetic step is a CUDA kernel of libgempy_b200.so called through the C ABI (gempy_b200/_lib.py).
+torch is used for device-memory ownership, streams and (multi-GPU) torch.distributed only.
+There is no CPU fallback: without the library or a CUDA device this module raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from .. import _lib
+from .data import (BlockSolutionType, CombinedScalarFieldsOutput, DualContouringData, DualContouringMesh, EngineGrid,
+                   ExportedFields, GenericGrid, InputDataDescriptor, InterpolationInput, InterpolationOptions,
+                   InterpOutput, OctreeLevel, RawArraysSolution, RegularGrid, ScalarFieldOutput, Solutions,
+                   StackRelationType)
+
+GRID_SHIFT = 1e-6          # regular-grid / octree points sit at centre + 1e-6 (pinned by the approved vectors)
+F64 = torch.float64
+
+
+def _rel_code(rel) -> int:
+    if rel is False or rel is None:
+        return StackRelationType.BASEMENT.value
+    return int(getattr(rel, "value", rel))
+
+
+def _kernel_code(k) -> int:
+    return _lib.GPB_KERNEL[getattr(k, "name", k)]
+
+
+def _n_drift(degree: int) -> int:
+    return {0: 0, 1: 3, 2: 9}[int(degree)]
+
+
+def _ptr(t: Optional[torch.Tensor], byte_offset: int = 0) -> Optional[int]:
+    if t is None:
+        return None
+    return t.data_ptr() + byte_offset
+
+
+# ------------------------------------------------------------------------------------------------ segments
+@dataclass
+class Segment:
+    """A set of evaluation points: either an implicit regular grid range or an explicit [3, m] device table."""
+    name: str
+    m: int
+    grid: Optional[_lib.GpbRegularGrid] = None
+    i0: int = 0
+    xyz: Optional[torch.Tensor] = None          # [3, m] contiguous
+
+
+def regular_descriptor(g: RegularGrid) -> _lib.GpbRegularGrid:
+    e, s = g.orthogonal_extent, g.regular_grid_shape
+    d = np.array([(e[1] - e[0]) / s[0], (e[3] - e[2]) / s[1], (e[5] - e[4]) / s[2]])
+    return _lib.GpbRegularGrid(e[0] + d[0] / 2 + GRID_SHIFT, e[2] + d[1] / 2 + GRID_SHIFT, e[4] + d[2] / 2 + GRID_SHIFT,
+                               d[0], d[1], d[2], int(s[0]), int(s[1]), int(s[2]))
+
+
+def regular_centers_device(g: RegularGrid, device) -> Tuple[torch.Tensor, np.ndarray]:
+    """Explicit [3, n] centres of a (small) regular grid, x slowest / z fastest, shift included."""
+    ax = g.axis_coords()
+    gx, gy, gz = np.meshgrid(*ax, indexing="ij")
+    xyz = np.stack([gx.ravel(), gy.ravel(), gz.ravel()]) + GRID_SHIFT
+    return torch.as_tensor(xyz, dtype=F64, device=device).contiguous(), g.dxdydz.copy()
+
+
+# ------------------------------------------------------------------------------------------------ stack tables
+class StackTables:
+    """Device tables of one stack (the ref/rest split of the engine's preprocess stage)."""
+
+    def __init__(self, ii: InterpolationInput, desc: InputDataDescriptor, i: int, ko, device):
+        ss, ts = desc.stack_structure, desc.tensors_structure
+        sp0 = int(ss.number_of_points_per_stack[:i].sum())
+        sp1 = sp0 + int(ss.number_of_points_per_stack[i])
+        or0 = int(ss.number_of_orientations_per_stack[:i].sum())
+        or1 = or0 + int(ss.number_of_orientations_per_stack[i])
+        su0 = int(ss.number_of_surfaces_per_stack[:i].sum())
+        su1 = su0 + int(ss.number_of_surfaces_per_stack[i])
+        self.sp_slice = slice(sp0, sp1)
+        self.surf_slice = slice(su0, su1)
+        nps = np.asarray(ts.number_of_points_per_surface[su0:su1], dtype=np.int64)
+        if (nps < 1).any():
+            raise ValueError(f"stack {i}: every surface needs at least one surface point")
+        sp = ii.surface_points.sp_coords[sp0:sp1]
+        nug = ii.surface_points.nugget_effect_scalar[sp0:sp1]
+        starts = np.concatenate([[0], np.cumsum(nps)[:-1]]).astype(np.int64)
+        is_ref = np.zeros(sp.shape[0], bool)
+        is_ref[starts] = True
+        reps = nps - 1
+        self.ref_local = starts                                   # reference point of each surface, stack-local index
+        self.is_ref = is_ref
+        self.n_surf = int(nps.shape[0])
+        self.n_rest = int(reps.sum())
+        self.n_ori = or1 - or0
+        self.n_drift = _n_drift(ko.uni_degree)
+        rest = sp[~is_ref]
+        ref = np.repeat(sp[starts], reps, axis=0)
+        row_nug = 0.5 * (nug[~is_ref] + np.repeat(nug[starts], reps))
+        surf_off = np.concatenate([[0], np.cumsum(reps)]).astype(np.int32)
+        dev = lambda a, dt=F64: torch.as_tensor(np.ascontiguousarray(a), dtype=dt, device=device)
+        self.rest = dev(rest.T)
+        self.ref = dev(ref.T)
+        self.sp_nugget = dev(row_nug)
+        self.ref_unique = dev(sp[starts].T)
+        self.surf_offsets = dev(surf_off, torch.int32)
+        self.ori_pos = dev(ii.orientations.dip_positions[or0:or1].T)
+        self.ori_grad = dev(ii.orientations.dip_gradients[or0:or1].T)
+        self.ori_nugget = dev(ii.orientations.nugget_effect_grad[or0:or1])
+        # gather indices of rest / ref points inside the stack's surface-point table (for the fault tables)
+        self.rest_idx = torch.as_tensor(np.nonzero(~is_ref)[0], device=device)
+        self.ref_idx = torch.as_tensor(np.repeat(starts, reps), device=device)
+        self.ko = ko
+        self.fault_rest = None
+        self.fault_ref = None
+        self.n_faults = 0
+
+    def set_faults(self, fault_on_sp: Optional[torch.Tensor]):
+        """fault_on_sp: [n_f, n_sp_of_stack] values of the active fault blocks at this stack's surface points."""
+        if fault_on_sp is None or fault_on_sp.shape[0] == 0:
+            self.fault_rest = self.fault_ref = None
+            self.n_faults = 0
+            return
+        self.n_faults = int(fault_on_sp.shape[0])
+        self.fault_rest = fault_on_sp.index_select(1, self.rest_idx).contiguous()
+        self.fault_ref = fault_on_sp.index_select(1, self.ref_idx).contiguous()
+
+    def struct(self) -> _lib.GpbStack:
+        ko = self.ko
+        return _lib.GpbStack(
+            self.n_ori, self.n_rest, self.n_surf, self.n_drift, self.n_faults, _kernel_code(ko.kernel_function),
+            float(ko.range), float(ko.c_o), float(ko.i_res), float(ko.gi_res),
+            _ptr(self.ori_pos), _ptr(self.ori_grad), _ptr(self.ori_nugget), _ptr(self.rest), _ptr(self.ref),
+            _ptr(self.sp_nugget), _ptr(self.fault_rest), _ptr(self.fault_ref), _ptr(self.surf_offsets),
+            _ptr(self.ref_unique))
+
+    @property
+    def n(self) -> int:
+        return 3 * self.n_ori + self.n_rest + self.n_drift + self.n_faults
+
+
+# ------------------------------------------------------------------------------------------------ engine
+@dataclass
+class FieldsOnDevice:
+    """Result of evaluating all stacks on one domain (device tensors)."""
+    segments: List[Segment]
+    grid_size: int
+    Z: torch.Tensor                    # [n_stacks, L]   L = grid_size + n_sp
+    G: Optional[torch.Tensor]          # [n_stacks, 3, L] or None
+    block: torch.Tensor                # [n_stacks, L]
+    final_block: torch.Tensor          # [L]
+    faults_block: torch.Tensor         # [L]
+    squeezed: torch.Tensor             # [n_stacks, L] uint8
+    mask: torch.Tensor                 # [n_stacks, L] uint8
+    isovalues: List[torch.Tensor]      # per stack [n_surf]
+    weights: List[torch.Tensor]
+    cond: List[Optional[float]]
+    srcs: List[torch.Tensor] = None    # packed evaluation tables per stack
+
+    def seg_slice(self, name: str) -> slice:
+        off = 0
+        for s in self.segments:
+            if s.name == name:
+                return slice(off, off + s.m)
+            off += s.m
+        return slice(0, 0)
+
+
+class B200Engine:
+    def __init__(self, device: Optional[int] = None):
+        if not torch.cuda.is_available():
+            raise _lib.GpbError("the B200 backend needs a CUDA device (no CPU fallback)")
+        self.lib = _lib.lib()
+        self.device_index = torch.cuda.current_device() if device is None else int(device)
+        self.device = torch.device("cuda", self.device_index)
+        sm, ma, mi = C.c_int(), C.c_int(), C.c_int()
+        _lib.check(self.lib.gpb_device_info(self.device_index, C.byref(sm), C.byref(ma), C.byref(mi)))
+        self.sm_count = sm.value
+
+    # -- helpers --------------------------------------------------------------------------------------------
+    @property
+    def stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def empty(self, *shape, dtype=F64) -> torch.Tensor:
+        return torch.empty(*shape, dtype=dtype, device=self.device)
+
+    # -- stages ----------------------------------------------------------------------------------------------
+    def assemble(self, st: StackTables) -> Tuple[torch.Tensor, torch.Tensor]:
+        n = st.n
+        A = self.empty(n, n)                # column-major n x n (symmetric at this point)
+        b = self.empty(n)
+        s = st.struct()
+        _lib.check(self.lib.gpb_assemble_cov(C.byref(s), _ptr(A), n, _ptr(b), self.stream))
+        return A, b
+
+    def solve(self, A: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+        """In place: A -> LU, b -> weights.  Raises on a zero pivot."""
+        n = A.shape[0]
+        ipiv = self.empty(n, dtype=torch.int32)
+        info = torch.zeros(1, dtype=torch.int32, device=self.device)
+        _lib.check(self.lib.gpb_lu_solve(n, _ptr(A), n, _ptr(b), 1, n, _ptr(ipiv), _ptr(info), self.stream))
+        return b
+
+    def pack(self, st: StackTables, w: torch.Tensor) -> torch.Tensor:
+        s = st.struct()
+        nd = int(self.lib.gpb_eval_table_doubles(C.byref(s)))
+        src = self.empty(nd)
+        _lib.check(self.lib.gpb_pack_eval_table(C.byref(s), _ptr(w), _ptr(src), self.stream))
+        return src
+
+    def evaluate_segment(self, st: StackTables, src: torch.Tensor, seg: Segment, off: int, Z: torch.Tensor,
+                         G: Optional[torch.Tensor], fault_vals: Optional[torch.Tensor]):
+        """Z: [L] row of this stack; G: [3, L] or None; fault_vals: [n_f, L] or None; off = column offset."""
+        if seg.m == 0:
+            return
+        s = st.struct()
+        L = Z.shape[0]
+        o8 = off * 8
+        gp = [None, None, None] if G is None else [_ptr(G[a], o8) for a in range(3)]
+        fv = _ptr(fault_vals, o8) if fault_vals is not None else None
+        if seg.grid is not None:
+            _lib.check(self.lib.gpb_eval_regular(C.byref(s), _ptr(src), C.byref(seg.grid), seg.i0, seg.i0 + seg.m,
+                                                 fv, L, _ptr(Z, o8), gp[0], gp[1], gp[2], self.stream))
+        else:
+            _lib.check(self.lib.gpb_eval_points(C.byref(s), _ptr(src), _ptr(seg.xyz), seg.xyz.shape[1], seg.m,
+                                                fv, L, _ptr(Z, o8), gp[0], gp[1], gp[2], self.stream))
+
+    # -- all stacks on one domain ----------------------------------------------------------------------------
+    def interpolate_all_fields(self, ii: InterpolationInput, options: InterpolationOptions, desc: InputDataDescriptor,
+                               segments: List[Segment], weights_cache: List[Optional[torch.Tensor]],
+                               gradient: Optional[bool] = None, tables: Optional[List[StackTables]] = None
+                               ) -> FieldsOnDevice:
+        ko = options.kernel_options
+        if gradient is None:
+            gradient = bool(options.evaluation_options.compute_scalar_gradient)
+        ss = desc.stack_structure
+        n_st = ss.n_stacks
+        rel = [_rel_code(r) for r in ss.masking_descriptor]
+        fr = np.asarray(ss.faults_relations) if ss.faults_relations is not None else np.zeros((n_st, n_st), bool)
+        sp_all = torch.as_tensor(np.ascontiguousarray(ii.surface_points.sp_coords.T), dtype=F64, device=self.device)
+        n_sp = sp_all.shape[1]
+        gsz = sum(s.m for s in segments)
+        L = gsz + n_sp
+        sp_seg = Segment("surface_points", n_sp, xyz=sp_all)
+        Z = self.empty(n_st, L)
+        G = self.empty(n_st, 3, L) if gradient else None
+        block = self.empty(n_st, L)
+        values_everywhere = self.empty(n_st, L)
+        unit_values = torch.as_tensor(np.asarray(ii.unit_values, dtype=np.float64), device=self.device)
+        iso_min = self.empty(n_st)
+        iso_max = self.empty(n_st)
+        isos, conds, srcs = [], [], []
+        tmp_min = self.empty(1)
+        if tables is None:
+            tables = [StackTables(ii, desc, i, ko, self.device) for i in range(n_st)]
+        for i in range(n_st):
+            st = tables[i]
+            active = np.nonzero(fr[:, i])[0]
+            f_every = None
+            if active.size:
+                f_every = values_everywhere.index_select(0, torch.as_tensor(active, device=self.device)).contiguous()
+                st.set_faults(f_every[:, gsz:][:, st.sp_slice])
+            else:
+                st.set_faults(None)
+            cond = None
+            if weights_cache[i] is None:
+                A, b = self.assemble(st)
+                if getattr(ko, "compute_condition_number", False):
+                    cond = float(torch.linalg.cond(A).item())
+                weights_cache[i] = self.solve(A, b)
+                del A
+            w = weights_cache[i]
+            if w.shape[0] != st.n:
+                raise ValueError(f"stack {i}: cached weights have length {w.shape[0]}, system size is {st.n}")
+            src = self.pack(st, w)
+            srcs.append(src)
+            Gi = G[i] if gradient else None
+            # surface points first (the isovalues feed the activator), then every grid segment
+            self.evaluate_segment(st, src, sp_seg, gsz, Z[i], Gi, f_every)
+            off = 0
+            for seg in segments:
+                self.evaluate_segment(st, src, seg, off, Z[i], Gi, f_every)
+                off += seg.m
+            ref_global = torch.as_tensor(gsz + st.sp_slice.start + st.ref_local, device=self.device)
+            iso = Z[i].index_select(0, ref_global).contiguous()
+            isos.append(iso)
+            iso_min[i] = iso.min()
+            iso_max[i] = iso.max()
+            ids = unit_values[st.surf_slice.start:st.surf_slice.stop + 1].contiguous()
+            if ids.shape[0] != st.n_surf + 1:
+                raise ValueError("unit_values must hold one id per surface plus the basement")
+            _lib.check(self.lib.gpb_activate(_ptr(Z[i]), L, _ptr(iso), _ptr(ids), st.n_surf, float(options.sigmoid_slope),
+                                             _ptr(block[i]), self.stream))
+            if rel[i] == StackRelationType.FAULT.value:
+                _lib.check(self.lib.gpb_min(_ptr(block[i]), L, _ptr(tmp_min), self.stream))
+                _lib.check(self.lib.gpb_shift(_ptr(block[i]), L, _ptr(tmp_min), _ptr(values_everywhere[i]), self.stream))
+            else:
+                values_everywhere[i].copy_(block[i])
+            conds.append(cond)
+            if cond is not None:
+                ko.condition_number = cond
+        final_block = self.empty(L)
+        faults_block = self.empty(L)
+        squeezed = self.empty(n_st, L, dtype=torch.uint8)
+        mask = self.empty(n_st, L, dtype=torch.uint8)
+        rel_arr = (C.c_int * n_st)(*rel)
+        _lib.check(self.lib.gpb_combine(_ptr(Z), _ptr(block), L, L, n_st, rel_arr, _ptr(iso_min), _ptr(iso_max),
+                                        _ptr(final_block), _ptr(faults_block), _ptr(squeezed), _ptr(mask), self.stream))
+        return FieldsOnDevice(segments, gsz, Z, G, block, final_block, faults_block, squeezed, mask, isos,
+                              [weights_cache[i] for i in range(n_st)], conds, srcs)
+
+    def gradient_at(self, st: StackTables, src: torch.Tensor, xyz: torch.Tensor) -> torch.Tensor:
+        """Engine-convention gradient [3, m] of one stack's field at explicit points.  The fault drift has no
+        gradient term, so the fault columns are skipped."""
+        m = xyz.shape[1]
+        Z = self.empty(m)
+        G = self.empty(3, m)
+        s = st.struct()
+        s.n_faults = 0
+        _lib.check(self.lib.gpb_eval_points(C.byref(s), _ptr(src), _ptr(xyz), m, m, None, 0, _ptr(Z), _ptr(G[0]), _ptr(G[1]),
+                                            _ptr(G[2]), self.stream))
+        return G
+
+    # -- octree ----------------------------------------------------------------------------------------------
+    def corners_of(self, centers: torch.Tensor, d: np.ndarray) -> torch.Tensor:
+        nv = centers.shape[1]
+        out = self.empty(3, 8 * nv)
+        _lib.check(self.lib.gpb_voxel_corners(_ptr(centers), nv, nv, d[0] / 2, d[1] / 2, d[2] / 2, _ptr(out), 8 * nv,
+                                              self.stream))
+        return out
+
+    def refine(self, centers: torch.Tensor, d: np.ndarray, lith_corners: torch.Tensor, fault_corners: torch.Tensor,
+               force_all: bool) -> Tuple[torch.Tensor, torch.Tensor]:
+        nv = centers.shape[1]
+        mark = self.empty(nv, dtype=torch.uint8)
+        _lib.check(self.lib.gpb_mark_voxels(_ptr(lith_corners), _ptr(fault_corners), nv, int(force_all), _ptr(mark),
+                                            self.stream))
+        n_children = C.c_longlong(0)
+        _lib.check(self.lib.gpb_emit_children(_ptr(centers), nv, nv, _ptr(mark), d[0] / 4, d[1] / 4, d[2] / 4, None, 0,
+                                              C.byref(n_children), self.stream))
+        nc = int(n_children.value)
+        children = self.empty(3, nc)
+        if nc:
+            _lib.check(self.lib.gpb_emit_children(_ptr(centers), nv, nv, _ptr(mark), d[0] / 4, d[1] / 4, d[2] / 4,
+                                                  _ptr(children), nc, C.byref(n_children), self.stream))
+        return children, mark
+
+
+# ------------------------------------------------------------------------------------------------ materialisation
+def _np(t: Optional[torch.Tensor]) -> Optional[np.ndarray]:
+    return None if t is None else t.detach().cpu().numpy()
+
+
+def _level_outputs(f: FieldsOnDevice, grid: EngineGrid, rel_enum: Sequence) -> List[InterpOutput]:
+    Z, block = _np(f.Z), _np(f.block)
+    G = _np(f.G)
+    final_block, faults_block = _np(f.final_block), _np(f.faults_block)
+    squeezed, mask = _np(f.squeezed).astype(bool), _np(f.mask).astype(bool)
+    outs = []
+    for i in range(Z.shape[0]):
+        ef = ExportedFields(Z[i], None if G is None else G[i, 0], None if G is None else G[i, 1],
+                            None if G is None else G[i, 2], f.grid_size, _np(f.isovalues[i]))
+        sfo = ScalarFieldOutput(_np(f.weights[i]), grid, ef, block[i][None, :], rel_enum[i], mask[i])
+        comb = CombinedScalarFieldsOutput(squeezed[i], final_block, faults_block)
+        outs.append(InterpOutput(sfo, comb))
+    return outs
+
+
+def _fill_regular_from_octree(levels_host, base_shape: np.ndarray, key) -> np.ndarray:
+    """Dense array at the finest octree resolution: level-0 values upsampled, refined voxels overwritten by their
+    children (the engine's octree -> regular fill used by RawArraysSolution)."""
+    shape = np.asarray(base_shape, dtype=int)
+    vals = key(levels_host[0]).reshape(shape)
+    # index arrays of the voxels of each level inside the level's full lattice
+    ijk = np.stack(np.meshgrid(*[np.arange(s) for s in shape], indexing="ij"), axis=-1).reshape(-1, 3)
+    dense = vals
+    for lvl in range(1, len(levels_host)):
+        sel = levels_host[lvl - 1]["selected"]
+        dense = dense.repeat(2, axis=0).repeat(2, axis=1).repeat(2, axis=2)
+        parents = ijk[sel]
+        off = np.array([[i, j, k] for i in (0, 1) for j in (0, 1) for k in (0, 1)])
+        ijk = (parents[:, None, :] * 2 + off[None, :, :]).reshape(-1, 3)
+        v = key(levels_host[lvl])
+        dense[ijk[:, 0], ijk[:, 1], ijk[:, 2]] = v
+    return dense.ravel()
+
+
+# ------------------------------------------------------------------------------------------------ triangulation
+def triangulate(valid: np.ndarray, ijk: np.ndarray) -> np.ndarray:
+    """Quads (as two triangles) around every crossed edge shared by four existing surface voxels; vertex index =
+    rank among voxels with at least one crossing (same rule as oracle.dual_contour_triangles, vectorised)."""
+    vv = valid.any(axis=1)
+    k = ijk[vv].astype(np.int64)
+    val = valid[vv]
+    if k.shape[0] == 0:
+        return np.zeros((0, 3), dtype=np.int64)
+    lo = k.min(axis=0) - 1
+    span = k.max(axis=0) - lo + 2
+    code = lambda a: ((a[:, 0] - lo[0]) * span[1] + (a[:, 1] - lo[1])) * span[2] + (a[:, 2] - lo[2])
+    codes = code(k)
+    order = np.argsort(codes, kind="stable")
+    sorted_codes = codes[order]
+
+    def find(a):
+        c = code(a)
+        pos = np.searchsorted(sorted_codes, c)
+        pos = np.clip(pos, 0, len(sorted_codes) - 1)
+        ok = sorted_codes[pos] == c
+        return np.where(ok, order[pos], -1)
+
+    tris = []
+    hh_edge = {0: 3, 1: 7, 2: 11}
+    others = {0: (1, 2), 1: (0, 2), 2: (0, 1)}
+    for ax in range(3):
+        e = hh_edge[ax]
+        u, v = others[ax]
+        n = np.nonzero(val[:, e])[0]
+        if n.size == 0:
+            continue
+        ku = k[n].copy(); ku[:, u] += 1
+        kv = k[n].copy(); kv[:, v] += 1
+        kuv = ku.copy(); kuv[:, v] += 1
+        a, b, c = find(ku), find(kv), find(kuv)
+        ok = (a >= 0) & (b >= 0) & (c >= 0)
+        n, a, b, c = n[ok], a[ok], b[ok], c[ok]
+        t = np.stack([np.stack([n, a, c], axis=1), np.stack([n, c, b], axis=1)], axis=1).reshape(-1, 3)
+        tris.append(t)
+    return np.concatenate(tris).astype(np.int64) if tris else np.zeros((0, 3), dtype=np.int64)
+
+
+# ------------------------------------------------------------------------------------------------ entry point
+def compute_model(interpolation_input: InterpolationInput, options: InterpolationOptions,
+                  data_descriptor: InputDataDescriptor, geophysics_input=None, *, device: Optional[int] = None,
+                  engine: Optional[B200Engine] = None) -> Solutions:
+    """Drop-in for ``gempy_engine.compute_model`` (same positional/keyword signature; the keyword-only extras
+    select the CUDA device).  Raises ``NotImplementedError`` for geophysics input."""
+    if geophysics_input is not None or interpolation_input.grid.geophysics_grid is not None:
+        raise NotImplementedError("forward gravity is outside the B200 backend's scope (SURVEY.md section 8f)")
+    eng = engine or B200Engine(device)
+    ii, desc = interpolation_input, data_descriptor
+    eo = options.evaluation_options
+    grid = ii.grid
+    ss = desc.stack_structure
+    n_st = ss.n_stacks
+    rel_enum = list(ss.masking_descriptor)
+    ko = options.kernel_options
+    if grid.octree_grid is None:
+        raise ValueError("the engine grid always carries an octree grid (_engine_factory.py:88-96)")
+
+    cache: List[Optional[torch.Tensor]] = [None] * n_st
+    if ii.weights:
+        for i, w in enumerate(ii.weights):
+            if w is not None and len(w):
+                cache[i] = torch.as_tensor(np.asarray(w, dtype=np.float64), device=eng.device)
+    tables = [StackTables(ii, desc, i, ko, eng.device) for i in range(n_st)]
+
+    n_levels = int(eo.number_octree_levels)
+    dc_level = min(int(eo.number_octree_levels_surface), n_levels) - 1 if eo.mesh_extraction else -1
+    centers, d = regular_centers_device(grid.octree_grid, eng.device)
+    extra: List[Segment] = []
+    if grid.dense_grid is not None:
+        extra.append(Segment("dense_grid", grid.dense_grid.n_points, grid=regular_descriptor(grid.dense_grid)))
+    for name in ("custom_grid", "topography", "sections"):
+        g = getattr(grid, name)
+        if g is not None:
+            extra.append(Segment(name, g.n_points,
+                                 xyz=torch.as_tensor(np.ascontiguousarray(g.values.T), dtype=F64, device=eng.device)))
+
+    octree_levels: List[OctreeLevel] = []
+    levels_host = []
+    prev_regular = grid.octree_grid
+    dc_payload = None
+    for lvl in range(n_levels):
+        need_corners = (lvl < n_levels - 1) or (lvl == dc_level)
+        segs = [Segment("octree_grid", centers.shape[1], xyz=centers)]
+        if lvl == 0:
+            segs += extra
+        corners = None
+        if need_corners:
+            corners = eng.corners_of(centers, d)
+            segs.append(Segment("corners", corners.shape[1], xyz=corners))
+        f = eng.interpolate_all_fields(ii, options, desc, segs, cache, tables=tables)
+        # ---- host containers of this level
+        if lvl == 0:
+            og0 = RegularGrid(grid.octree_grid.orthogonal_extent, grid.octree_grid.regular_grid_shape)
+            og0._values = _np(centers).T.copy()            # explicit centres (shift included), as evaluated
+            lvl_grid = EngineGrid(octree_grid=og0, dense_grid=grid.dense_grid, topography=grid.topography,
+                                  sections=grid.sections, custom_grid=grid.custom_grid)
+        else:
+            og = RegularGrid.from_octree_level(_np(centers).T, prev_regular)
+            og._dxdydz = d.copy()
+            prev_regular = og
+            lvl_grid = EngineGrid(octree_grid=og)
+        outs = _level_outputs(f, lvl_grid, rel_enum)
+        level = OctreeLevel(grid_centers=lvl_grid, outputs_centers=outs,
+                            grid_corners=None if corners is None else EngineGrid.from_xyz_coords(_np(corners).T))
+        octree_levels.append(level)
+        nv = centers.shape[1]
+        host = {"lith": np.rint(outs[-1].combined_scalar_field.final_block[:nv]),
+                "faults": np.rint(outs[-1].combined_scalar_field.faults_block[:nv]), "selected": None}
+        levels_host.append(host)
+        if lvl == dc_level:
+            dc_payload = (centers, d.copy(), corners, f)
+        if lvl == n_levels - 1:
+            break
+        csl = f.seg_slice("corners")
+        children, mark = eng.refine(centers, d, f.final_block[csl].contiguous(), f.faults_block[csl].contiguous(),
+                                    force_all=lvl < int(eo.octree_min_level))
+        level.marked_voxels = _np(mark).astype(bool)
+        host["selected"] = level.marked_voxels
+        centers = children
+        d = d / 2
+
+    meshes = None
+    if eo.mesh_extraction and dc_payload is not None:
+        meshes = _dual_contouring(eng, ii, options, desc, tables, cache, dc_payload, grid.octree_grid)
+
+    sol = Solutions(octree_levels, meshes, None, options.block_solutions_type)
+    sol.raw_arrays = _raw_arrays(sol, levels_host, grid, options, meshes)
+    return sol
+
+
+def _dual_contouring(eng: B200Engine, ii, options, desc, tables, cache, payload, root_grid) -> List[DualContouringMesh]:
+    centers, d, corners, f = payload
+    nv = centers.shape[1]
+    csl = f.seg_slice("corners")
+    e = root_grid.orthogonal_extent
+    ijk = np.rint((_np(centers).T - GRID_SHIFT - e[[0, 2, 4]]) / d - 0.5).astype(np.int64)
+    meshes: List[DualContouringMesh] = []
+    ss = desc.stack_structure
+    rel = [_rel_code(r) for r in ss.masking_descriptor]
+    lib = eng.lib
+    for i in range(ss.n_stacks):
+        Zc = f.Z[i, csl].contiguous()
+        if rel[i] == StackRelationType.FAULT.value:
+            own = None
+        else:
+            own = eng.empty(nv, dtype=torch.uint8)
+            sq = f.squeezed[i, csl].contiguous()
+            _lib.check(lib.gpb_any8(_ptr(sq), nv, _ptr(own), eng.stream))
+        iso_host = _np(f.isovalues[i])
+        for s_idx, iso in enumerate(iso_host):
+            valid = eng.empty(12 * nv, dtype=torch.uint8)
+            xyz_e = eng.empty(3, 12 * nv)
+            _lib.check(lib.gpb_dc_edges(_ptr(corners), 8 * nv, _ptr(Zc), nv, float(iso), _ptr(own), _ptr(valid),
+                                        _ptr(xyz_e), eng.stream))
+            # gradient of stack i's field at the crossings: one more fused evaluation on the edge points
+            grad = eng.gradient_at(tables[i], f.srcs[i], xyz_e)
+            verts = eng.empty(3, nv)
+            _lib.check(lib.gpb_dc_vertices(_ptr(valid), _ptr(xyz_e), _ptr(grad), nv, 1.0, _ptr(verts), eng.stream))
+            valid_h = _np(valid).astype(bool).reshape(nv, 12)
+            verts_h = _np(verts).T
+            keep = valid_h.any(axis=1)
+            tris = triangulate(valid_h, ijk)
+            data = DualContouringData(_np(xyz_e).T[valid_h.ravel()], valid_h, _np(grad).T[valid_h.ravel()])
+            meshes.append(DualContouringMesh(verts_h[keep], tris, data))
+    return meshes
+
+
+def _raw_arrays(sol: Solutions, levels_host, grid: EngineGrid, options, meshes) -> RawArraysSolution:
+    ra = RawArraysSolution()
+    first = sol.octrees_output[0]
+    outs = first.outputs_centers
+    last = outs[-1]
+    fb, fa = last.combined_scalar_field.final_block, last.combined_scalar_field.faults_block
+    g0 = first.grid_centers
+    if options.block_solutions_type == BlockSolutionType.DENSE_GRID and grid.dense_grid is not None:
+        sl = g0.dense_grid_slice
+        ra.lith_block = np.rint(fb[sl])
+        ra.fault_block = np.rint(fa[sl])
+        ra.scalar_field_matrix = np.stack([o.exported_fields._scalar_field[sl] for o in outs])
+        ra.block_matrix = np.stack([o.scalar_fields.values_block[0, sl] for o in outs])
+        ra.mask_matrix = np.stack([o.scalar_fields.mask_components[sl] for o in outs])
+        ra.mask_matrix_squeezed = np.stack([o.combined_scalar_field.squeezed_mask_array[sl] for o in outs])
+    elif options.block_solutions_type == BlockSolutionType.OCTREE:
+        base = grid.octree_grid.regular_grid_shape
+        ra.lith_block = _fill_regular_from_octree(levels_host, base, lambda h: h["lith"])
+        ra.fault_block = _fill_regular_from_octree(levels_host, base, lambda h: h["faults"])
+        n0 = int(np.prod(base))
+        ra.scalar_field_matrix = np.stack([o.exported_fields._scalar_field[:n0] for o in outs])
+        ra.block_matrix = np.stack([o.scalar_fields.values_block[0, :n0] for o in outs])
+        ra.mask_matrix = np.stack([o.scalar_fields.mask_components[:n0] for o in outs])
+        ra.mask_matrix_squeezed = np.stack([o.combined_scalar_field.squeezed_mask_array[:n0] for o in outs])
+    if ra.lith_block.size:
+        mult = max(len(np.unique(ra.lith_block)), 1)
+        ra.litho_faults_block = ra.lith_block + ra.fault_block * mult
+    for name in ("custom", "topography", "sections"):
+        sl = getattr(g0, {"custom": "custom_grid_slice", "topography": "topography_slice", "sections": "sections_slice"}[name])
+        if sl.stop > sl.start:
+            setattr(ra, name, np.rint(fb[sl]))
+    if meshes is not None:
+        ra.vertices = [m.vertices for m in meshes]
+        ra.edges = [m.edges for m in meshes]
+    return ra

@@ -1,0 +1,166 @@
+/* gempy_b200.h -- C ABI of the B200 backend for GemPy's implicit co-kriging hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch types.  Every `double*` / `int*`
+ * below is a DEVICE pointer unless the parameter is documented as host; `stream` is a cudaStream_t
+ * passed as void* (0 = legacy default stream).  Every entry returns 0 on success or a negative
+ * GPB_E_* code, in which case gpb_last_error() holds a message.  Launches are asynchronous on
+ * `stream` unless stated otherwise.
+ *
+ * Reference interface replaced (the engine package itself is not vendored in the reference tree; the
+ * only reference-side binding is the Python call
+ *     gempy_engine.compute_model(interpolation_input, options, data_descriptor, geophysics_input)
+ * at /root/reference/gempy/API/compute_API.py:68-73, :140-145 and
+ * gempy/modules/optimize_nuggets/_ops.py:18-23).  gempy_b200/engine/compute.py is the host mirror of
+ * that call; it binds the entry points below with ctypes (gempy_b200/_lib.py).  Per-entry notes say
+ * which engine stage each one implements.
+ *
+ * Layout conventions
+ *  - every coordinate table is SoA: [3][n] doubles (x row, y row, z row), in the TRANSFORMED
+ *    coordinate system the bridge produces (_engine_factory.py:26-37);
+ *  - system rows/cols are ordered [G_x(n_ori) | G_y | G_z | increments (n_rest) | drift | faults];
+ *  - matrices are column-major with leading dimension lda (they are symmetric on assembly).
+ */
+#ifndef GEMPY_B200_H
+#define GEMPY_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GPB_OK 0
+#define GPB_E_INVALID  (-1)   /* bad argument */
+#define GPB_E_CUDA     (-2)   /* CUDA runtime error */
+#define GPB_E_SINGULAR (-3)   /* zero pivot in the LU */
+#define GPB_E_NODEVICE (-4)   /* no usable sm_100 device */
+
+#define GPB_KERNEL_CUBIC       0
+#define GPB_KERNEL_EXPONENTIAL 1   /* exp(-r^2 / (2 a^2)) */
+#define GPB_KERNEL_MATERN52    2
+
+#define GPB_REL_ERODE    1   /* StackRelationType encodings of the reference's serialization goldens */
+#define GPB_REL_ONLAP    2
+#define GPB_REL_FAULT    3
+#define GPB_REL_BASEMENT 4
+
+/* One stack (= one scalar field) after the ref/rest split.
+ * Mirrors what the engine's preprocess stage produces from SurfacePoints / Orientations
+ * (_engine_factory.py:27-37) for one structural group (structural_frame.py:333-350). */
+typedef struct gpb_stack {
+    int n_ori;              /* orientations */
+    int n_rest;             /* increments rest_i - ref_i  (= n_sp - n_surfaces) */
+    int n_surf;             /* surfaces in the stack */
+    int n_drift;            /* 0, 3 (degree 1) or 9 (degree 2) */
+    int n_faults;           /* fault-drift columns */
+    int kernel;             /* GPB_KERNEL_* */
+    double range, c_o, i_res, gi_res;
+    const double* ori_pos;      /* [3][n_ori] */
+    const double* ori_grad;     /* [3][n_ori] */
+    const double* ori_nugget;   /* [n_ori]    */
+    const double* rest;         /* [3][n_rest] */
+    const double* ref;          /* [3][n_rest]  reference point of each increment's surface */
+    const double* sp_nugget;    /* [n_rest]  row nugget of each increment */
+    const double* fault_rest;   /* [n_faults][n_rest] fault-block value at rest_i (may be NULL if n_faults == 0) */
+    const double* fault_ref;    /* [n_faults][n_rest] */
+    const int*    surf_offsets; /* [n_surf+1] first increment row of every surface */
+    const double* ref_unique;   /* [3][n_surf] the reference point of each surface */
+} gpb_stack;
+
+/* Regular (dense or octree-root) grid: cell centres, x slowest / z fastest
+ * (gempy/core/data/grid_modules/regular_grid.py:58-71), every centre displaced by `shift`. */
+typedef struct gpb_regular_grid {
+    double x0, y0, z0;      /* centre of cell (0,0,0), shift included */
+    double dx, dy, dz;
+    int nx, ny, nz;
+} gpb_regular_grid;
+
+/* ---- library ---------------------------------------------------------------------------------- */
+const char* gpb_last_error(void);
+int  gpb_version(void);
+/* Number of SMs / compute capability of `device`; GPB_E_NODEVICE if it is not sm_100. (host) */
+int  gpb_device_info(int device, int* sm_count, int* cc_major, int* cc_minor);
+/* Counter of kernels this library has launched since load (host; used by bench.py's gpu_launches). */
+long long gpb_launch_count(void);
+
+/* Measured FP64 FMA throughput of the current device (register-resident DFMA chains, 8 per thread), in
+ * TFLOP/s (FMA = 2).  Used as the roofline denominator of the evaluation kernel.  Synchronises. (host out) */
+int gpb_bench_dfma(int iters, double* tflops_host, void* stream);
+
+/* ---- (1) covariance assembly  [engine stage "kernel_constructor", SURVEY 8a2 row (1)] ------------ */
+/* n = 3*n_ori + n_rest + n_drift + n_faults.  Writes the full symmetric n x n matrix A (lda >= n) and the
+ * right-hand side b = [G_x; G_y; G_z; 0]. */
+int gpb_system_size(const gpb_stack* st);
+int gpb_assemble_cov(const gpb_stack* st, double* A, int lda, double* b, void* stream);
+
+/* ---- (2) dense solve  [engine stage "solver", kernel_solver = 1 (direct)] ------------------------- */
+/* In-place blocked right-looking LU with partial pivoting (DMMA trailing updates), then the triangular
+ * solves.  A is overwritten with L\U, b (n x nrhs, ldb) with the solution, ipiv (n ints) with the pivot rows.
+ * `info` (device int, may be NULL) receives 0 or the 1-based index of a zero pivot. */
+int gpb_lu_solve(int n, double* A, int lda, double* b, int nrhs, int ldb, int* ipiv, int* info, void* stream);
+/* Factor only / solve only (weight reuse across octree levels, timing against cusolverDnDgetrf/Dgetrs). */
+int gpb_lu_factor(int n, double* A, int lda, int* ipiv, int* info, void* stream);
+int gpb_lu_apply(int n, const double* LU, int lda, const int* ipiv, double* b, int nrhs, int ldb, void* stream);
+
+/* ---- (3) fused field + gradient evaluation  [engine stage "evaluator"; the dominant kernel] -------- */
+/* Pack the weights of one solved stack into the evaluation source tables (range-normalised coordinates,
+ * pre-scaled weights, one aggregated source per reference point).  `src` must hold gpb_eval_table_doubles()
+ * doubles. */
+long long gpb_eval_table_doubles(const gpb_stack* st);
+int gpb_pack_eval_table(const gpb_stack* st, const double* w, double* src, void* stream);
+/* Evaluate Z (and, if gx/gy/gz != NULL, the engine-convention gradient) at grid points [i0, i1) of a
+ * regular grid; outputs are indexed from 0 (out[k] is point i0 + k).  fault_vals: [n_faults][ld_fault] values
+ * of the active fault blocks at the same points (NULL if n_faults == 0). */
+int gpb_eval_regular(const gpb_stack* st, const double* src, const gpb_regular_grid* grid,
+                     long long i0, long long i1, const double* fault_vals, long long ld_fault,
+                     double* Z, double* gx, double* gy, double* gz, void* stream);
+/* Same at an explicit point list xyz = [3][ld_xyz] (octree levels, corners, custom grids, surface points). */
+int gpb_eval_points(const gpb_stack* st, const double* src, const double* xyz, long long ld_xyz, long long m,
+                    const double* fault_vals, long long ld_fault,
+                    double* Z, double* gx, double* gy, double* gz, void* stream);
+
+/* ---- (4a) activator + masks + combination  [engine stages "activator", mask/combine] -------------- */
+/* block[k] = sum_j ids[j] * (sigma(slope (Z - iso[j])) - sigma(slope (Z - iso[j-1])));  ids has n_surf+1 entries. */
+int gpb_activate(const double* Z, long long m, const double* isovalues, const double* ids, int n_surf,
+                 double slope, double* block, void* stream);
+/* Min over a device array (fault blocks are shifted by their minimum before they act as drift). */
+int gpb_min(const double* v, long long m, double* out_min, void* stream);
+int gpb_shift(const double* v, long long m, const double* minus, double* out, void* stream);
+/* Combine stacks top-down.  Z/block: [n_stacks][ld]; relations: host int[n_stacks]; iso_min/iso_max: device
+ * [n_stacks] (min / max isovalue of each stack).  Outputs: final_block[m], faults_block[m],
+ * squeezed_mask[n_stacks][ld] (uint8), mask[n_stacks][ld] (uint8, may be NULL). */
+int gpb_combine(const double* Z, const double* block, long long ld, long long m, int n_stacks,
+                const int* relations_host, const double* iso_min, const double* iso_max,
+                double* final_block, double* faults_block, unsigned char* squeezed_mask, unsigned char* mask,
+                void* stream);
+
+/* ---- (4b) octree refinement  [engine stage "octrees_topology"] ----------------------------------- */
+/* Corners of voxels (8 per voxel, sign pattern x:----++++ y:--++--++ z:-+-+-+-+), voxel-major:
+ * corner = centre +- (hx, hy, hz); pass the half cell size. */
+int gpb_voxel_corners(const double* centers, long long ld_c, long long nvox, double hx, double hy, double hz,
+                      double* corners, long long ld_k, void* stream);
+/* ids_corners: [8*nvox] combined lith+fault ids.  mark[v] = 1 if the 8 ids differ (or force_all). */
+int gpb_mark_voxels(const double* lith_corners, const double* fault_corners, long long nvox, int force_all,
+                    unsigned char* mark, void* stream);
+/* Stable compaction of marked voxels into 8 children each (same sign pattern; child = centre +- (hx,hy,hz),
+ * pass a quarter of the cell size).  children == NULL only counts.
+ * Returns the number of children through n_children_host (host; this call synchronises the stream). */
+int gpb_emit_children(const double* centers, long long ld_c, long long nvox, const unsigned char* mark,
+                      double hx, double hy, double hz, double* children, long long ld_ch,
+                      long long* n_children_host, void* stream);
+
+/* out[v] = 1 if any of in[8v .. 8v+7] is non-zero (voxel ownership from the squeezed mask at its corners). */
+int gpb_any8(const unsigned char* in, long long nvox, unsigned char* out, void* stream);
+
+/* ---- (4c) dual contouring  [engine stage "dual_contouring"] ---------------------------------------- */
+/* Edge crossings of one isovalue: for voxel v and edge e (x x x x y y y y z z z z) valid[v*12+e] and the
+ * crossing xyz_edge[3][12*nvox]; masked-out voxels (voxel_mask[v]==0) get no crossings. */
+int gpb_dc_edges(const double* corners, long long ld_k, const double* Z_corners, long long nvox, double iso,
+                 const unsigned char* voxel_mask, unsigned char* valid, double* xyz_edge, void* stream);
+/* Per-voxel QEF (12 edge planes with raw gradient normals + 3 mass-point planes of strength `bias`).
+ * grad_edge/xyz_edge: [3][12*nvox]; vertices: [3][nvox] (NaN for voxels without a crossing). */
+int gpb_dc_vertices(const unsigned char* valid, const double* xyz_edge, const double* grad_edge, long long nvox,
+                    double bias, double* vertices, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GEMPY_B200_H */

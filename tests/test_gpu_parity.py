@@ -1,0 +1,351 @@
+"""GPU parity: every CUDA stage, called through the C ABI, against the numpy oracle on the same inputs.
+
+Tolerances (BASELINE.json north_star): scalar fields and gradients 1e-9 relative (relative to the field's range),
+lith ids exact away from the isovalues (> 1e-6), mesh vertices 1e-6 of the model extent.
+"""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+from gempy_b200 import _lib, examples as ex            # noqa: E402
+from gempy_b200.engine import compute as gc            # noqa: E402
+from gempy_b200.engine.data import AvailableKernelFunctions as K  # noqa: E402
+from oracle import gempy_oracle as orc                 # noqa: E402
+
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "approved_scalar_fields.json")))
+RTOL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def eng():
+    return gc.B200Engine(0)
+
+
+def _oracle_stack(m, i=0, fault_on_sp=None):
+    ii, opt, desc = m.args()
+    sp0, or0, su0 = orc._stack_slices(desc)
+    sl_sp, sl_or = slice(sp0[i], sp0[i + 1]), slice(or0[i], or0[i + 1])
+    return orc.prepare_stack(ii.surface_points.sp_coords[sl_sp], ii.surface_points.nugget_effect_scalar[sl_sp],
+                             desc.tensors_structure.number_of_points_per_surface[su0[i]:su0[i + 1]],
+                             ii.orientations.dip_positions[sl_or], ii.orientations.dip_gradients[sl_or],
+                             ii.orientations.nugget_effect_grad[sl_or], fault_on_sp)
+
+
+def _rel_err(a, b):
+    scale = max(np.abs(b).max(), 1e-300)
+    return np.abs(a - b).max() / scale
+
+
+MODELS = {
+    "horizontal": lambda: ex.horizontal_strat(),
+    "anticline": lambda: ex.anticline(),
+    "synthetic_300": lambda: ex.synthetic_stress(n_sp_per_surface=60, n_surfaces=4, n_ori=60, resolution=(8, 8, 8)),
+}
+
+
+# ------------------------------------------------------------------------------------------- (1) assembly
+@pytest.mark.parametrize("name", list(MODELS))
+@pytest.mark.parametrize("kernel", [K.cubic, K.exponential, K.matern_5_2])
+@pytest.mark.parametrize("degree", [1, 2])
+def test_covariance_assembly(eng, name, kernel, degree):
+    m = MODELS[name]()
+    ii, opt, desc = m.args()
+    opt.kernel_options.kernel_function = kernel
+    opt.kernel_options.uni_degree = degree
+    st = gc.StackTables(ii, desc, 0, opt.kernel_options, eng.device)
+    A, b = eng.assemble(st)
+    A_ref = orc.assemble_covariance(_oracle_stack(m), opt.kernel_options)
+    b_ref = orc.rhs(_oracle_stack(m), opt.kernel_options)
+    A_h = A.cpu().numpy()
+    assert A_h.shape == A_ref.shape
+    np.testing.assert_array_equal(A_h, A_h.T)                      # bitwise symmetric
+    assert np.abs(A_h - A_ref).max() <= 1e-12 * np.abs(A_ref).max()
+    np.testing.assert_array_equal(b.cpu().numpy(), b_ref)
+
+
+def test_covariance_with_fault_columns(eng):
+    m = ex.combination()
+    ii, opt, desc = m.args()
+    rng = np.random.default_rng(3)
+    n_sp = int(desc.stack_structure.number_of_points_per_stack[2])
+    f_on_sp = rng.integers(0, 2, size=(1, n_sp)).astype(float)
+    st = gc.StackTables(ii, desc, 2, opt.kernel_options, eng.device)
+    st.set_faults(torch.as_tensor(f_on_sp, device=eng.device))
+    A, _ = eng.assemble(st)
+    A_ref = orc.assemble_covariance(_oracle_stack(m, 2, f_on_sp), opt.kernel_options)
+    assert A.shape[0] == A_ref.shape[0] == 3 * 6 + 82 + 3 + 1
+    assert np.abs(A.cpu().numpy() - A_ref).max() <= 1e-12 * np.abs(A_ref).max()
+
+
+# ------------------------------------------------------------------------------------------- (2) solve
+@pytest.mark.parametrize("n", [1, 7, 33, 104, 160, 161, 500, 1000, 2049])
+def test_lu_solve_random(eng, n):
+    rng = np.random.default_rng(n)
+    A = rng.standard_normal((n, n)) + 0.1 * np.eye(n)
+    b = rng.standard_normal(n)
+    x_ref = np.linalg.solve(A, b)
+    Ad = torch.as_tensor(np.asfortranarray(A).T.copy(), device=eng.device)     # column-major storage
+    bd = torch.as_tensor(b.copy(), device=eng.device)
+    x = eng.solve(Ad, bd).cpu().numpy()
+    res = np.abs(A @ x - b).max() / (np.abs(A).max() * np.abs(x).max() * n * np.finfo(float).eps)
+    assert res < 50, f"scaled residual {res}"
+    cond = np.linalg.cond(A)
+    assert np.abs(x - x_ref).max() <= 1e-13 * cond * np.abs(x_ref).max() + 1e-300
+
+
+def test_lu_factor_apply_consistent(eng):
+    n = 700
+    rng = np.random.default_rng(0)
+    A = rng.standard_normal((n, n))
+    B = rng.standard_normal((n, 3))
+    Ad = torch.as_tensor(A.T.copy(), device=eng.device)
+    ipiv = eng.empty(n, dtype=torch.int32)
+    info = torch.zeros(1, dtype=torch.int32, device=eng.device)
+    _lib.check(eng.lib.gpb_lu_factor(n, Ad.data_ptr(), n, ipiv.data_ptr(), info.data_ptr(), eng.stream))
+    Bd = torch.as_tensor(B.T.copy(), device=eng.device)                        # [nrhs][n] = column-major n x nrhs
+    _lib.check(eng.lib.gpb_lu_apply(n, Ad.data_ptr(), n, ipiv.data_ptr(), Bd.data_ptr(), 3, n, eng.stream))
+    X = Bd.cpu().numpy().T
+    assert int(info.item()) == 0
+    assert np.abs(A @ X - B).max() < 1e-9
+    piv = ipiv.cpu().numpy()
+    assert (piv >= np.arange(n)).all() and (piv < n).all()
+
+
+def test_lu_reports_singular(eng):
+    n = 40
+    A = np.zeros((n, n))
+    Ad = torch.as_tensor(A, device=eng.device)
+    ipiv = eng.empty(n, dtype=torch.int32)
+    info = torch.zeros(1, dtype=torch.int32, device=eng.device)
+    _lib.check(eng.lib.gpb_lu_factor(n, Ad.data_ptr(), n, ipiv.data_ptr(), info.data_ptr(), eng.stream))
+    assert int(info.item()) == 1
+
+
+@pytest.mark.parametrize("name", list(MODELS))
+def test_weights_match_oracle(eng, name):
+    m = MODELS[name]()
+    ii, opt, desc = m.args()
+    st = gc.StackTables(ii, desc, 0, opt.kernel_options, eng.device)
+    A, b = eng.assemble(st)
+    w = eng.solve(A, b).cpu().numpy()
+    so = _oracle_stack(m)
+    A_ref = orc.assemble_covariance(so, opt.kernel_options)
+    w_ref = orc.solve(A_ref, orc.rhs(so, opt.kernel_options))
+    cond = np.linalg.cond(A_ref)
+    assert np.abs(w - w_ref).max() <= 1e-14 * cond * np.abs(w_ref).max()
+
+
+# ------------------------------------------------------------------------------------------- (3) evaluation
+def _eval_both(eng, m, xyz, kernel=K.cubic, degree=1, regular=None):
+    ii, opt, desc = m.args()
+    opt.kernel_options.kernel_function = kernel
+    opt.kernel_options.uni_degree = degree
+    ko = opt.kernel_options
+    so = _oracle_stack(m)
+    w = orc.solve(orc.assemble_covariance(so, ko), orc.rhs(so, ko))
+    st = gc.StackTables(ii, desc, 0, ko, eng.device)
+    src = eng.pack(st, torch.as_tensor(w, device=eng.device))
+    npts = xyz.shape[0]
+    Z = eng.empty(npts)
+    G = eng.empty(3, npts)
+    if regular is None:
+        seg = gc.Segment("p", npts, xyz=torch.as_tensor(np.ascontiguousarray(xyz.T), device=eng.device))
+    else:
+        seg = gc.Segment("r", npts, grid=gc.regular_descriptor(regular))
+    eng.evaluate_segment(st, src, seg, 0, Z, G, None)
+    Z2 = eng.empty(npts)
+    eng.evaluate_segment(st, src, seg, 0, Z2, None, None)                      # field-only variant
+    Zr, Gr = orc.evaluate(so, ko, w, xyz, gradient=True)
+    return Z.cpu().numpy(), G.cpu().numpy().T, Z2.cpu().numpy(), Zr, Gr
+
+
+@pytest.mark.parametrize("name", list(MODELS))
+@pytest.mark.parametrize("kernel", [K.cubic, K.exponential, K.matern_5_2])
+def test_eval_points_field_and_gradient(eng, name, kernel):
+    m = MODELS[name]()
+    ii, _, _ = m.args()
+    rng = np.random.default_rng(1)
+    # random points + the data points themselves (r = 0 paths) + a ragged count that is not a multiple of the chunk
+    xyz = np.vstack([rng.uniform(-0.5, 0.5, size=(3001, 3)), ii.surface_points.sp_coords, ii.orientations.dip_positions])
+    Z, G, Z2, Zr, Gr = _eval_both(eng, m, xyz, kernel)
+    assert _rel_err(Z, Zr) < RTOL
+    assert _rel_err(Z2, Zr) < RTOL
+    assert _rel_err(G, Gr) < RTOL
+
+
+def test_eval_degree2_drift(eng):
+    m = MODELS["synthetic_300"]()
+    rng = np.random.default_rng(2)
+    xyz = rng.uniform(-0.5, 0.5, size=(777, 3))
+    Z, G, Z2, Zr, Gr = _eval_both(eng, m, xyz, K.cubic, degree=2)
+    assert _rel_err(Z, Zr) < RTOL and _rel_err(G, Gr) < RTOL
+
+
+def test_eval_regular_matches_points(eng):
+    m = ex.anticline(resolution=(17, 9, 23))
+    ii, _, _ = m.args()
+    g = ii.grid.dense_grid
+    xyz = g.values + gc.GRID_SHIFT
+    Z, G, Z2, Zr, Gr = _eval_both(eng, m, xyz, regular=g)
+    assert _rel_err(Z, Zr) < RTOL and _rel_err(G, Gr) < RTOL
+
+
+def test_eval_empty_and_single_point(eng):
+    m = MODELS["anticline"]()
+    Z, G, Z2, Zr, Gr = _eval_both(eng, m, np.array([[0.01, 0.02, 0.03]]))
+    assert _rel_err(Z, Zr) < RTOL
+    ii, opt, desc = m.args()
+    st = gc.StackTables(ii, desc, 0, opt.kernel_options, eng.device)
+    s = st.struct()
+    src = eng.empty(int(eng.lib.gpb_eval_table_doubles(C.byref(s))))
+    _lib.check(eng.lib.gpb_eval_points(C.byref(s), src.data_ptr(), None, 0, 0, None, 0, None, None, None, None, eng.stream))
+
+
+def test_eval_rejects_bad_arguments(eng):
+    m = MODELS["anticline"]()
+    ii, opt, desc = m.args()
+    st = gc.StackTables(ii, desc, 0, opt.kernel_options, eng.device)
+    s = st.struct()
+    src = eng.empty(int(eng.lib.gpb_eval_table_doubles(C.byref(s))))
+    Z = eng.empty(10)
+    rc = eng.lib.gpb_eval_points(C.byref(s), src.data_ptr(), None, 10, 10, None, 0, Z.data_ptr(), None, None, None, eng.stream)
+    assert rc == -1 and b"null" in eng.lib.gpb_last_error()
+    with pytest.raises(_lib.GpbError):
+        _lib.check(rc)
+
+
+# ------------------------------------------------------------------------------------------- full pipeline
+def _verify_scalar_field(sol):
+    out = sol.octrees_output[-1].outputs[0]
+    sf = out.exported_fields.scalar_field
+    return sf[::int(len(sf) / 50)]
+
+
+@pytest.mark.parametrize("key,build", [("anticline", ex.anticline), ("fault", ex.one_fault), ("combination", ex.combination)])
+def test_compute_model_reproduces_approved_vectors(key, build):
+    """The reference's own golden test (test/test_model_types/test_example_models_I.py:19-88), run through the
+    drop-in entry point."""
+    m = build()
+    sol = gc.compute_model(*m.args())
+    got = _verify_scalar_field(sol)
+    want = np.array(GOLD[key])
+    assert got.shape == (51,)
+    np.testing.assert_allclose(got, want, rtol=0, atol=5e-8)
+
+
+@pytest.mark.parametrize("build", [ex.anticline, ex.one_fault, ex.combination])
+def test_compute_model_matches_oracle_everywhere(build):
+    m = build()
+    sol = gc.compute_model(*m.args())
+    ref = orc.compute_model(*build().args())
+    assert len(sol.octrees_output) == len(ref.levels)
+    for lvl, (a, b) in enumerate(zip(sol.octrees_output, ref.levels)):
+        nv = b.centers.shape[0]
+        np.testing.assert_allclose(a.grid_centers.octree_grid.values, b.centers, rtol=0, atol=1e-15)
+        for i, (oa, ob) in enumerate(zip(a.outputs_centers, b.fields.stacks)):
+            za = oa.exported_fields.scalar_field[:nv]
+            zb = ob.Z[:nv]
+            assert _rel_err(za, zb) < RTOL, (lvl, i)
+            np.testing.assert_allclose(oa.exported_fields.scalar_field_at_surface_points, ob.isovalues, rtol=1e-9, atol=1e-12)
+        # lith ids: exact on every voxel further than 1e-6 from an isovalue of the stack that owns it
+        ids_a = np.rint(a.outputs_centers[-1].block[:nv])
+        ids_b = b.fields.lith_ids[:nv]
+        near = np.zeros(nv, bool)
+        for ob in b.fields.stacks:
+            near |= (np.abs(ob.Z[:nv, None] - ob.isovalues[None, :]) < 1e-6).any(axis=1)
+        np.testing.assert_array_equal(ids_a[~near], ids_b[~near])
+        if b.selected is not None:
+            np.testing.assert_array_equal(a.marked_voxels, b.selected)
+
+
+def test_custom_grid_known_answer_gpu():
+    xyz = np.array([[0, 0, 0], [1000, 0, 0], [0, 1000, 0], [1000, 1000, 0],
+                    [0, 0, 1000], [1000, 0, 1000], [0, 1000, 1000], [1000, 1000, 1000]], dtype=float)
+    m = ex.anticline(custom_xyz=xyz)
+    m.options.number_octree_levels = 2
+    sol = gc.compute_model(*m.args())
+    np.testing.assert_array_equal(sol.raw_arrays.custom, np.array([3., 3., 3., 3., 1., 1., 1., 1.]))
+
+
+def test_dense_grid_solution_shape_and_ids():
+    m = ex.combination(resolution=(20, 10, 10))
+    m.options.mesh_extraction = False
+    sol = gc.compute_model(*m.args())
+    assert sol.dc_meshes is None
+    assert sol.raw_arrays.scalar_field_matrix.shape == (3, 2000)           # test_outliers.py:51 contract
+    ii, opt, desc = ex.combination(resolution=(20, 10, 10)).args()
+    f = orc.interpolate_all_fields(ii, opt, desc, ii.grid.dense_grid.values + orc.GRID_SHIFT)
+    np.testing.assert_array_equal(sol.raw_arrays.lith_block, f.lith_ids)
+
+
+def test_dual_contouring_vertices_match_oracle():
+    m = ex.anticline(refinement=4)
+    sol = gc.compute_model(*m.args())
+    ref = orc.compute_model(*ex.anticline(refinement=4).args())
+    assert len(sol.dc_meshes) == len(ref.meshes) == 2
+    extent_t = 0.5
+    for a, b in zip(sol.dc_meshes, ref.meshes):
+        assert a.vertices.shape == b.vertices.shape
+        assert np.abs(a.vertices - b.vertices).max() < 1e-6 * extent_t
+        assert set(map(tuple, a.edges.tolist())) == set(map(tuple, b.edges.tolist()))
+
+
+def test_weights_reused_when_provided():
+    m = ex.anticline(refinement=2)
+    sol = gc.compute_model(*m.args())
+    w = [o.weights for o in sol.root_output.outputs]
+    m2 = ex.anticline(refinement=2)
+    m2.interpolation_input.weights = w
+    sol2 = gc.compute_model(*m2.args())
+    np.testing.assert_array_equal(sol2.octrees_output[-1].outputs[0].exported_fields.scalar_field,
+                                  sol.octrees_output[-1].outputs[0].exported_fields.scalar_field)
+
+
+# ------------------------------------------------------------------------------------------- size-independent properties
+def test_linearity_in_the_weights_at_scale(eng):
+    """Z is linear in the packed weights: eval(w1 + w2) == eval(w1) + eval(w2), on 2M points / 2.5k data."""
+    m = ex.synthetic_stress(n_sp_per_surface=500, n_surfaces=4, n_ori=500, resolution=(128, 128, 128))
+    ii, opt, desc = m.args()
+    st = gc.StackTables(ii, desc, 0, opt.kernel_options, eng.device)
+    rng = np.random.default_rng(5)
+    w1 = torch.as_tensor(rng.standard_normal(st.n), device=eng.device)
+    w2 = torch.as_tensor(rng.standard_normal(st.n), device=eng.device)
+    seg = gc.Segment("r", ii.grid.dense_grid.n_points, grid=gc.regular_descriptor(ii.grid.dense_grid))
+    outs = []
+    for w in (w1, w2, w1 + w2):
+        Z = eng.empty(seg.m)
+        G = eng.empty(3, seg.m)
+        eng.evaluate_segment(st, eng.pack(st, w), seg, 0, Z, G, None)
+        outs.append((Z, G))
+    zs = (outs[0][0] + outs[1][0] - outs[2][0]).abs().max().item()
+    gs = (outs[0][1] + outs[1][1] - outs[2][1]).abs().max().item()
+    scale = outs[2][0].abs().max().item()
+    assert zs < 1e-11 * scale and gs < 1e-10 * outs[2][1].abs().max().item()
+
+
+def test_interpolant_honours_data_at_scale(eng):
+    """Solve a 2.5k-point system on the GPU and check Z(rest) = Z(ref) and grad Z(x_o) = G_o to nugget level."""
+    m = ex.synthetic_stress(n_sp_per_surface=500, n_surfaces=4, n_ori=500, resolution=(4, 4, 4))
+    ii, opt, desc = m.args()
+    st = gc.StackTables(ii, desc, 0, opt.kernel_options, eng.device)
+    A, b = eng.assemble(st)
+    w = eng.solve(A, b)
+    src = eng.pack(st, w)
+    pts = np.vstack([ii.surface_points.sp_coords, ii.orientations.dip_positions])
+    seg = gc.Segment("p", pts.shape[0], xyz=torch.as_tensor(np.ascontiguousarray(pts.T), device=eng.device))
+    Z = eng.empty(seg.m)
+    G = eng.empty(3, seg.m)
+    eng.evaluate_segment(st, src, seg, 0, Z, G, None)
+    Z, G = Z.cpu().numpy(), G.cpu().numpy().T
+    n_sp = ii.surface_points.n_points
+    for k in range(4):
+        z = Z[500 * k:500 * (k + 1)]
+        assert np.abs(z - z[0]).max() < 2e-2
+    assert np.abs(G[n_sp:] - ii.orientations.dip_gradients).max() < 0.2
