@@ -117,7 +117,7 @@ __device__ double entry(const gpb_stack& st, const RowDesc& ri, const RowDesc& r
         cov_terms<KERNEL>(dist3(p.a, q.b, h), a, C10, kp, ka);
         cov_terms<KERNEL>(dist3(p.b, q.a, h), a, C01, kp, ka);
         cov_terms<KERNEL>(dist3(p.b, q.b, h), a, C00, kp, ka);
-        double v = c_o * st.i_res * (C11 - C10 - C01 + C00);
+        double v = c_o * st.i_res * ((C11 + C00) - (C10 + C01));      // symmetric under (i, j) swap
         if (diag) v += c_o * p.nug;
         return v;
     }

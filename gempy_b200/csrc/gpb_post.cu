@@ -163,7 +163,9 @@ __global__ void mark_kernel(const double* __restrict__ lith, const double* __res
 
 __global__ void any8_kernel(const unsigned char* __restrict__ in, long long nvox, unsigned char* __restrict__ out) {
     for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < nvox; v += (long long)gridDim.x * blockDim.x) {
-        const unsigned long long w = *reinterpret_cast<const unsigned long long*>(in + 8 * v);
+        unsigned w = 0;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) w |= in[8 * v + c];
         out[v] = w ? 1 : 0;
     }
 }
@@ -404,7 +406,6 @@ extern "C" int gpb_emit_children(const double* centers, long long ld_c, long lon
 
 extern "C" int gpb_any8(const unsigned char* in, long long nvox, unsigned char* out, void* stream) {
     GPB_REQUIRE(in && out && nvox >= 0, "bad arguments");
-    GPB_REQUIRE((reinterpret_cast<uintptr_t>(in) & 7) == 0, "input must be 8-byte aligned");
     if (nvox == 0) return GPB_OK;
     any8_kernel<<<blocks_for(nvox), kT, 0, (cudaStream_t)stream>>>(in, nvox, out);
     GPB_LAUNCH_CHECK();
