@@ -12,11 +12,27 @@
 //   Interchanges are applied LAPACK-style inside a panel and LINPACK-style across panels (columns left of a
 //   panel are never permuted); gpb_lu_apply replays them panel by panel, so factor + apply are self-consistent.
 #include "gpb_common.cuh"
+#include <cooperative_groups.h>
+
+namespace cg = cooperative_groups;
 
 namespace {
 
-constexpr int kNB = 32;          // panel width = K of the trailing update
+constexpr int kNB = 32;          // (maximum) panel width = K of the trailing update
 constexpr int kSmallN = 160;     // whole-matrix-in-smem path
+
+// Panel width at column k0 of an n x n factorisation: a pure function of (n, k0) and the device's cluster
+// configuration, evaluated identically by gpb_lu_factor (host) and by the forward substitution of gpb_lu_apply
+// (device), so the interchanges are replayed over exactly the panels that produced them.
+__host__ __device__ inline int panel_width_hd(int n, int k0, int cluster, unsigned long long smem_cap) {
+    int jb = kNB;
+    if (cluster > 0) {
+        const long long m = n - k0;
+        const long long R = (m + cluster - 1) / cluster;
+        while (jb > 8 && (unsigned long long)(R + 2) * jb * sizeof(double) > smem_cap) jb >>= 1;
+    }
+    return (n - k0 < jb) ? n - k0 : jb;
+}
 
 // =====================================================================================================
 // small systems: one CTA, matrix in shared memory
@@ -178,6 +194,107 @@ __global__ void __launch_bounds__(1024) panel_kernel(int n, int k0, int jb, doub
     }
 }
 
+
+// -----------------------------------------------------------------------------------------------------
+// Cluster panel: the rows of the tall panel are distributed over the shared memory of the CTAs of one
+// thread-block cluster (up to 16 SMs).  Per column: local arg-max -> candidates exchanged through distributed
+// shared memory -> cluster barrier -> the pivot row is broadcast (and the displaced top row sent to the pivot's
+// owner) through DSMEM -> cluster barrier -> CTA-local rank-1 update out of shared memory.  Two cluster
+// barriers per column replace the grid-wide synchronisation a multi-CTA panel would otherwise need.
+// -----------------------------------------------------------------------------------------------------
+constexpr int kPanelThreads = 512;
+constexpr int kMaxCluster = 16;
+
+__global__ void __launch_bounds__(kPanelThreads, 1)
+panel_cluster_kernel(int n, int k0, int jb, double* __restrict__ A, int lda, int* __restrict__ ipiv, int* __restrict__ info,
+                     int R, int ldp) {
+    extern __shared__ double P[];                  // [jb][ldp] : this CTA's rows of the panel, column-major
+    __shared__ double prow[kNB], trow[kNB];
+    __shared__ double cand_v[kMaxCluster];
+    __shared__ int cand_i[kMaxCluster];
+    __shared__ double red_v[kPanelThreads / 32];
+    __shared__ int red_i[kPanelThreads / 32];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int C = (int)cluster.num_blocks();
+    const int rank = (int)cluster.block_rank();
+    const int tid = threadIdx.x;
+    const int r0 = k0 + rank * R;
+    const int nrows = max(0, min(n, r0 + R) - r0);
+
+    for (int e = tid; e < nrows * jb; e += kPanelThreads) {
+        const int c = e / nrows, i = e - c * nrows;
+        P[c * ldp + i] = A[(long long)(k0 + c) * lda + r0 + i];
+    }
+    __syncthreads();
+    cluster.sync();                                // every CTA of the cluster is resident before any DSMEM access
+
+    for (int j = 0; j < jb; ++j) {
+        const int kj = k0 + j;
+        // ---- local pivot candidate (first maximum of |column j| over this CTA's active rows)
+        double best = -1.0;
+        int bi = n;
+        for (int i = tid; i < nrows; i += kPanelThreads) {
+            const int gi = r0 + i;
+            if (gi >= kj) {
+                const double v = fabs(P[j * ldp + i]);
+                if (v > best) { best = v; bi = gi; }
+            }
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_down_sync(0xffffffffu, best, o);
+            const int oi = __shfl_down_sync(0xffffffffu, bi, o);
+            if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+        }
+        if ((tid & 31) == 0) { red_v[tid >> 5] = best; red_i[tid >> 5] = bi; }
+        __syncthreads();
+        if (tid == 0) {
+            for (int w = 1; w < kPanelThreads / 32; ++w)
+                if (red_v[w] > best || (red_v[w] == best && red_i[w] < bi)) { best = red_v[w]; bi = red_i[w]; }
+            for (int c = 0; c < C; ++c) {          // publish to every CTA of the cluster
+                cluster.map_shared_rank(cand_v, c)[rank] = best;
+                cluster.map_shared_rank(cand_i, c)[rank] = bi;
+            }
+        }
+        cluster.sync();                            // (1) candidates visible everywhere
+        double gbest = cand_v[0];
+        int p = cand_i[0];
+        for (int c = 1; c < C; ++c)
+            if (cand_v[c] > gbest || (cand_v[c] == gbest && cand_i[c] < p)) { gbest = cand_v[c]; p = cand_i[c]; }
+        const int owner_p = (p - k0) / R, owner_t = (kj - k0) / R;
+        if (rank == 0 && tid == 0) {
+            ipiv[kj] = p;
+            if (gbest == 0.0 && info && *info == 0) *info = kj + 1;
+        }
+        if (rank == owner_p && tid < jb) {
+            const double v = P[tid * ldp + (p - r0)];
+            for (int c = 0; c < C; ++c) cluster.map_shared_rank(prow, c)[tid] = v;
+        }
+        if (p != kj && rank == owner_t && tid < jb)
+            cluster.map_shared_rank(trow, owner_p)[tid] = P[tid * ldp + (kj - r0)];
+        cluster.sync();                            // (2) pivot row / displaced row delivered
+        if (p != kj && tid < jb) {
+            if (rank == owner_t) P[tid * ldp + (kj - r0)] = prow[tid];
+            if (rank == owner_p) P[tid * ldp + (p - r0)] = trow[tid];
+        }
+        __syncthreads();
+        const double pv = prow[j];
+        const double inv = pv != 0.0 ? 1.0 / pv : 0.0;
+        for (int i = tid; i < nrows; i += kPanelThreads) {
+            if (r0 + i > kj) {
+                const double l = P[j * ldp + i] * inv;
+                P[j * ldp + i] = l;
+                for (int c = j + 1; c < jb; ++c) P[c * ldp + i] = fma(-l, prow[c], P[c * ldp + i]);
+            }
+        }
+        __syncthreads();
+    }
+    for (int e = tid; e < nrows * jb; e += kPanelThreads) {
+        const int c = e / nrows, i = e - c * nrows;
+        A[(long long)(k0 + c) * lda + r0 + i] = P[c * ldp + i];
+    }
+    cluster.sync();                                // no CTA exits while a neighbour may still address its smem
+}
+
 // Apply the panel's interchanges to the columns right of the panel and solve U12 = L11^-1 A12.
 // One CTA handles 64 columns.
 __global__ void __launch_bounds__(256) swap_trsm_kernel(int n, int k0, int jb, double* __restrict__ A, int lda,
@@ -286,15 +403,16 @@ __global__ void __launch_bounds__(256) gemm_kernel(int M, int N, int K, const do
 
 // ---- triangular solves with the blocked factors (one CTA; panel-by-panel) --------------------------------
 __global__ void __launch_bounds__(1024) apply_kernel(int n, const double* __restrict__ LU, int lda, const int* __restrict__ ipiv,
-                                                      double* __restrict__ b, int nrhs, int ldb) {
+                                                      double* __restrict__ b, int nrhs, int ldb, int cluster,
+                                                      unsigned long long smem_cap) {
     __shared__ double xs[kNB];
     __shared__ double D[kNB][kNB + 1];
     const int tid = threadIdx.x, nt = blockDim.x;
     for (int r = 0; r < nrhs; ++r) {
         double* x = b + (long long)r * ldb;
-        // forward: P, L
-        for (int k0 = 0; k0 < n; k0 += kNB) {
-            const int jb = min(kNB, n - k0);
+        // forward: P, L  (same panel schedule as the factorisation)
+        for (int k0 = 0, jb = 0; k0 < n; k0 += jb) {
+            jb = panel_width_hd(n, k0, cluster, smem_cap);
             __syncthreads();
             for (int e = tid; e < jb * jb; e += nt) {
                 const int c = e / jb, i = e - c * jb;
@@ -354,13 +472,91 @@ __global__ void __launch_bounds__(1024) apply_kernel(int n, const double* __rest
 
 __global__ void zero_info_kernel(int* info) { if (info) *info = 0; }
 
+struct PanelConfig {
+    int cluster = 0;          // CTAs per cluster (0: cluster panel unavailable -> single-CTA panel)
+    size_t smem_cap = 0;      // usable dynamic shared memory per CTA
+};
+
+const PanelConfig& panel_config() {
+    static PanelConfig cfg;
+    static bool done = false;
+    if (done) return cfg;
+    done = true;
+    const size_t want = 200 * 1024;
+    if (cudaFuncSetAttribute(panel_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want) != cudaSuccess) {
+        cudaGetLastError();
+        return cfg;
+    }
+    cudaFuncSetAttribute(panel_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    cudaGetLastError();
+    for (int c : {16, 8, 4, 2}) {
+        cudaLaunchConfig_t lc{};
+        lc.gridDim = dim3(c);
+        lc.blockDim = dim3(kPanelThreads);
+        lc.dynamicSmemBytes = want;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = c; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        lc.attrs = at; lc.numAttrs = 1;
+        int nclusters = 0;
+        if (cudaOccupancyMaxActiveClusters(&nclusters, panel_cluster_kernel, &lc) == cudaSuccess && nclusters >= 1) {
+            cfg.cluster = c;
+            cfg.smem_cap = want;
+            break;
+        }
+        cudaGetLastError();
+    }
+    return cfg;
+}
+
+// Panel width at column k0 of an n x n factorisation.  A pure function of (n, k0) and the device's cluster
+// configuration, so that gpb_lu_apply replays exactly the panels gpb_lu_factor used.
+int panel_width(int n, int k0) {
+    const PanelConfig& cfg = panel_config();
+    return panel_width_hd(n, k0, cfg.cluster, (unsigned long long)cfg.smem_cap);
+}
+
+bool panel_fits_cluster(int n, int k0, int jb) {
+    const PanelConfig& cfg = panel_config();
+    if (cfg.cluster == 0) return false;
+    const long long m = n - k0;
+    const long long R = (m + cfg.cluster - 1) / cfg.cluster;
+    return (size_t)(R + 2) * jb * sizeof(double) <= cfg.smem_cap;
+}
+
+int launch_panel(int n, int k0, int jb, double* A, int lda, int* ipiv, int* info, cudaStream_t s) {
+    if (!panel_fits_cluster(n, k0, jb)) {
+        panel_kernel<<<1, 1024, 0, s>>>(n, k0, jb, A, lda, ipiv, info);
+        GPB_LAUNCH_CHECK();
+        return GPB_OK;
+    }
+    const PanelConfig& cfg = panel_config();
+    const int m = n - k0;
+    int R = (m + cfg.cluster - 1) / cfg.cluster;
+    if (R < 1) R = 1;
+    const int ldp = (R + 1) & ~1;
+    cudaLaunchConfig_t lc{};
+    lc.gridDim = dim3(cfg.cluster);
+    lc.blockDim = dim3(kPanelThreads);
+    lc.dynamicSmemBytes = (size_t)ldp * jb * sizeof(double);
+    lc.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = cfg.cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    lc.attrs = at; lc.numAttrs = 1;
+    GPB_CHECK_CUDA(cudaLaunchKernelEx(&lc, panel_cluster_kernel, n, k0, jb, A, lda, ipiv, info, R, ldp));
+    ++g_gpb_launches;
+    return GPB_OK;
+}
+
+
 int factor_blocked(int n, double* A, int lda, int* ipiv, int* info, cudaStream_t s) {
     zero_info_kernel<<<1, 1, 0, s>>>(info);
     GPB_LAUNCH_CHECK();
-    for (int k0 = 0; k0 < n; k0 += kNB) {
-        const int jb = (n - k0 < kNB) ? n - k0 : kNB;
-        panel_kernel<<<1, 1024, 0, s>>>(n, k0, jb, A, lda, ipiv, info);
-        GPB_LAUNCH_CHECK();
+    for (int k0 = 0; k0 < n;) {
+        const int jb = panel_width(n, k0);
+        int rc = launch_panel(n, k0, jb, A, lda, ipiv, info, s);
+        if (rc) return rc;
         const int nright = n - k0 - jb;
         if (nright > 0) {
             swap_trsm_kernel<<<(nright + 63) / 64, 256, 0, s>>>(n, k0, jb, A, lda, ipiv);
@@ -371,6 +567,7 @@ int factor_blocked(int n, double* A, int lda, int* ipiv, int* info, cudaStream_t
                                              A + (long long)(k0 + jb) * lda + k0, A + (long long)(k0 + jb) * lda + k0 + jb, lda);
             GPB_LAUNCH_CHECK();
         }
+        k0 += jb;
     }
     return GPB_OK;
 }
@@ -397,7 +594,9 @@ extern "C" int gpb_lu_factor(int n, double* A, int lda, int* ipiv, int* info, vo
 
 extern "C" int gpb_lu_apply(int n, const double* LU, int lda, const int* ipiv, double* b, int nrhs, int ldb, void* stream) {
     GPB_REQUIRE(n > 0 && LU && ipiv && b && lda >= n && ldb >= n && nrhs >= 1, "bad arguments");
-    apply_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(n, LU, lda, ipiv, b, nrhs, ldb);
+    const PanelConfig& cfg = panel_config();
+    apply_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(n, LU, lda, ipiv, b, nrhs, ldb, cfg.cluster,
+                                                       (unsigned long long)cfg.smem_cap);
     GPB_LAUNCH_CHECK();
     return GPB_OK;
 }
