@@ -25,6 +25,7 @@ import numpy as np
 import torch
 
 from .. import _lib
+from .comm import Comm
 from .data import (BlockSolutionType, CombinedScalarFieldsOutput, DualContouringData, DualContouringMesh, EngineGrid,
                    ExportedFields, GenericGrid, InputDataDescriptor, InterpolationInput, InterpolationOptions,
                    InterpOutput, OctreeLevel, RawArraysSolution, RegularGrid, ScalarFieldOutput, Solutions,
@@ -244,8 +245,12 @@ class B200Engine:
     # -- all stacks on one domain ----------------------------------------------------------------------------
     def interpolate_all_fields(self, ii: InterpolationInput, options: InterpolationOptions, desc: InputDataDescriptor,
                                segments: List[Segment], weights_cache: List[Optional[torch.Tensor]],
-                               gradient: Optional[bool] = None, tables: Optional[List[StackTables]] = None
-                               ) -> FieldsOnDevice:
+                               gradient: Optional[bool] = None, tables: Optional[List[StackTables]] = None,
+                               comm: Optional[Comm] = None) -> FieldsOnDevice:
+        """`segments` are this rank's evaluation points.  With a multi-rank `comm`, rank 0 solves and broadcasts
+        the weights and the fault-block minima are all-reduced, so every rank sees the values a single-GPU run
+        would produce."""
+        comm = comm or Comm()
         ko = options.kernel_options
         if gradient is None:
             gradient = bool(options.evaluation_options.compute_scalar_gradient)
@@ -280,11 +285,15 @@ class B200Engine:
                 st.set_faults(None)
             cond = None
             if weights_cache[i] is None:
-                A, b = self.assemble(st)
-                if getattr(ko, "compute_condition_number", False):
-                    cond = float(torch.linalg.cond(A).item())
-                weights_cache[i] = self.solve(A, b)
-                del A
+                if comm.rank == 0:
+                    A, b = self.assemble(st)
+                    if getattr(ko, "compute_condition_number", False):
+                        cond = float(torch.linalg.cond(A).item())
+                    w_new = self.solve(A, b)
+                    del A
+                else:
+                    w_new = self.empty(st.n)
+                weights_cache[i] = comm.broadcast(w_new, src=0)
             w = weights_cache[i]
             if w.shape[0] != st.n:
                 raise ValueError(f"stack {i}: cached weights have length {w.shape[0]}, system size is {st.n}")
@@ -309,6 +318,7 @@ class B200Engine:
                                              _ptr(block[i]), self.stream))
             if rel[i] == StackRelationType.FAULT.value:
                 _lib.check(self.lib.gpb_min(_ptr(block[i]), L, _ptr(tmp_min), self.stream))
+                comm.all_reduce_min(tmp_min)
                 _lib.check(self.lib.gpb_shift(_ptr(block[i]), L, _ptr(tmp_min), _ptr(values_everywhere[i]), self.stream))
             else:
                 values_everywhere[i].copy_(block[i])
@@ -345,12 +355,17 @@ class B200Engine:
                                               self.stream))
         return out
 
-    def refine(self, centers: torch.Tensor, d: np.ndarray, lith_corners: torch.Tensor, fault_corners: torch.Tensor,
-               force_all: bool) -> Tuple[torch.Tensor, torch.Tensor]:
-        nv = centers.shape[1]
+    def mark(self, nv: int, lith_corners: torch.Tensor, fault_corners: torch.Tensor, force_all: bool) -> torch.Tensor:
+        """Refinement test on nv voxels given the ids at their 8 corners each (uint8 marks)."""
         mark = self.empty(nv, dtype=torch.uint8)
-        _lib.check(self.lib.gpb_mark_voxels(_ptr(lith_corners), _ptr(fault_corners), nv, int(force_all), _ptr(mark),
-                                            self.stream))
+        if nv:
+            _lib.check(self.lib.gpb_mark_voxels(_ptr(lith_corners), _ptr(fault_corners), nv, int(force_all), _ptr(mark),
+                                                self.stream))
+        return mark
+
+    def emit(self, centers: torch.Tensor, d: np.ndarray, mark: torch.Tensor) -> torch.Tensor:
+        """Children (8 per marked voxel, parent order preserved) of the marked voxels."""
+        nv = centers.shape[1]
         n_children = C.c_longlong(0)
         _lib.check(self.lib.gpb_emit_children(_ptr(centers), nv, nv, _ptr(mark), d[0] / 4, d[1] / 4, d[2] / 4, None, 0,
                                               C.byref(n_children), self.stream))
@@ -359,7 +374,28 @@ class B200Engine:
         if nc:
             _lib.check(self.lib.gpb_emit_children(_ptr(centers), nv, nv, _ptr(mark), d[0] / 4, d[1] / 4, d[2] / 4,
                                                   _ptr(children), nc, C.byref(n_children), self.stream))
-        return children, mark
+        return children
+
+    def gather_fields(self, f: FieldsOnDevice, totals: Sequence[int], comm: Comm) -> FieldsOnDevice:
+        """All-gather a range-sharded level into whole arrays (segment by segment; the surface-point tail is
+        replicated).  Identity on a single rank."""
+        if comm.world == 1:
+            return f
+        n_sp = f.Z.shape[1] - f.grid_size
+
+        def full(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+            if t is None:
+                return None
+            parts, off = [], 0
+            for seg, tot in zip(f.segments, totals):
+                parts.append(comm.all_gather_cat(t[..., off:off + seg.m].contiguous(), tot))
+                off += seg.m
+            parts.append(t[..., off:off + n_sp])
+            return torch.cat(parts, dim=-1).contiguous()
+
+        segs = [Segment(sg.name, int(tot)) for sg, tot in zip(f.segments, totals)]
+        return FieldsOnDevice(segs, int(sum(totals)), full(f.Z), full(f.G), full(f.block), full(f.final_block),
+                              full(f.faults_block), full(f.squeezed), full(f.mask), f.isovalues, f.weights, f.cond, f.srcs)
 
 
 # ------------------------------------------------------------------------------------------------ materialisation
@@ -447,9 +483,11 @@ def triangulate(valid: np.ndarray, ijk: np.ndarray) -> np.ndarray:
 # ------------------------------------------------------------------------------------------------ entry point
 def compute_model(interpolation_input: InterpolationInput, options: InterpolationOptions,
                   data_descriptor: InputDataDescriptor, geophysics_input=None, *, device: Optional[int] = None,
-                  engine: Optional[B200Engine] = None) -> Solutions:
+                  engine: Optional[B200Engine] = None, comm: Optional[Comm] = None) -> Solutions:
     """Drop-in for ``gempy_engine.compute_model`` (same positional/keyword signature; the keyword-only extras
-    select the CUDA device).  Raises ``NotImplementedError`` for geophysics input."""
+    select the CUDA device and, for one-process-per-GPU runs, the torch.distributed group).  Every rank returns
+    the same, complete ``Solutions``.  Raises ``NotImplementedError`` for geophysics input."""
+    comm = comm or Comm()
     if geophysics_input is not None or interpolation_input.grid.geophysics_grid is not None:
         raise NotImplementedError("forward gravity is outside the B200 backend's scope (SURVEY.md section 8f)")
     eng = engine or B200Engine(device)
@@ -473,14 +511,21 @@ def compute_model(interpolation_input: InterpolationInput, options: Interpolatio
     n_levels = int(eo.number_octree_levels)
     dc_level = min(int(eo.number_octree_levels_surface), n_levels) - 1 if eo.mesh_extraction else -1
     centers, d = regular_centers_device(grid.octree_grid, eng.device)
-    extra: List[Segment] = []
+    extra_full: List[Segment] = []
     if grid.dense_grid is not None:
-        extra.append(Segment("dense_grid", grid.dense_grid.n_points, grid=regular_descriptor(grid.dense_grid)))
+        extra_full.append(Segment("dense_grid", grid.dense_grid.n_points, grid=regular_descriptor(grid.dense_grid)))
     for name in ("custom_grid", "topography", "sections"):
         g = getattr(grid, name)
         if g is not None:
-            extra.append(Segment(name, g.n_points,
-                                 xyz=torch.as_tensor(np.ascontiguousarray(g.values.T), dtype=F64, device=eng.device)))
+            extra_full.append(Segment(name, g.n_points,
+                                      xyz=torch.as_tensor(np.ascontiguousarray(g.values.T), dtype=F64, device=eng.device)))
+
+    def local_part(seg: Segment) -> Segment:
+        """This rank's contiguous share of a segment."""
+        i0, i1 = comm.shard(seg.m)
+        if seg.grid is not None:
+            return Segment(seg.name, i1 - i0, grid=seg.grid, i0=seg.i0 + i0)
+        return Segment(seg.name, i1 - i0, xyz=seg.xyz[:, i0:i1].contiguous())
 
     octree_levels: List[OctreeLevel] = []
     levels_host = []
@@ -488,14 +533,30 @@ def compute_model(interpolation_input: InterpolationInput, options: Interpolatio
     dc_payload = None
     for lvl in range(n_levels):
         need_corners = (lvl < n_levels - 1) or (lvl == dc_level)
-        segs = [Segment("octree_grid", centers.shape[1], xyz=centers)]
+        nv = centers.shape[1]
+        v0, v1 = comm.shard(nv)
+        centers_loc = centers[:, v0:v1].contiguous()
+        segs = [Segment("octree_grid", v1 - v0, xyz=centers_loc)]
+        totals = [nv]
         if lvl == 0:
-            segs += extra
+            for sg in extra_full:
+                segs.append(local_part(sg))
+                totals.append(sg.m)
         corners = None
         if need_corners:
-            corners = eng.corners_of(centers, d)
-            segs.append(Segment("corners", corners.shape[1], xyz=corners))
-        f = eng.interpolate_all_fields(ii, options, desc, segs, cache, tables=tables)
+            corners_loc = eng.corners_of(centers_loc, d)
+            segs.append(Segment("corners", corners_loc.shape[1], xyz=corners_loc))
+            totals.append(8 * nv)
+            corners = corners_loc if comm.world == 1 else eng.corners_of(centers, d)
+        f_loc = eng.interpolate_all_fields(ii, options, desc, segs, cache, tables=tables, comm=comm)
+        # ---- refinement marks: local test, all-gathered so that every rank emits the identical child list
+        mark_full = None
+        if lvl < n_levels - 1:
+            csl = f_loc.seg_slice("corners")
+            mark_loc = eng.mark(v1 - v0, f_loc.final_block[csl].contiguous(), f_loc.faults_block[csl].contiguous(),
+                                force_all=lvl < int(eo.octree_min_level))
+            mark_full = comm.all_gather_cat(mark_loc, nv)
+        f = eng.gather_fields(f_loc, totals, comm)
         # ---- host containers of this level
         if lvl == 0:
             og0 = RegularGrid(grid.octree_grid.orthogonal_extent, grid.octree_grid.regular_grid_shape)
@@ -511,7 +572,6 @@ def compute_model(interpolation_input: InterpolationInput, options: Interpolatio
         level = OctreeLevel(grid_centers=lvl_grid, outputs_centers=outs,
                             grid_corners=None if corners is None else EngineGrid.from_xyz_coords(_np(corners).T))
         octree_levels.append(level)
-        nv = centers.shape[1]
         host = {"lith": np.rint(outs[-1].combined_scalar_field.final_block[:nv]),
                 "faults": np.rint(outs[-1].combined_scalar_field.faults_block[:nv]), "selected": None}
         levels_host.append(host)
@@ -519,12 +579,9 @@ def compute_model(interpolation_input: InterpolationInput, options: Interpolatio
             dc_payload = (centers, d.copy(), corners, f)
         if lvl == n_levels - 1:
             break
-        csl = f.seg_slice("corners")
-        children, mark = eng.refine(centers, d, f.final_block[csl].contiguous(), f.faults_block[csl].contiguous(),
-                                    force_all=lvl < int(eo.octree_min_level))
-        level.marked_voxels = _np(mark).astype(bool)
+        level.marked_voxels = _np(mark_full).astype(bool)
         host["selected"] = level.marked_voxels
-        centers = children
+        centers = eng.emit(centers, d, mark_full)
         d = d / 2
 
     meshes = None
