@@ -16,10 +16,10 @@
 //   [ n_ori_pad x {X, Y, Z, w'x, w'y, w'z} ]   w' = -(c_o*gi_res/a) * w
 //   [ tail: mu_z[9] (drift, field), mu_g[9] (drift, gradient), scal[6], w_fault[n_faults] ]
 #include "gpb_common.cuh"
+#include <cstdlib>
 
 namespace {
 
-constexpr int kThreads = 256;
 constexpr int kTileSp = 256;                  // sources per tile: 256 * 32 B = 8 KB
 constexpr int kTileOri = 128;                 // 128 * 48 B = 6 KB
 constexpr int kTileBytes = kTileSp * 32;      // stage buffer size
@@ -92,8 +92,8 @@ __device__ __forceinline__ void cov_ori(double u, double t, double& kp, double& 
     }
 }
 
-template <int KERNEL, bool GRAD, bool REGULAR, int P>
-__global__ void __launch_bounds__(kThreads, (P <= 2) ? 2 : 1)
+template <int KERNEL, bool GRAD, bool REGULAR, int P, int kThreads, int kMinBlocks>
+__global__ void __launch_bounds__(kThreads, kMinBlocks)
 eval_kernel(const EvalParams prm) {
     __shared__ __align__(128) double stage[2][kTileBytes / 8];
     __shared__ __align__(8) uint64_t full[2];
@@ -320,20 +320,39 @@ __global__ void pack_kernel(const PackParams p) {
     }
 }
 
-template <int KERNEL, bool GRAD, bool REGULAR>
-int launch_eval(const EvalParams& prm, cudaStream_t stream) {
-    constexpr int P = GRAD ? 4 : 4;
-    const long long chunk = (long long)kThreads * P;
+template <int KERNEL, bool GRAD, bool REGULAR, int P, int T, int MINB>
+int launch_eval_cfg(const EvalParams& prm, cudaStream_t stream) {
+    const long long chunk = (long long)T * P;
     const long long n_chunks = (prm.m + chunk - 1) / chunk;
     if (n_chunks == 0) return GPB_OK;
     int occ = 1;
-    GPB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, eval_kernel<KERNEL, GRAD, REGULAR, P>, kThreads, 0));
+    GPB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, eval_kernel<KERNEL, GRAD, REGULAR, P, T, MINB>, T, 0));
     if (occ < 1) occ = 1;
     long long grid = (long long)gpb_sm_count() * occ;
     if (grid > n_chunks) grid = n_chunks;
-    eval_kernel<KERNEL, GRAD, REGULAR, P><<<(unsigned)grid, kThreads, 0, stream>>>(prm);
+    eval_kernel<KERNEL, GRAD, REGULAR, P, T, MINB><<<(unsigned)grid, T, 0, stream>>>(prm);
     GPB_LAUNCH_CHECK();
     return GPB_OK;
+}
+
+// Launch configuration: P points per thread, T threads per CTA, MINB resident CTAs per SM.
+// GPB_EVAL_VARIANT (environment, tuning only) selects alternative configurations of the cubic kernel.
+template <int KERNEL, bool GRAD, bool REGULAR>
+int launch_eval(const EvalParams& prm, cudaStream_t stream) {
+    if constexpr (KERNEL == GPB_KERNEL_CUBIC) {
+        static const int variant = [] { const char* e = getenv("GPB_EVAL_VARIANT"); return e ? atoi(e) : 0; }();
+        switch (variant) {
+            case 1: return launch_eval_cfg<KERNEL, GRAD, REGULAR, 2, 256, 2>(prm, stream);
+            case 2: return launch_eval_cfg<KERNEL, GRAD, REGULAR, 4, 384, 1>(prm, stream);
+            case 3: return launch_eval_cfg<KERNEL, GRAD, REGULAR, 2, 512, 1>(prm, stream);
+            case 4: return launch_eval_cfg<KERNEL, GRAD, REGULAR, 4, 128, 3>(prm, stream);
+            case 5: return launch_eval_cfg<KERNEL, GRAD, REGULAR, 2, 128, 4>(prm, stream);
+            case 6: return launch_eval_cfg<KERNEL, GRAD, REGULAR, 3, 128, 3>(prm, stream);
+            case 7: return launch_eval_cfg<KERNEL, GRAD, REGULAR, 4, 64, 6>(prm, stream);
+            default: break;
+        }
+    }
+    return launch_eval_cfg<KERNEL, GRAD, REGULAR, 4, 256, 1>(prm, stream);
 }
 
 template <bool REGULAR>

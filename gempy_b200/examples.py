@@ -224,26 +224,11 @@ def synthetic_stress(n_sp_per_surface: int = 1000, n_surfaces: int = 4, n_ori: i
 def synthetic_multi_fault(n_faults: int = 10, n_series: int = 5, surfaces_per_series: int = 3,
                           n_sp_per_surface: int = 100, n_ori_per_series: int = 30, n_sp_fault: int = 20,
                           n_ori_fault: int = 2, refinement: int = 8, seed: int = 1234) -> ExampleModel:
-    """BASELINE config 4: planar fault stacks with random strike/dip (chained,
-    upper-triangular fault relations) + stratigraphic series carrying fault-drift terms."""
+    """BASELINE config 4: planar fault stacks with random strike/dip + stratigraphic series
+    carrying one fault-drift column per fault."""
     rng = np.random.default_rng(seed)
     sp, op, og = {}, {}, {}
-    stacks = []
-    for f in range(n_faults):
-        nm = f"fault{f}"
-        strike = rng.uniform(0, np.pi)
-        dip = rng.uniform(np.deg2rad(55), np.deg2rad(85))
-        n = np.array([np.cos(strike) * np.sin(dip), np.sin(strike) * np.sin(dip), np.cos(dip)])
-        c = rng.uniform(-0.3, 0.3, size=3) * np.array([1, 1, 0.2])
-        # points on the plane n.(x-c)=0
-        u = np.cross(n, [0, 0, 1.0]); u /= np.linalg.norm(u)
-        v = np.cross(n, u)
-        ab = rng.uniform(-0.4, 0.4, size=(n_sp_fault, 2))
-        sp[nm] = c + ab[:, :1] * u + ab[:, 1:] * v
-        ab = rng.uniform(-0.3, 0.3, size=(n_ori_fault, 2))
-        op[nm] = c + ab[:, :1] * u + ab[:, 1:] * v
-        og[nm] = np.repeat(n[None], n_ori_fault, 0)
-        stacks.append((f"Fault{f}", [nm], F))
+    strat_stacks = []
     zs = np.linspace(0.35, -0.35, n_series * surfaces_per_series)
     for s in range(n_series):
         names = []
@@ -266,11 +251,52 @@ def synthetic_multi_fault(n_faults: int = 10, n_series: int = 5, surfaces_per_se
             nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
             op[nm] = np.column_stack([xo, height(z0, xo[:, 0], xo[:, 1])])
             og[nm] = nrm
-        stacks.append((f"Series{s}", names, E))
+        strat_stacks.append((f"Series{s}", names, E))
+
+    def increments(side):
+        """Rows rest - ref of a 0/1 side function, per series: what a fault-drift column looks like."""
+        cols = []
+        for _, names, _ in strat_stacks:
+            cols.append(np.concatenate([side[nm][1:] - side[nm][0] for nm in names]))
+        return cols
+
+    fault_stacks, accepted = [], [[] for _ in strat_stacks]
+    f = 0
+    while f < n_faults:
+        strike = rng.uniform(0, np.pi)
+        dip = rng.uniform(np.deg2rad(55), np.deg2rad(85))
+        n = np.array([np.cos(strike) * np.sin(dip), np.sin(strike) * np.sin(dip), np.cos(dip)])
+        c = rng.uniform(-0.3, 0.3, size=3) * np.array([1, 1, 0.2])
+        # the fault must split every series' surface points in a way no earlier fault (or combination) already does,
+        # otherwise two fault-drift columns coincide and the co-kriging system is singular
+        side = {nm: ((sp[nm] - c) @ n > 0).astype(float) for _, names, _ in strat_stacks for nm in names}
+        cols = increments(side)
+        ok = True
+        for k, col in enumerate(cols):
+            M = np.stack(accepted[k] + [col], axis=1)
+            if np.linalg.matrix_rank(M) < M.shape[1]:
+                ok = False
+        if not ok:
+            continue
+        for k, col in enumerate(cols):
+            accepted[k].append(col)
+        nm = f"fault{f}"
+        u = np.cross(n, [0, 0, 1.0]); u /= np.linalg.norm(u)
+        v = np.cross(n, u)
+        ab = rng.uniform(-0.4, 0.4, size=(n_sp_fault, 2))
+        sp[nm] = c + ab[:, :1] * u + ab[:, 1:] * v
+        ab = rng.uniform(-0.3, 0.3, size=(n_ori_fault, 2))
+        op[nm] = c + ab[:, :1] * u + ab[:, 1:] * v
+        og[nm] = np.repeat(n[None], n_ori_fault, 0)
+        fault_stacks.append((f"Fault{f}", [nm], F))
+        f += 1
+    stacks = fault_stacks + strat_stacks
     n_st = n_faults + n_series
     fr = np.zeros((n_st, n_st), bool)
     for f in range(n_faults):
-        fr[f, f + 1:] = True          # every fault offsets all younger-listed faults after it and all series
+        fr[f, n_faults:] = True       # every fault offsets every stratigraphic series (fault planes span the model,
+                                      # so each series has surface points on both sides and the drift columns are
+                                      # independent); faults do not offset each other
     ident = Transform(np.zeros(3), np.zeros(3), np.ones(3))
     return build_model("synthetic_multi_fault", sp, op, og, stacks, [-0.5, 0.5, -0.5, 0.5, -0.5, 0.5],
                        refinement=refinement, fault_relations=fr, transform=ident, legacy_octree_init=True)
