@@ -320,6 +320,195 @@ __global__ void pack_kernel(const PackParams p) {
     }
 }
 
+
+// ---- regular-grid "z-run" variant ------------------------------------------------------------------------
+// Every thread owns P consecutive cells of one (x, y) column of the regular grid (z is the fastest axis,
+// gempy/core/data/grid_modules/regular_grid.py:58-71).  dx, dy, dx^2 + dy^2 and (for orientations) dx w'x + dy w'y
+// are computed once per (thread, source) and shared by the P points: 3 (surface points) / 4.5 (orientations)
+// fewer FP64 instructions per pair at P = 4.  Requires nz % P == 0, i0 % P == 0, m % P == 0.
+template <int KERNEL, bool GRAD, int P, int kThreads, int kMinBlocks>
+__global__ void __launch_bounds__(kThreads, kMinBlocks)
+eval_zrun_kernel(const EvalParams prm) {
+    __shared__ __align__(128) double stage[2][kTileBytes / 8];
+    __shared__ __align__(8) uint64_t full[2];
+
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        gpb_mbar_init(&full[0], 1);
+        gpb_mbar_init(&full[1], 1);
+        gpb_fence_mbar_init();
+    }
+    __syncthreads();
+
+    const long long n_sp_tiles = prm.n_sps_pad / kTileSp;
+    const long long n_ori_tiles = prm.n_ori_pad / kTileOri;
+    const long long n_tiles = n_sp_tiles + n_ori_tiles;
+    const double* src_ori = prm.src + 4 * prm.n_sps_pad;
+    const double* tail = src_ori + 6 * prm.n_ori_pad;
+
+    const long long n_runs = prm.m / P;                       // runs of P points
+    const long long n_chunks = (n_runs + kThreads - 1) / kThreads;
+    unsigned long long gt = 0;
+
+    auto issue = [&](long long j, unsigned long long g) {
+        const int b = (int)(g & 1);
+        if (j < n_sp_tiles) {
+            gpb_mbar_expect_tx(&full[b], kTileSp * 32);
+            gpb_bulk_g2s(stage[b], prm.src + 4 * (long long)kTileSp * j, kTileSp * 32, &full[b]);
+        } else {
+            gpb_mbar_expect_tx(&full[b], kTileOri * 48);
+            gpb_bulk_g2s(stage[b], src_ori + 6 * (long long)kTileOri * (j - n_sp_tiles), kTileOri * 48, &full[b]);
+        }
+    };
+
+    for (long long c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+        const long long run = c * kThreads + tid;
+        const bool live = run < n_runs;
+        const long long r = live ? run : n_runs - 1;            // idle tail threads recompute the last run
+        const long long g0 = prm.i0 + r * P;
+        const long long nyz = (long long)prm.grid.ny * prm.grid.nz;
+        const long long ix = g0 / nyz;
+        const long long rem = g0 - ix * nyz;
+        const long long iy = rem / prm.grid.nz;
+        const long long iz0 = rem - iy * prm.grid.nz;
+        const double X = fma((double)ix, prm.grid.dx, prm.grid.x0) * prm.inv_a;
+        const double Y = fma((double)iy, prm.grid.dy, prm.grid.y0) * prm.inv_a;
+        double Zc[P], accZ[P], hx[P], hy[P], hz[P];
+#pragma unroll
+        for (int k = 0; k < P; ++k) {
+            Zc[k] = fma((double)(iz0 + k), prm.grid.dz, prm.grid.z0) * prm.inv_a;
+            accZ[k] = 0.0; hx[k] = 0.0; hy[k] = 0.0; hz[k] = 0.0;
+        }
+
+        if (tid == 0 && n_tiles > 0) issue(0, gt);
+        for (long long j = 0; j < n_tiles; ++j, ++gt) {
+            if (tid == 0 && j + 1 < n_tiles) issue(j + 1, gt + 1);
+            const int b = (int)(gt & 1);
+            gpb_mbar_wait(&full[b], (uint32_t)((gt >> 1) & 1));
+            const double* s = stage[b];
+            if (j < n_sp_tiles) {
+#pragma unroll 2
+                for (int q = 0; q < kTileSp; ++q) {
+                    const double2 a0 = *reinterpret_cast<const double2*>(s + 4 * q);
+                    const double2 a1 = *reinterpret_cast<const double2*>(s + 4 * q + 2);
+                    const double dx = X - a0.x, dy = Y - a0.y;
+                    const double pxy = fma(dy, dy, fma(dx, dx, prm.eps_u));
+#pragma unroll
+                    for (int k = 0; k < P; ++k) {
+                        const double dz = Zc[k] - a1.x;
+                        const double u = fma(dz, dz, pxy);
+                        const double t = gpb_fast_sqrt(u);
+                        double cv, kp;
+                        cov_sp<KERNEL>(u, t, cv, kp);
+                        accZ[k] = fma(a1.y, cv, accZ[k]);
+                        if constexpr (GRAD) {
+                            const double g = a1.y * kp;
+                            hx[k] = fma(g, dx, hx[k]);
+                            hy[k] = fma(g, dy, hy[k]);
+                            hz[k] = fma(g, dz, hz[k]);
+                        }
+                    }
+                }
+                if (j == n_sp_tiles - 1) {
+                    if constexpr (GRAD) {
+                        const double rr = tail[18];
+#pragma unroll
+                        for (int k = 0; k < P; ++k) { hx[k] *= rr; hy[k] *= rr; hz[k] *= rr; }
+                    }
+                }
+            } else {
+#pragma unroll 2
+                for (int q = 0; q < kTileOri; ++q) {
+                    const double2 a0 = *reinterpret_cast<const double2*>(s + 6 * q);
+                    const double2 a1 = *reinterpret_cast<const double2*>(s + 6 * q + 2);
+                    const double2 a2 = *reinterpret_cast<const double2*>(s + 6 * q + 4);
+                    const double dx = X - a0.x, dy = Y - a0.y;
+                    const double pxy = fma(dy, dy, fma(dx, dx, prm.eps_u));
+                    const double hwxy = fma(dy, a2.x, dx * a1.y);
+#pragma unroll
+                    for (int k = 0; k < P; ++k) {
+                        const double dz = Zc[k] - a1.x;
+                        const double u = fma(dz, dz, pxy);
+                        const double t = gpb_fast_sqrt(u);
+                        double kp, dd;
+                        cov_ori<KERNEL>(u, t, kp, dd);
+                        const double hw = fma(dz, a2.y, hwxy);
+                        accZ[k] = fma(kp, hw, accZ[k]);
+                        if constexpr (GRAD) {
+                            const double c1 = -(dd * gpb_fast_rcp(u + prm.eps_reg)) * hw;
+                            hx[k] = fma(c1, dx, fma(kp, a1.y, hx[k]));
+                            hy[k] = fma(c1, dy, fma(kp, a2.x, hy[k]));
+                            hz[k] = fma(c1, dz, fma(kp, a2.y, hz[k]));
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+        }
+
+        const double inv_agi = tail[19];
+        double zo[P], g0o[P], g1o[P], g2o[P];
+#pragma unroll
+        for (int k = 0; k < P; ++k) {
+            double z = accZ[k];
+            double g0v = hx[k] * inv_agi, g1v = hy[k] * inv_agi, g2v = hz[k] * inv_agi;
+            if (prm.n_drift >= 3) {
+                z = fma(tail[0], X, fma(tail[1], Y, fma(tail[2], Zc[k], z)));
+                if constexpr (GRAD) { g0v += tail[9]; g1v += tail[10]; g2v += tail[11]; }
+            }
+            if (prm.n_drift == 9) {
+                z = fma(tail[3], X * X, fma(tail[4], Y * Y, fma(tail[5], Zc[k] * Zc[k], z)));
+                z = fma(tail[6], X * Y, fma(tail[7], X * Zc[k], fma(tail[8], Y * Zc[k], z)));
+                if constexpr (GRAD) {
+                    g0v += 2.0 * tail[12] * X + tail[15] * Y + tail[16] * Zc[k];
+                    g1v += 2.0 * tail[13] * Y + tail[15] * X + tail[17] * Zc[k];
+                    g2v += 2.0 * tail[14] * Zc[k] + tail[16] * X + tail[17] * Y;
+                }
+            }
+            if (live)
+                for (int f = 0; f < prm.n_faults; ++f)
+                    z = fma(tail[kTailDoubles + f], prm.fault_vals[(long long)f * prm.ld_fault + run * P + k], z);
+            zo[k] = z; g0o[k] = g0v; g1o[k] = g1v; g2o[k] = g2v;
+        }
+        if (live) {
+            const long long o = run * P;
+            // P consecutive doubles per thread: 16-byte vector stores (alignment checked by the launcher)
+#pragma unroll
+            for (int k = 0; k < P; k += 2) {
+                *reinterpret_cast<double2*>(prm.Z + o + k) = make_double2(zo[k], zo[k + 1]);
+                if constexpr (GRAD) {
+                    *reinterpret_cast<double2*>(prm.gx + o + k) = make_double2(g0o[k], g0o[k + 1]);
+                    *reinterpret_cast<double2*>(prm.gy + o + k) = make_double2(g1o[k], g1o[k + 1]);
+                    *reinterpret_cast<double2*>(prm.gz + o + k) = make_double2(g2o[k], g2o[k + 1]);
+                }
+            }
+        }
+    }
+}
+
+template <int KERNEL, bool GRAD, int P, int T, int MINB>
+int launch_zrun_cfg(const EvalParams& prm, cudaStream_t stream) {
+    const long long n_runs = prm.m / P;
+    const long long n_chunks = (n_runs + T - 1) / T;
+    if (n_chunks == 0) return GPB_OK;
+    int occ = 1;
+    GPB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, eval_zrun_kernel<KERNEL, GRAD, P, T, MINB>, T, 0));
+    if (occ < 1) occ = 1;
+    long long grid = (long long)gpb_sm_count() * occ;
+    if (grid > n_chunks) grid = n_chunks;
+    eval_zrun_kernel<KERNEL, GRAD, P, T, MINB><<<(unsigned)grid, T, 0, stream>>>(prm);
+    GPB_LAUNCH_CHECK();
+    return GPB_OK;
+}
+
+// z-run eligibility: whole runs of P cells inside one (x, y) column, 16-byte aligned outputs
+template <int P>
+bool zrun_ok(const EvalParams& prm) {
+    auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    return prm.grid.nz % P == 0 && prm.i0 % P == 0 && prm.m % P == 0 && prm.m >= P && al(prm.Z) &&
+           (prm.gx == nullptr || (al(prm.gx) && al(prm.gy) && al(prm.gz)));
+}
+
 template <int KERNEL, bool GRAD, bool REGULAR, int P, int T, int MINB>
 int launch_eval_cfg(const EvalParams& prm, cudaStream_t stream) {
     const long long chunk = (long long)T * P;
@@ -339,8 +528,17 @@ int launch_eval_cfg(const EvalParams& prm, cudaStream_t stream) {
 // GPB_EVAL_VARIANT (environment, tuning only) selects alternative configurations of the cubic kernel.
 template <int KERNEL, bool GRAD, bool REGULAR>
 int launch_eval(const EvalParams& prm, cudaStream_t stream) {
+    static const int variant = [] { const char* e = getenv("GPB_EVAL_VARIANT"); return e ? atoi(e) : 0; }();
+    if constexpr (REGULAR) {
+        // regular grids: z-run kernel whenever the range is made of whole runs (variant 100 forces the generic one)
+        if (variant == 8 && zrun_ok<8>(prm)) return launch_zrun_cfg<KERNEL, GRAD, 8, 256, 1>(prm, stream);
+        if (variant == 9 && zrun_ok<8>(prm)) return launch_zrun_cfg<KERNEL, GRAD, 8, 128, 2>(prm, stream);
+        if (variant == 10 && zrun_ok<4>(prm)) return launch_zrun_cfg<KERNEL, GRAD, 4, 384, 1>(prm, stream);
+        if (variant == 11 && zrun_ok<4>(prm)) return launch_zrun_cfg<KERNEL, GRAD, 4, 128, 3>(prm, stream);
+        if (variant == 12 && zrun_ok<8>(prm)) return launch_zrun_cfg<KERNEL, GRAD, 8, 192, 1>(prm, stream);
+        if (variant < 100 && zrun_ok<4>(prm)) return launch_zrun_cfg<KERNEL, GRAD, 4, 256, 1>(prm, stream);
+    }
     if constexpr (KERNEL == GPB_KERNEL_CUBIC) {
-        static const int variant = [] { const char* e = getenv("GPB_EVAL_VARIANT"); return e ? atoi(e) : 0; }();
         switch (variant) {
             case 1: return launch_eval_cfg<KERNEL, GRAD, REGULAR, 2, 256, 2>(prm, stream);
             case 2: return launch_eval_cfg<KERNEL, GRAD, REGULAR, 4, 384, 1>(prm, stream);

@@ -26,7 +26,7 @@ import torch
 
 from .. import _lib
 from .comm import Comm
-from .data import (BlockSolutionType, CombinedScalarFieldsOutput, DualContouringData, DualContouringMesh, EngineGrid,
+from .data import (BlockSolutionType, CombinedScalarFieldsOutput, Deferred, DualContouringData, DualContouringMesh, EngineGrid,
                    ExportedFields, GenericGrid, InputDataDescriptor, InterpolationInput, InterpolationOptions,
                    InterpOutput, OctreeLevel, RawArraysSolution, RegularGrid, ScalarFieldOutput, Solutions,
                    StackRelationType)
@@ -404,16 +404,17 @@ def _np(t: Optional[torch.Tensor]) -> Optional[np.ndarray]:
 
 
 def _level_outputs(f: FieldsOnDevice, grid: EngineGrid, rel_enum: Sequence) -> List[InterpOutput]:
-    Z, block = _np(f.Z), _np(f.block)
-    G = _np(f.G)
-    final_block, faults_block = _np(f.final_block), _np(f.faults_block)
-    squeezed, mask = _np(f.squeezed).astype(bool), _np(f.mask).astype(bool)
+    """Host containers over the device results; every array is copied on first access only."""
+    D = Deferred
+    fb = D(lambda: _np(f.final_block))
+    fa = D(lambda: _np(f.faults_block))
     outs = []
-    for i in range(Z.shape[0]):
-        ef = ExportedFields(Z[i], None if G is None else G[i, 0], None if G is None else G[i, 1],
-                            None if G is None else G[i, 2], f.grid_size, _np(f.isovalues[i]))
-        sfo = ScalarFieldOutput(_np(f.weights[i]), grid, ef, block[i][None, :], rel_enum[i], mask[i])
-        comb = CombinedScalarFieldsOutput(squeezed[i], final_block, faults_block)
+    for i in range(f.Z.shape[0]):
+        g = (None, None, None) if f.G is None else tuple(D(lambda i=i, a=a: _np(f.G[i, a])) for a in range(3))
+        ef = ExportedFields(D(lambda i=i: _np(f.Z[i])), g[0], g[1], g[2], f.grid_size, D(lambda i=i: _np(f.isovalues[i])))
+        sfo = ScalarFieldOutput(D(lambda i=i: _np(f.weights[i])), grid, ef, D(lambda i=i: _np(f.block[i])[None, :]),
+                                rel_enum[i], D(lambda i=i: _np(f.mask[i]).astype(bool)))
+        comb = CombinedScalarFieldsOutput(D(lambda i=i: _np(f.squeezed[i]).astype(bool)), fb, fa)
         outs.append(InterpOutput(sfo, comb))
     return outs
 
@@ -422,7 +423,7 @@ def _fill_regular_from_octree(levels_host, base_shape: np.ndarray, key) -> np.nd
     """Dense array at the finest octree resolution: level-0 values upsampled, refined voxels overwritten by their
     children (the engine's octree -> regular fill used by RawArraysSolution)."""
     shape = np.asarray(base_shape, dtype=int)
-    vals = key(levels_host[0]).reshape(shape)
+    vals = np.asarray(key(levels_host[0])).reshape(shape)
     # index arrays of the voxels of each level inside the level's full lattice
     ijk = np.stack(np.meshgrid(*[np.arange(s) for s in shape], indexing="ij"), axis=-1).reshape(-1, 3)
     dense = vals
@@ -558,22 +559,25 @@ def compute_model(interpolation_input: InterpolationInput, options: Interpolatio
             mark_full = comm.all_gather_cat(mark_loc, nv)
         f = eng.gather_fields(f_loc, totals, comm)
         # ---- host containers of this level
+        centers_host = Deferred(lambda c=centers: _np(c).T.copy())     # explicit centres (shift included), as evaluated
         if lvl == 0:
             og0 = RegularGrid(grid.octree_grid.orthogonal_extent, grid.octree_grid.regular_grid_shape)
-            og0._values = _np(centers).T.copy()            # explicit centres (shift included), as evaluated
+            og0._values, og0._n_points = centers_host, nv
             lvl_grid = EngineGrid(octree_grid=og0, dense_grid=grid.dense_grid, topography=grid.topography,
                                   sections=grid.sections, custom_grid=grid.custom_grid)
         else:
-            og = RegularGrid.from_octree_level(_np(centers).T, prev_regular)
-            og._dxdydz = d.copy()
+            og = RegularGrid.from_octree_level(centers_host, prev_regular)
+            og._dxdydz, og._n_points = d.copy(), nv
             prev_regular = og
             lvl_grid = EngineGrid(octree_grid=og)
         outs = _level_outputs(f, lvl_grid, rel_enum)
         level = OctreeLevel(grid_centers=lvl_grid, outputs_centers=outs,
-                            grid_corners=None if corners is None else EngineGrid.from_xyz_coords(_np(corners).T))
+                            _grid_corners=None if corners is None else
+                            Deferred(lambda c=corners: EngineGrid.from_xyz_coords(_np(c).T)))
         octree_levels.append(level)
-        host = {"lith": np.rint(outs[-1].combined_scalar_field.final_block[:nv]),
-                "faults": np.rint(outs[-1].combined_scalar_field.faults_block[:nv]), "selected": None}
+        host = {"lith": Deferred(lambda o=outs[-1], nv=nv: np.rint(o.combined_scalar_field.final_block[:nv])),
+                "faults": Deferred(lambda o=outs[-1], nv=nv: np.rint(o.combined_scalar_field.faults_block[:nv])),
+                "selected": None}
         levels_host.append(host)
         if lvl == dc_level:
             dc_payload = (centers, d.copy(), corners, f)
@@ -631,36 +635,40 @@ def _dual_contouring(eng: B200Engine, ii, options, desc, tables, cache, payload,
 
 
 def _raw_arrays(sol: Solutions, levels_host, grid: EngineGrid, options, meshes) -> RawArraysSolution:
+    """RawArraysSolution over the level-0 outputs (dense grid) or the octree -> regular fill; lazy."""
     ra = RawArraysSolution()
     first = sol.octrees_output[0]
     outs = first.outputs_centers
     last = outs[-1]
-    fb, fa = last.combined_scalar_field.final_block, last.combined_scalar_field.faults_block
     g0 = first.grid_centers
+    fb = lambda: last.combined_scalar_field.final_block
+    fa = lambda: last.combined_scalar_field.faults_block
+    lith = lambda h: h["lith"].get()
+    faul = lambda h: h["faults"].get()
+    sl = None
     if options.block_solutions_type == BlockSolutionType.DENSE_GRID and grid.dense_grid is not None:
         sl = g0.dense_grid_slice
-        ra.lith_block = np.rint(fb[sl])
-        ra.fault_block = np.rint(fa[sl])
-        ra.scalar_field_matrix = np.stack([o.exported_fields._scalar_field[sl] for o in outs])
-        ra.block_matrix = np.stack([o.scalar_fields.values_block[0, sl] for o in outs])
-        ra.mask_matrix = np.stack([o.scalar_fields.mask_components[sl] for o in outs])
-        ra.mask_matrix_squeezed = np.stack([o.combined_scalar_field.squeezed_mask_array[sl] for o in outs])
+        ra.set_lazy("lith_block", lambda: np.rint(fb()[sl]))
+        ra.set_lazy("fault_block", lambda: np.rint(fa()[sl]))
     elif options.block_solutions_type == BlockSolutionType.OCTREE:
         base = grid.octree_grid.regular_grid_shape
-        ra.lith_block = _fill_regular_from_octree(levels_host, base, lambda h: h["lith"])
-        ra.fault_block = _fill_regular_from_octree(levels_host, base, lambda h: h["faults"])
-        n0 = int(np.prod(base))
-        ra.scalar_field_matrix = np.stack([o.exported_fields._scalar_field[:n0] for o in outs])
-        ra.block_matrix = np.stack([o.scalar_fields.values_block[0, :n0] for o in outs])
-        ra.mask_matrix = np.stack([o.scalar_fields.mask_components[:n0] for o in outs])
-        ra.mask_matrix_squeezed = np.stack([o.combined_scalar_field.squeezed_mask_array[:n0] for o in outs])
-    if ra.lith_block.size:
-        mult = max(len(np.unique(ra.lith_block)), 1)
-        ra.litho_faults_block = ra.lith_block + ra.fault_block * mult
-    for name in ("custom", "topography", "sections"):
-        sl = getattr(g0, {"custom": "custom_grid_slice", "topography": "topography_slice", "sections": "sections_slice"}[name])
-        if sl.stop > sl.start:
-            setattr(ra, name, np.rint(fb[sl]))
+        sl = slice(0, int(np.prod(base)))
+        ra.set_lazy("lith_block", lambda: _fill_regular_from_octree(levels_host, base, lith))
+        ra.set_lazy("fault_block", lambda: _fill_regular_from_octree(levels_host, base, faul))
+    if sl is not None:
+        ra.set_lazy("scalar_field_matrix", lambda: np.stack([o.exported_fields.scalar_field_everywhere[sl] for o in outs]))
+        ra.set_lazy("block_matrix", lambda: np.stack([o.scalar_fields.values_block[0, sl] for o in outs]))
+        ra.set_lazy("mask_matrix", lambda: np.stack([o.scalar_fields.mask_components[sl] for o in outs]))
+        ra.set_lazy("mask_matrix_squeezed", lambda: np.stack([o.combined_scalar_field.squeezed_mask_array[sl] for o in outs]))
+
+        def litho_faults():
+            lb, fbk = ra.lith_block, ra.fault_block
+            return lb + fbk * max(len(np.unique(lb)), 1)
+        ra.set_lazy("litho_faults_block", litho_faults)
+    for name, attr in (("custom", "custom_grid_slice"), ("topography", "topography_slice"), ("sections", "sections_slice")):
+        s_ = getattr(g0, attr)
+        if s_.stop > s_.start:
+            ra.set_lazy(name, lambda s_=s_: np.rint(fb()[s_]))
     if meshes is not None:
         ra.vertices = [m.vertices for m in meshes]
         ra.edges = [m.edges for m in meshes]

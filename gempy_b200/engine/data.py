@@ -62,6 +62,27 @@ class MeshExtractionMaskingOptions(enum.Enum):
     RAW = 4
 
 
+# --------------------------------------------------------------------------- lazy host arrays
+class Deferred:
+    """A device-resident result that is copied to the host on first use.  ``compute_model`` returns in
+    milliseconds at octree level 8; the multi-GB arrays only cross PCIe if somebody reads them."""
+    __slots__ = ("_fetch", "_value")
+
+    def __init__(self, fetch):
+        self._fetch = fetch
+        self._value = None
+
+    def get(self):
+        if self._fetch is not None:
+            self._value = self._fetch()
+            self._fetch = None
+        return self._value
+
+
+def _res(x):
+    return x.get() if isinstance(x, Deferred) else x
+
+
 # --------------------------------------------------------------------------- inputs
 @dataclass
 class SurfacePoints:
@@ -108,8 +129,9 @@ class RegularGrid:
     the CUDA path never needs it for a regular grid (coordinates come from the linear index)."""
     orthogonal_extent: np.ndarray
     regular_grid_shape: np.ndarray
-    _values: Optional[np.ndarray] = field(default=None, repr=False)   # explicit centres (octree levels > 0)
+    _values: object = field(default=None, repr=False)   # explicit centres (octree levels > 0); may be Deferred
     _dxdydz: Optional[np.ndarray] = field(default=None, repr=False)
+    _n_points: Optional[int] = field(default=None, repr=False)
 
     def __post_init__(self):
         self.orthogonal_extent = np.asarray(self.orthogonal_extent, dtype=np.float64).reshape(6)
@@ -119,7 +141,8 @@ class RegularGrid:
     def from_octree_level(cls, xyz_coords_octree: np.ndarray, previous_regular_grid: "RegularGrid",
                           active_cells=None, left_right=None) -> "RegularGrid":
         g = cls(previous_regular_grid.orthogonal_extent, previous_regular_grid.regular_grid_shape * 2)
-        g._values = np.ascontiguousarray(xyz_coords_octree, dtype=np.float64)
+        g._values = xyz_coords_octree if isinstance(xyz_coords_octree, Deferred) else \
+            np.ascontiguousarray(xyz_coords_octree, dtype=np.float64)
         g._dxdydz = previous_regular_grid.dxdydz / 2.0
         return g
 
@@ -150,12 +173,15 @@ class RegularGrid:
         if self._values is None:
             g = np.meshgrid(*self.axis_coords(), indexing="ij")
             self._values = np.vstack([c.ravel() for c in g]).T.astype(np.float64)
+        self._values = _res(self._values)
         return self._values
 
     @property
     def n_points(self) -> int:
+        if self._n_points is not None:
+            return self._n_points
         if self._values is not None:
-            return self._values.shape[0]
+            return _res(self._values).shape[0]
         return int(np.prod(self.regular_grid_shape))
 
 
@@ -486,46 +512,71 @@ class ExportedFields:
     """Scalar field (and optional gradient) on [all grid points ++ all surface points of the stack's
     model]; the ``scalar_field`` view drops the surface-point tail
     (test/test_model_types/test_example_models_I.py:20-21)."""
-    _scalar_field: np.ndarray
-    _gx_field: Optional[np.ndarray] = None
-    _gy_field: Optional[np.ndarray] = None
-    _gz_field: Optional[np.ndarray] = None
+    _scalar_field: object
+    _gx_field: object = None
+    _gy_field: object = None
+    _gz_field: object = None
     _grid_size: int = 0
-    _scalar_field_at_surface_points: Optional[np.ndarray] = None
+    _scalar_field_at_surface_points: object = None
 
     @property
     def scalar_field_everywhere(self) -> np.ndarray:
+        self._scalar_field = _res(self._scalar_field)
         return self._scalar_field
 
     @property
     def scalar_field(self) -> np.ndarray:
-        return self._scalar_field[:self._grid_size]
+        return self.scalar_field_everywhere[:self._grid_size]
+
+    def _g(self, name):
+        v = _res(getattr(self, name))
+        setattr(self, name, v)
+        return v
 
     @property
     def gx_field(self):
-        return None if self._gx_field is None else self._gx_field[:self._grid_size]
+        v = self._g("_gx_field")
+        return None if v is None else v[:self._grid_size]
 
     @property
     def gy_field(self):
-        return None if self._gy_field is None else self._gy_field[:self._grid_size]
+        v = self._g("_gy_field")
+        return None if v is None else v[:self._grid_size]
 
     @property
     def gz_field(self):
-        return None if self._gz_field is None else self._gz_field[:self._grid_size]
+        v = self._g("_gz_field")
+        return None if v is None else v[:self._grid_size]
 
     @property
     def scalar_field_at_surface_points(self) -> np.ndarray:
+        self._scalar_field_at_surface_points = _res(self._scalar_field_at_surface_points)
         return self._scalar_field_at_surface_points
 
 
 @dataclass
 class ScalarFieldOutput:
-    weights: np.ndarray
+    _weights: object
     grid: EngineGrid
     exported_fields: ExportedFields
-    values_block: np.ndarray            # (1, n_xyz) activator output on grid ++ surface points
+    _values_block: object               # (1, n_xyz) activator output on grid ++ surface points
     stack_relation: StackRelationType
-    mask_components: Optional[np.ndarray] = None
+    _mask_components: object = None
+
+    @property
+    def weights(self) -> np.ndarray:
+        self._weights = _res(self._weights)
+        return self._weights
+
+    @property
+    def values_block(self) -> np.ndarray:
+        self._values_block = _res(self._values_block)
+        return self._values_block
+
+    @property
+    def mask_components(self) -> np.ndarray:
+        self._mask_components = _res(self._mask_components)
+        return self._mask_components
 
     @property
     def grid_size(self) -> int:
@@ -534,10 +585,25 @@ class ScalarFieldOutput:
 
 @dataclass
 class CombinedScalarFieldsOutput:
-    squeezed_mask_array: np.ndarray     # (n_xyz,) bool: where this stack owns the final block
-    final_block: np.ndarray             # (n_xyz,) combined lith block (same for every stack)
-    faults_block: np.ndarray            # (n_xyz,) sum of fault blocks
+    _squeezed_mask_array: object        # (n_xyz,) bool: where this stack owns the final block
+    _final_block: object                # (n_xyz,) combined lith block (same for every stack)
+    _faults_block: object               # (n_xyz,) sum of fault blocks
     final_exported_fields: Optional[ExportedFields] = None
+
+    @property
+    def squeezed_mask_array(self) -> np.ndarray:
+        self._squeezed_mask_array = _res(self._squeezed_mask_array)
+        return self._squeezed_mask_array
+
+    @property
+    def final_block(self) -> np.ndarray:
+        self._final_block = _res(self._final_block)
+        return self._final_block
+
+    @property
+    def faults_block(self) -> np.ndarray:
+        self._faults_block = _res(self._faults_block)
+        return self._faults_block
 
 
 @dataclass
@@ -562,8 +628,8 @@ class InterpOutput:
         sl = self.grid.dense_grid_slice
         ef = self.scalar_fields.exported_fields
         pick = lambda a: None if a is None else a[sl]
-        return ExportedFields(pick(ef._scalar_field), pick(ef._gx_field), pick(ef._gy_field), pick(ef._gz_field),
-                              sl.stop - sl.start, ef._scalar_field_at_surface_points)
+        return ExportedFields(pick(ef.scalar_field_everywhere), pick(ef._g("_gx_field")), pick(ef._g("_gy_field")),
+                              pick(ef._g("_gz_field")), sl.stop - sl.start, ef.scalar_field_at_surface_points)
 
     @property
     def values_block(self) -> np.ndarray:
@@ -593,9 +659,14 @@ class InterpOutput:
 class OctreeLevel:
     grid_centers: EngineGrid
     outputs_centers: List[InterpOutput]
-    grid_corners: Optional[EngineGrid] = None
+    _grid_corners: object = None
     outputs_corners: Optional[List[InterpOutput]] = None
     marked_voxels: Optional[np.ndarray] = None      # refine mask over this level's voxels
+
+    @property
+    def grid_corners(self) -> Optional[EngineGrid]:
+        self._grid_corners = _res(self._grid_corners)
+        return self._grid_corners
 
     @property
     def outputs(self) -> List[InterpOutput]:
@@ -635,23 +706,33 @@ class DualContouringMesh:
 class RawArraysSolution:
     """Dense arrays GemPy users read after ``compute_model``:
     lith_block, fault_block, litho_faults_block, scalar_field_matrix, block_matrix, mask_matrix,
-    mask_matrix_squeezed, custom, vertices, edges."""
+    mask_matrix_squeezed, custom, vertices, edges.  Each array is materialised on first access."""
     BlockSolutionType = BlockSolutionType
+    _DEFAULTS = {
+        "lith_block": lambda: np.empty(0), "fault_block": lambda: np.empty(0), "litho_faults_block": lambda: np.empty(0),
+        "scalar_field_matrix": lambda: np.empty((0, 0)), "block_matrix": lambda: np.empty((0, 0)),
+        "mask_matrix": lambda: np.empty((0, 0)), "mask_matrix_squeezed": lambda: np.empty((0, 0)),
+        "custom": lambda: None, "topography": lambda: None, "sections": lambda: None, "dense_ids": lambda: None,
+    }
 
     def __init__(self):
-        self.lith_block = np.empty(0)
-        self.fault_block = np.empty(0)
-        self.litho_faults_block = np.empty(0)
-        self.scalar_field_matrix = np.empty((0, 0))
-        self.block_matrix = np.empty((0, 0))
-        self.mask_matrix = np.empty((0, 0))
-        self.mask_matrix_squeezed = np.empty((0, 0))
-        self.custom = None
-        self.topography = None
-        self.sections = None
-        self.dense_ids = None
+        self._lazy = {}
         self.vertices: list = []
         self.edges: list = []
+
+    def set_lazy(self, name: str, fn) -> None:
+        self._lazy[name] = fn
+
+    def __getattr__(self, name):            # reached only when the attribute is not materialised yet
+        lazy = self.__dict__.get("_lazy", {})
+        if name in lazy:
+            v = lazy.pop(name)()
+        elif name in RawArraysSolution._DEFAULTS:
+            v = RawArraysSolution._DEFAULTS[name]()
+        else:
+            raise AttributeError(name)
+        setattr(self, name, v)
+        return v
 
 
 class Solutions:

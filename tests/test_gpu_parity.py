@@ -197,6 +197,39 @@ def test_eval_regular_matches_points(eng):
     assert _rel_err(Z, Zr) < RTOL and _rel_err(G, Gr) < RTOL
 
 
+@pytest.mark.parametrize("shape", [(12, 6, 16), (5, 7, 8), (3, 3, 4)])
+@pytest.mark.parametrize("kernel", [K.cubic, K.matern_5_2])
+def test_eval_regular_zrun_path(eng, shape, kernel):
+    """nz % 4 == 0 selects the z-run kernel (P consecutive z cells per thread share dx, dy)."""
+    m = ex.anticline(resolution=shape)
+    ii, _, _ = m.args()
+    g = ii.grid.dense_grid
+    xyz = g.values + gc.GRID_SHIFT
+    Z, G, Z2, Zr, Gr = _eval_both(eng, m, xyz, kernel, regular=g)
+    assert _rel_err(Z, Zr) < RTOL and _rel_err(Z2, Zr) < RTOL and _rel_err(G, Gr) < RTOL
+
+
+def test_eval_regular_subrange_offsets(eng):
+    """Point ranges [i0, i1) as used by the multi-GPU sharding, aligned and unaligned to the z-run length."""
+    m = ex.anticline(resolution=(8, 8, 8))
+    ii, opt, desc = m.args()
+    g = ii.grid.dense_grid
+    ko = opt.kernel_options
+    so = _oracle_stack(m)
+    w = orc.solve(orc.assemble_covariance(so, ko), orc.rhs(so, ko))
+    st = gc.StackTables(ii, desc, 0, ko, eng.device)
+    src = eng.pack(st, torch.as_tensor(w, device=eng.device))
+    xyz = g.values + gc.GRID_SHIFT
+    Zr, Gr = orc.evaluate(so, ko, w, xyz, gradient=True)
+    for i0, i1 in ((0, 512), (256, 512), (128, 300), (3, 77), (500, 512)):
+        seg = gc.Segment("r", i1 - i0, grid=gc.regular_descriptor(g), i0=i0)
+        Z = eng.empty(i1 - i0)
+        G = eng.empty(3, i1 - i0)
+        eng.evaluate_segment(st, src, seg, 0, Z, G, None)
+        assert _rel_err(Z.cpu().numpy(), Zr[i0:i1]) < RTOL, (i0, i1)
+        assert _rel_err(G.cpu().numpy().T, Gr[i0:i1]) < RTOL, (i0, i1)
+
+
 def test_eval_empty_and_single_point(eng):
     m = MODELS["anticline"]()
     Z, G, Z2, Zr, Gr = _eval_both(eng, m, np.array([[0.01, 0.02, 0.03]]))
