@@ -259,14 +259,8 @@ def run_gpu(args):
         host_out = torch.empty((4, m), dtype=torch.float64, pin_memory=True)
 
         def e2e_step():
-            st2 = gc.StackTables(ii, desc, 0, ko, eng.device)          # H2D of the input tables
-            A2, b2 = eng.assemble(st2)
-            w2 = eng.solve(A2, b2)
-            src2 = eng.pack(st2, w2)
-            eng.evaluate_segment(st2, src2, seg, 0, Z, G, None)
-            host_out[0].copy_(Z, non_blocking=True)
-            host_out[1:].copy_(G, non_blocking=True)
-            torch.cuda.synchronize()
+            # the host-facing call: numpy tables in, pinned host arrays out (H2D, assemble, solve, evaluate, D2H)
+            gc.compute_dense_fields(ii, opt, desc, engine=eng, point_range=(i0, i1), out=host_out)
             return float(host_out[0, 0])
 
         e2e_step()

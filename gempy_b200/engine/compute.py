@@ -398,6 +398,65 @@ class B200Engine:
                               full(f.faults_block), full(f.squeezed), full(f.mask), f.isovalues, f.weights, f.cond, f.srcs)
 
 
+# ------------------------------------------------------------------------------------------------ dense field API
+def compute_dense_fields(interpolation_input: InterpolationInput, options: InterpolationOptions,
+                         data_descriptor: InputDataDescriptor, *, stack: int = 0, engine: Optional[B200Engine] = None,
+                         point_range: Optional[Tuple[int, int]] = None, out: Optional[torch.Tensor] = None,
+                         n_slabs: int = 8, device: Optional[int] = None) -> torch.Tensor:
+    """Scalar field and gradient of one (fault-free) stack on the dense regular grid, host in / host out.
+
+    The reference obtains these with ``compute_model`` + ``evaluation_options.compute_scalar_gradient = True`` and reads
+    ``exported_fields_dense_grid.{scalar_field, gx_field, gy_field, gz_field}``.  This is the streaming form of that
+    call for grids whose outputs are too large to keep (512^3: 4.3 GB): tables H2D, assemble, solve, then the grid
+    range is evaluated slab by slab on the compute stream while a copy stream drains finished slabs into pinned host
+    memory.  Returns a pinned ``[4, m]`` tensor: Z, gx, gy, gz of points [i0, i1)."""
+    eng = engine or B200Engine(device)
+    ii, desc, ko = interpolation_input, data_descriptor, options.kernel_options
+    g = ii.grid.dense_grid
+    if g is None:
+        raise ValueError("compute_dense_fields needs a dense grid")
+    i0, i1 = point_range if point_range is not None else (0, g.n_points)
+    m = i1 - i0
+    st = StackTables(ii, desc, stack, ko, eng.device)
+    if np.asarray(desc.stack_structure.faults_relations)[:, stack].any() if desc.stack_structure.faults_relations is not None else False:
+        raise ValueError("compute_dense_fields handles fault-free stacks; use compute_model for faulted ones")
+    A, b = eng.assemble(st)
+    w = eng.solve(A, b)
+    del A
+    src = eng.pack(st, w)
+    if out is None:
+        out = torch.empty((4, m), dtype=F64, pin_memory=True)
+    gd = regular_descriptor(g)
+    nyz = int(g.regular_grid_shape[1] * g.regular_grid_shape[2])
+    # slabs aligned to whole x planes when possible (keeps every slab on the z-run kernel)
+    per = max(1, -(-m // max(1, n_slabs)))
+    if per > nyz:
+        per = -(-per // nyz) * nyz
+    compute = torch.cuda.current_stream(eng.device)
+    copier = torch.cuda.Stream(eng.device)
+    bufs = [eng.empty(4, per) for _ in range(2)]
+    free_ev = [None, None]
+    k = 0
+    for s0 in range(0, m, per):
+        s1 = min(m, s0 + per)
+        buf = bufs[k & 1]
+        if free_ev[k & 1] is not None:
+            compute.wait_event(free_ev[k & 1])          # the copy that used this buffer has finished
+        seg = Segment("dense_grid", s1 - s0, grid=gd, i0=i0 + s0)
+        eng.evaluate_segment(st, src, seg, 0, buf[0], buf[1:], None)
+        done = torch.cuda.Event()
+        done.record(compute)
+        with torch.cuda.stream(copier):
+            copier.wait_event(done)
+            out[:, s0:s1].copy_(buf[:, :s1 - s0], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copier)
+            free_ev[k & 1] = ev
+        k += 1
+    copier.synchronize()
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ materialisation
 def _np(t: Optional[torch.Tensor]) -> Optional[np.ndarray]:
     return None if t is None else t.detach().cpu().numpy()
