@@ -205,19 +205,31 @@ __global__ void __launch_bounds__(1024) panel_kernel(int n, int k0, int jb, doub
 constexpr int kPanelThreads = 512;
 constexpr int kMaxCluster = 16;
 
+// Per-column exchange area (lives in every CTA's shared memory, written remotely through DSMEM).
+struct PanelExchange {
+    double cand_v[kMaxCluster];            // |pivot candidate| of each CTA (-1: no active row)
+    int cand_i[kMaxCluster];               // its global row
+    double cand_row[kMaxCluster][kNB];     // the candidate's row of the panel
+    double top_row[kNB];                   // row k0 + j (the row the pivot is exchanged with)
+};
+
+__device__ __forceinline__ void better(double& bv, int& bi, double ov, int oi) {
+    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+}
+
 __global__ void __launch_bounds__(kPanelThreads, 1)
 panel_cluster_kernel(int n, int k0, int jb, double* __restrict__ A, int lda, int* __restrict__ ipiv, int* __restrict__ info,
                      int R, int ldp) {
     extern __shared__ double P[];                  // [jb][ldp] : this CTA's rows of the panel, column-major
-    __shared__ double prow[kNB], trow[kNB];
-    __shared__ double cand_v[kMaxCluster];
-    __shared__ int cand_i[kMaxCluster];
+    __shared__ PanelExchange ex[2];                // double buffered by column parity
     __shared__ double red_v[kPanelThreads / 32];
     __shared__ int red_i[kPanelThreads / 32];
+    __shared__ double loc_v;
+    __shared__ int loc_i;
     cg::cluster_group cluster = cg::this_cluster();
     const int C = (int)cluster.num_blocks();
     const int rank = (int)cluster.block_rank();
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int r0 = k0 + rank * R;
     const int nrows = max(0, min(n, r0 + R) - r0);
 
@@ -226,64 +238,83 @@ panel_cluster_kernel(int n, int k0, int jb, double* __restrict__ A, int lda, int
         P[c * ldp + i] = A[(long long)(k0 + c) * lda + r0 + i];
     }
     __syncthreads();
+    // candidate for column 0
+    double best = -1.0;
+    int bi = n;
+    for (int i = tid; i < nrows; i += kPanelThreads) {
+        const double v = fabs(P[i]);
+        if (v > best) { best = v; bi = r0 + i; }
+    }
     cluster.sync();                                // every CTA of the cluster is resident before any DSMEM access
 
     for (int j = 0; j < jb; ++j) {
         const int kj = k0 + j;
-        // ---- local pivot candidate (first maximum of |column j| over this CTA's active rows)
-        double best = -1.0;
-        int bi = n;
-        for (int i = tid; i < nrows; i += kPanelThreads) {
-            const int gi = r0 + i;
-            if (gi >= kj) {
-                const double v = fabs(P[j * ldp + i]);
-                if (v > best) { best = v; bi = gi; }
-            }
-        }
-        for (int o = 16; o > 0; o >>= 1) {
-            const double ov = __shfl_down_sync(0xffffffffu, best, o);
-            const int oi = __shfl_down_sync(0xffffffffu, bi, o);
-            if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
-        }
-        if ((tid & 31) == 0) { red_v[tid >> 5] = best; red_i[tid >> 5] = bi; }
+        const int buf = j & 1;
+        // ---- (1) CTA-wide candidate
+        for (int o = 16; o > 0; o >>= 1)
+            better(best, bi, __shfl_down_sync(0xffffffffu, best, o), __shfl_down_sync(0xffffffffu, bi, o));
+        if (lane == 0) { red_v[warp] = best; red_i[warp] = bi; }
         __syncthreads();
-        if (tid == 0) {
-            for (int w = 1; w < kPanelThreads / 32; ++w)
-                if (red_v[w] > best || (red_v[w] == best && red_i[w] < bi)) { best = red_v[w]; bi = red_i[w]; }
-            for (int c = 0; c < C; ++c) {          // publish to every CTA of the cluster
-                cluster.map_shared_rank(cand_v, c)[rank] = best;
-                cluster.map_shared_rank(cand_i, c)[rank] = bi;
-            }
+        if (warp == 0) {
+            double v = lane < kPanelThreads / 32 ? red_v[lane] : -1.0;
+            int ii = lane < kPanelThreads / 32 ? red_i[lane] : n;
+            for (int o = 8; o > 0; o >>= 1)
+                better(v, ii, __shfl_down_sync(0xffffffffu, v, o), __shfl_down_sync(0xffffffffu, ii, o));
+            if (lane == 0) { loc_v = v; loc_i = ii; }
         }
-        cluster.sync();                            // (1) candidates visible everywhere
-        double gbest = cand_v[0];
-        int p = cand_i[0];
-        for (int c = 1; c < C; ++c)
-            if (cand_v[c] > gbest || (cand_v[c] == gbest && cand_i[c] < p)) { gbest = cand_v[c]; p = cand_i[c]; }
-        const int owner_p = (p - k0) / R, owner_t = (kj - k0) / R;
+        __syncthreads();
+        const double my_v = loc_v;
+        const int my_i = loc_i;
+        // ---- (2) publish candidate (+ its row) and, from its owner, the top row, to every CTA
+        const int owner_t = (kj - k0) / R;
+        for (int e = tid; e < C * jb; e += kPanelThreads) {
+            const int dst = e / jb, c = e - dst * jb;
+            PanelExchange* rx = cluster.map_shared_rank(&ex[buf], dst);
+            rx->cand_row[rank][c] = (my_i < n) ? P[c * ldp + (my_i - r0)] : 0.0;
+            if (rank == owner_t) rx->top_row[c] = P[c * ldp + (kj - r0)];
+        }
+        if (tid < C) {
+            PanelExchange* rx = cluster.map_shared_rank(&ex[buf], tid);
+            rx->cand_v[rank] = my_v;
+            rx->cand_i[rank] = my_i;
+        }
+        cluster.sync();                            // the only cluster barrier of this column
+        // ---- (3) everybody elects the same pivot
+        double gv = ex[buf].cand_v[0];
+        int p = ex[buf].cand_i[0], win = 0;
+        for (int c = 1; c < C; ++c) {
+            const double cv = ex[buf].cand_v[c];
+            const int ci = ex[buf].cand_i[c];
+            if (cv > gv || (cv == gv && ci < p)) { gv = cv; p = ci; win = c; }
+        }
+        const double* prow = ex[buf].cand_row[win];
         if (rank == 0 && tid == 0) {
             ipiv[kj] = p;
-            if (gbest == 0.0 && info && *info == 0) *info = kj + 1;
+            if (gv == 0.0 && info && *info == 0) *info = kj + 1;
         }
-        if (rank == owner_p && tid < jb) {
-            const double v = P[tid * ldp + (p - r0)];
-            for (int c = 0; c < C; ++c) cluster.map_shared_rank(prow, c)[tid] = v;
-        }
-        if (p != kj && rank == owner_t && tid < jb)
-            cluster.map_shared_rank(trow, owner_p)[tid] = P[tid * ldp + (kj - r0)];
-        cluster.sync();                            // (2) pivot row / displaced row delivered
+        const int owner_p = (p - k0) / R;
         if (p != kj && tid < jb) {
             if (rank == owner_t) P[tid * ldp + (kj - r0)] = prow[tid];
-            if (rank == owner_p) P[tid * ldp + (p - r0)] = trow[tid];
+            if (rank == owner_p) P[tid * ldp + (p - r0)] = ex[buf].top_row[tid];
         }
         __syncthreads();
+        // ---- (4) rank-1 update of this CTA's rows, fused with the candidate search of column j + 1
         const double pv = prow[j];
         const double inv = pv != 0.0 ? 1.0 / pv : 0.0;
+        best = -1.0;
+        bi = n;
         for (int i = tid; i < nrows; i += kPanelThreads) {
-            if (r0 + i > kj) {
+            const int gi = r0 + i;
+            if (gi > kj) {
                 const double l = P[j * ldp + i] * inv;
                 P[j * ldp + i] = l;
-                for (int c = j + 1; c < jb; ++c) P[c * ldp + i] = fma(-l, prow[c], P[c * ldp + i]);
+                if (j + 1 < jb) {
+                    const double v1 = fma(-l, prow[j + 1], P[(j + 1) * ldp + i]);
+                    P[(j + 1) * ldp + i] = v1;
+                    const double a1 = fabs(v1);
+                    if (a1 > best) { best = a1; bi = gi; }
+                    for (int c = j + 2; c < jb; ++c) P[c * ldp + i] = fma(-l, prow[c], P[c * ldp + i]);
+                }
             }
         }
         __syncthreads();
@@ -297,14 +328,20 @@ panel_cluster_kernel(int n, int k0, int jb, double* __restrict__ A, int lda, int
 
 // Apply the panel's interchanges to the columns right of the panel and solve U12 = L11^-1 A12.
 // One CTA handles 64 columns.
+// Blocks beyond the matrix' own column blocks work on the right-hand sides B (n x nrhs, ldb): the forward
+// substitution of gpb_lu_solve is carried along with the factorisation.
 __global__ void __launch_bounds__(256) swap_trsm_kernel(int n, int k0, int jb, double* __restrict__ A, int lda,
-                                                        const int* __restrict__ ipiv) {
+                                                        const int* __restrict__ ipiv, int n_mat_blocks,
+                                                        double* __restrict__ B, int ldb, int nrhs) {
     __shared__ double L[kNB][kNB + 1];
     __shared__ double T[64][kNB + 1];
     __shared__ int piv[kNB];
     const int tid = threadIdx.x;
-    const int c0 = k0 + jb + blockIdx.x * 64;
-    const int ncol = min(64, n - c0);
+    const bool on_rhs = (int)blockIdx.x >= n_mat_blocks;
+    const int c0 = on_rhs ? ((int)blockIdx.x - n_mat_blocks) * 64 : k0 + jb + blockIdx.x * 64;
+    const int ncol = on_rhs ? min(64, nrhs - c0) : min(64, n - c0);
+    double* const M = on_rhs ? B : A;              // the columns this block transforms
+    const int ldm = on_rhs ? ldb : lda;
     for (int e = tid; e < jb * jb; e += 256) {
         const int j = e / jb, i = e - j * jb;
         L[i][j] = A[(long long)(k0 + j) * lda + k0 + i];
@@ -313,7 +350,7 @@ __global__ void __launch_bounds__(256) swap_trsm_kernel(int n, int k0, int jb, d
     __syncthreads();
     // interchanges: one thread per column, sequential over the panel's pivots
     if (tid < ncol) {
-        double* c = A + (long long)(c0 + tid) * lda;
+        double* c = M + (long long)(c0 + tid) * ldm;
         for (int j = 0; j < jb; ++j) {
             const int p = piv[j];
             if (p != k0 + j) { const double t = c[k0 + j]; c[k0 + j] = c[p]; c[p] = t; }
@@ -322,7 +359,7 @@ __global__ void __launch_bounds__(256) swap_trsm_kernel(int n, int k0, int jb, d
     __syncthreads();
     for (int e = tid; e < ncol * jb; e += 256) {
         const int c = e / jb, i = e - c * jb;
-        T[c][i] = A[(long long)(c0 + c) * lda + k0 + i];
+        T[c][i] = M[(long long)(c0 + c) * ldm + k0 + i];
     }
     __syncthreads();
     if (tid < ncol) {
@@ -334,7 +371,78 @@ __global__ void __launch_bounds__(256) swap_trsm_kernel(int n, int k0, int jb, d
     __syncthreads();
     for (int e = tid; e < ncol * jb; e += 256) {
         const int c = e / jb, i = e - c * jb;
-        A[(long long)(c0 + c) * lda + k0 + i] = T[c][i];
+        M[(long long)(c0 + c) * ldm + k0 + i] = T[c][i];
+    }
+}
+
+// Right-hand sides: B[k0+jb:, :] -= L21 * B[k0:k0+jb, :]   (the gemv twin of the trailing update)
+__global__ void __launch_bounds__(256) rhs_update_kernel(int n, int k0, int jb, const double* __restrict__ A, int lda,
+                                                         double* __restrict__ B, int ldb, int nrhs) {
+    __shared__ double xs[kNB];
+    const int i = k0 + jb + blockIdx.x * 256 + threadIdx.x;
+    for (int r = 0; r < nrhs; ++r) {
+        double* x = B + (long long)r * ldb;
+        __syncthreads();
+        if (threadIdx.x < jb) xs[threadIdx.x] = x[k0 + threadIdx.x];
+        __syncthreads();
+        if (i < n) {
+            double v = x[i];
+            for (int c = 0; c < jb; ++c) v = fma(-A[(long long)(k0 + c) * lda + i], xs[c], v);
+            x[i] = v;
+        }
+    }
+}
+
+// Backward substitution U x = y with one CTA per block of kNB rows.  CTA `blockIdx.x` owns the block row
+// nblk - 1 - blockIdx.x, so CTAs are scheduled in dependency order; a CTA consumes the solution blocks below it as
+// their flags appear (release/acquire through global memory) and publishes its own block when done.
+__global__ void __launch_bounds__(128) trsv_upper_kernel(int n, const double* __restrict__ LU, int lda, double* __restrict__ x,
+                                                         int* __restrict__ flags) {
+    __shared__ double D[kNB][kNB + 1];
+    __shared__ double xk[kNB];
+    __shared__ double part[4][kNB];
+    const int nblk = (n + kNB - 1) / kNB;
+    const int j = nblk - 1 - (int)blockIdx.x;
+    const int r0 = j * kNB;
+    const int jb = min(kNB, n - r0);
+    const int tid = threadIdx.x, row = tid & 31, q = tid >> 5;
+    for (int e = tid; e < jb * jb; e += 128) {
+        const int c = e / jb, i = e - c * jb;
+        D[i][c] = LU[(long long)(r0 + c) * lda + r0 + i];
+    }
+    double acc = 0.0;
+    for (int k = nblk - 1; k > j; --k) {
+        const int c0 = k * kNB;
+        const int kb = min(kNB, n - c0);
+        if (tid == 0) {
+            while (atomicAdd(&flags[k], 0) == 0) { __nanosleep(20); }
+            __threadfence();
+        }
+        __syncthreads();
+        if (tid < kb) xk[tid] = __ldcg(x + c0 + tid);
+        __syncthreads();
+        if (row < jb) {
+#pragma unroll
+            for (int cc = 0; cc < 8; ++cc) {
+                const int c = q * 8 + cc;
+                if (c < kb) acc = fma(LU[(long long)(c0 + c) * lda + r0 + row], xk[c], acc);
+            }
+        }
+    }
+    part[q][row] = acc;
+    __syncthreads();
+    if (tid < 32) {
+        double v = 0.0;
+        if (tid < jb) v = x[r0 + tid] - (part[0][tid] + part[1][tid] + part[2][tid] + part[3][tid]);
+        for (int c = jb - 1; c >= 0; --c) {
+            if (tid == c) v /= D[c][c];
+            const double xc = __shfl_sync(0xffffffffu, v, c);
+            if (tid < c) v = fma(-D[tid][c], xc, v);
+        }
+        if (tid < jb) x[r0 + tid] = v;
+        __threadfence();
+        __syncwarp();
+        if (tid == 0) atomicExch(&flags[j], 1);
     }
 }
 
@@ -550,25 +658,47 @@ int launch_panel(int n, int k0, int jb, double* A, int lda, int* ipiv, int* info
 }
 
 
-int factor_blocked(int n, double* A, int lda, int* ipiv, int* info, cudaStream_t s) {
+int factor_blocked(int n, double* A, int lda, int* ipiv, int* info, double* B, int nrhs, int ldb, cudaStream_t s) {
     zero_info_kernel<<<1, 1, 0, s>>>(info);
     GPB_LAUNCH_CHECK();
+    const int rhs_blocks = (B != nullptr) ? (nrhs + 63) / 64 : 0;
     for (int k0 = 0; k0 < n;) {
         const int jb = panel_width(n, k0);
         int rc = launch_panel(n, k0, jb, A, lda, ipiv, info, s);
         if (rc) return rc;
         const int nright = n - k0 - jb;
-        if (nright > 0) {
-            swap_trsm_kernel<<<(nright + 63) / 64, 256, 0, s>>>(n, k0, jb, A, lda, ipiv);
+        const int mat_blocks = (nright + 63) / 64;
+        if (mat_blocks + rhs_blocks > 0) {
+            swap_trsm_kernel<<<mat_blocks + rhs_blocks, 256, 0, s>>>(n, k0, jb, A, lda, ipiv, mat_blocks, B, ldb, nrhs);
             GPB_LAUNCH_CHECK();
+        }
+        if (nright > 0) {
             const int M = n - k0 - jb;
             dim3 grid((M + kGM - 1) / kGM, (nright + kGN - 1) / kGN);
             gemm_kernel<<<grid, 256, 0, s>>>(M, nright, jb, A + (long long)k0 * lda + k0 + jb,
                                              A + (long long)(k0 + jb) * lda + k0, A + (long long)(k0 + jb) * lda + k0 + jb, lda);
             GPB_LAUNCH_CHECK();
+            if (B != nullptr) {
+                rhs_update_kernel<<<(M + 255) / 256, 256, 0, s>>>(n, k0, jb, A, lda, B, ldb, nrhs);
+                GPB_LAUNCH_CHECK();
+            }
         }
         k0 += jb;
     }
+    return GPB_OK;
+}
+
+// U x = y for every right-hand side (multi-CTA pipelined backward substitution)
+int backward_blocked(int n, const double* LU, int lda, double* B, int nrhs, int ldb, cudaStream_t s) {
+    const int nblk = (n + kNB - 1) / kNB;
+    int* flags = nullptr;
+    GPB_CHECK_CUDA(cudaMallocAsync((void**)&flags, sizeof(int) * nblk, s));
+    for (int r = 0; r < nrhs; ++r) {
+        GPB_CHECK_CUDA(cudaMemsetAsync(flags, 0, sizeof(int) * nblk, s));
+        trsv_upper_kernel<<<nblk, 128, 0, s>>>(n, LU, lda, B + (long long)r * ldb, flags);
+        GPB_LAUNCH_CHECK();
+    }
+    GPB_CHECK_CUDA(cudaFreeAsync(flags, s));
     return GPB_OK;
 }
 
@@ -589,7 +719,7 @@ int small_path(int n, double* A, int lda, double* b, int nrhs, int ldb, int* ipi
 extern "C" int gpb_lu_factor(int n, double* A, int lda, int* ipiv, int* info, void* stream) {
     GPB_REQUIRE(n > 0 && A && ipiv && lda >= n, "bad arguments");
     if (n <= kSmallN) return small_path(n, A, lda, nullptr, 0, 0, ipiv, info, 0, (cudaStream_t)stream);
-    return factor_blocked(n, A, lda, ipiv, info, (cudaStream_t)stream);
+    return factor_blocked(n, A, lda, ipiv, info, nullptr, 0, 0, (cudaStream_t)stream);
 }
 
 extern "C" int gpb_lu_apply(int n, const double* LU, int lda, const int* ipiv, double* b, int nrhs, int ldb, void* stream) {
@@ -604,7 +734,8 @@ extern "C" int gpb_lu_apply(int n, const double* LU, int lda, const int* ipiv, d
 extern "C" int gpb_lu_solve(int n, double* A, int lda, double* b, int nrhs, int ldb, int* ipiv, int* info, void* stream) {
     GPB_REQUIRE(n > 0 && A && b && ipiv && lda >= n && ldb >= n && nrhs >= 1, "bad arguments");
     if (n <= kSmallN) return small_path(n, A, lda, b, nrhs, ldb, ipiv, info, 1, (cudaStream_t)stream);
-    int rc = factor_blocked(n, A, lda, ipiv, info, (cudaStream_t)stream);
+    // forward substitution rides along with the factorisation (b is one more block of columns), then U x = y
+    int rc = factor_blocked(n, A, lda, ipiv, info, b, nrhs, ldb, (cudaStream_t)stream);
     if (rc) return rc;
-    return gpb_lu_apply(n, A, lda, ipiv, b, nrhs, ldb, stream);
+    return backward_blocked(n, A, lda, b, nrhs, ldb, (cudaStream_t)stream);
 }

@@ -448,7 +448,8 @@ def compute_dense_fields(interpolation_input: InterpolationInput, options: Inter
         done.record(compute)
         with torch.cuda.stream(copier):
             copier.wait_event(done)
-            out[:, s0:s1].copy_(buf[:, :s1 - s0], non_blocking=True)
+            for a in range(4):                          # row by row: contiguous 1-D copies stay on the DMA path
+                out[a, s0:s1].copy_(buf[a, :s1 - s0], non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(copier)
             free_ev[k & 1] = ev
