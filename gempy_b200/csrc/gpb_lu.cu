@@ -34,6 +34,15 @@ __host__ __device__ inline int panel_width_hd(int n, int k0, int cluster, unsign
     return (n - k0 < jb) ? n - k0 : jb;
 }
 
+// Outer block at column k0 = two consecutive panels (w1 + w2 <= 64 columns).  Interchanges are LAPACK-style inside an
+// outer block and LINPACK-style across outer blocks; the trailing update uses K = w1 + w2.  Systems that take the
+// shared-memory path (n <= kSmallN) use single 32-column blocks.
+__host__ __device__ inline void outer_widths_hd(int n, int k0, int cluster, unsigned long long smem_cap, int& w1, int& w2) {
+    w1 = panel_width_hd(n, k0, cluster, smem_cap);
+    w2 = 0;
+    if (n > kSmallN && k0 + w1 < n) w2 = panel_width_hd(n, k0 + w1, cluster, smem_cap);
+}
+
 // =====================================================================================================
 // small systems: one CTA, matrix in shared memory
 // =====================================================================================================
@@ -308,12 +317,24 @@ panel_cluster_kernel(int n, int k0, int jb, double* __restrict__ A, int lda, int
             if (gi > kj) {
                 const double l = P[j * ldp + i] * inv;
                 P[j * ldp + i] = l;
-                if (j + 1 < jb) {
-                    const double v1 = fma(-l, prow[j + 1], P[(j + 1) * ldp + i]);
-                    P[(j + 1) * ldp + i] = v1;
-                    const double a1 = fabs(v1);
-                    if (a1 > best) { best = a1; bi = gi; }
-                    for (int c = j + 2; c < jb; ++c) P[c * ldp + i] = fma(-l, prow[c], P[c * ldp + i]);
+                // chunks of 8 columns: all loads first, so the shared-memory latency is paid once per chunk
+                for (int c0 = j + 1; c0 < jb; c0 += 8) {
+                    double v[8], pr[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int c = c0 + u;
+                        v[u] = (c < jb) ? P[c * ldp + i] : 0.0;
+                        pr[u] = (c < jb) ? prow[c] : 0.0;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) v[u] = fma(-l, pr[u], v[u]);
+                    if (c0 == j + 1) {
+                        const double a1 = fabs(v[0]);
+                        if (a1 > best) { best = a1; bi = gi; }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u)
+                        if (c0 + u < jb) P[(c0 + u) * ldp + i] = v[u];
                 }
             }
         }
@@ -326,59 +347,79 @@ panel_cluster_kernel(int n, int k0, int jb, double* __restrict__ A, int lda, int
     cluster.sync();                                // no CTA exits while a neighbour may still address its smem
 }
 
-// Apply the panel's interchanges to the columns right of the panel and solve U12 = L11^-1 A12.
-// One CTA handles 64 columns.
+// Apply the interchanges ipiv[k0 .. k0+wb) to the matrix columns [col_begin, col_end) and solve
+// U12 = L11^-1 A12 with the wb x wb unit-lower block at (k0, k0).  One CTA handles 64 columns.
 // Blocks beyond the matrix' own column blocks work on the right-hand sides B (n x nrhs, ldb): the forward
 // substitution of gpb_lu_solve is carried along with the factorisation.
-__global__ void __launch_bounds__(256) swap_trsm_kernel(int n, int k0, int jb, double* __restrict__ A, int lda,
-                                                        const int* __restrict__ ipiv, int n_mat_blocks,
-                                                        double* __restrict__ B, int ldb, int nrhs) {
-    __shared__ double L[kNB][kNB + 1];
-    __shared__ double T[64][kNB + 1];
-    __shared__ int piv[kNB];
+constexpr int kWB = 64;          // maximum outer block width
+__global__ void __launch_bounds__(256) swap_trsm_kernel(int n, int k0, int wb, int col_begin, int col_end,
+                                                        double* __restrict__ A, int lda, const int* __restrict__ ipiv,
+                                                        int n_mat_blocks, double* __restrict__ B, int ldb, int nrhs) {
+    extern __shared__ double sm_st[];
+    const int ldl = wb + 1;
+    double* L = sm_st;                         // [wb][ldl]
+    double* T = sm_st + wb * ldl;              // [64][ldl]
+    __shared__ int piv[kWB];
     const int tid = threadIdx.x;
     const bool on_rhs = (int)blockIdx.x >= n_mat_blocks;
-    const int c0 = on_rhs ? ((int)blockIdx.x - n_mat_blocks) * 64 : k0 + jb + blockIdx.x * 64;
-    const int ncol = on_rhs ? min(64, nrhs - c0) : min(64, n - c0);
+    const int c0 = on_rhs ? ((int)blockIdx.x - n_mat_blocks) * 64 : col_begin + blockIdx.x * 64;
+    const int ncol = on_rhs ? min(64, nrhs - c0) : min(64, col_end - c0);
     double* const M = on_rhs ? B : A;              // the columns this block transforms
     const int ldm = on_rhs ? ldb : lda;
-    for (int e = tid; e < jb * jb; e += 256) {
-        const int j = e / jb, i = e - j * jb;
-        L[i][j] = A[(long long)(k0 + j) * lda + k0 + i];
+    for (int e = tid; e < wb * wb; e += 256) {
+        const int j = e / wb, i = e - j * wb;
+        L[i * ldl + j] = A[(long long)(k0 + j) * lda + k0 + i];
     }
-    if (tid < jb) piv[tid] = ipiv[k0 + tid];
+    if (tid < wb) piv[tid] = ipiv[k0 + tid];
     __syncthreads();
-    // interchanges: one thread per column, sequential over the panel's pivots
+    // interchanges: one thread per column, sequential over the block's pivots
     if (tid < ncol) {
         double* c = M + (long long)(c0 + tid) * ldm;
-        for (int j = 0; j < jb; ++j) {
+        for (int j = 0; j < wb; ++j) {
             const int p = piv[j];
             if (p != k0 + j) { const double t = c[k0 + j]; c[k0 + j] = c[p]; c[p] = t; }
         }
     }
     __syncthreads();
-    for (int e = tid; e < ncol * jb; e += 256) {
-        const int c = e / jb, i = e - c * jb;
-        T[c][i] = M[(long long)(c0 + c) * ldm + k0 + i];
+    for (int e = tid; e < ncol * wb; e += 256) {
+        const int c = e / wb, i = e - c * wb;
+        T[c * ldl + i] = M[(long long)(c0 + c) * ldm + k0 + i];
     }
     __syncthreads();
-    if (tid < ncol) {
-        for (int k = 0; k < jb; ++k) {
-            const double xk = T[tid][k];
-            for (int i = k + 1; i < jb; ++i) T[tid][i] = fma(-L[i][k], xk, T[tid][i]);
+    // 4 threads per column: the updates of rows i > k are split over them
+    {
+        const int c = tid >> 2, part = tid & 3;
+        for (int k = 0; k < wb; ++k) {
+            if (c < ncol) {
+                const double xk = T[c * ldl + k];
+                for (int i = k + 1 + part; i < wb; i += 4) T[c * ldl + i] = fma(-L[i * ldl + k], xk, T[c * ldl + i]);
+            }
+            __syncwarp();
         }
     }
     __syncthreads();
-    for (int e = tid; e < ncol * jb; e += 256) {
-        const int c = e / jb, i = e - c * jb;
-        M[(long long)(c0 + c) * ldm + k0 + i] = T[c][i];
+    for (int e = tid; e < ncol * wb; e += 256) {
+        const int c = e / wb, i = e - c * wb;
+        M[(long long)(c0 + c) * ldm + k0 + i] = T[c * ldl + i];
+    }
+}
+
+// Apply the interchanges ipiv[ks .. ke) to the columns [c_begin, c_end) (second panel's swaps on the first
+// panel's L columns: LAPACK-style inside an outer block).
+__global__ void swap_cols_kernel(double* __restrict__ A, int lda, const int* __restrict__ ipiv, int ks, int ke, int c_begin, int c_end) {
+    const int c = c_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= c_end) return;
+    double* col = A + (long long)c * lda;
+    for (int j = ks; j < ke; ++j) {
+        const int p = ipiv[j];
+        if (p != j) { const double t = col[j]; col[j] = col[p]; col[p] = t; }
     }
 }
 
 // Right-hand sides: B[k0+jb:, :] -= L21 * B[k0:k0+jb, :]   (the gemv twin of the trailing update)
 __global__ void __launch_bounds__(256) rhs_update_kernel(int n, int k0, int jb, const double* __restrict__ A, int lda,
                                                          double* __restrict__ B, int ldb, int nrhs) {
-    __shared__ double xs[kNB];
+    __shared__ double xs[kWB];
     const int i = k0 + jb + blockIdx.x * 256 + threadIdx.x;
     for (int r = 0; r < nrhs; ++r) {
         double* x = B + (long long)r * ldb;
@@ -463,16 +504,6 @@ __global__ void __launch_bounds__(256) gemm_kernel(int M, int N, int K, const do
     __shared__ double Bs[kGN * kLdB];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int m0 = blockIdx.x * kGM, n0 = blockIdx.y * kGN;
-    // stage A: columns k are contiguous in m
-    for (int e = tid; e < K * kGM; e += 256) {
-        const int k = e / kGM, m = e - k * kGM;
-        As[k * kLdA + m] = (m0 + m < M) ? -Ap[(long long)k * lda + m0 + m] : 0.0;     // negated: C += (-A) B
-    }
-    for (int e = tid; e < kGN * K; e += 256) {
-        const int nn = e / K, k = e - nn * K;
-        Bs[nn * kLdB + k] = (n0 + nn < N) ? Bp[(long long)(n0 + nn) * lda + k] : 0.0;
-    }
-    __syncthreads();
     // 8 warps: 2 along M (32 rows each) x 4 along N (16 cols each); warp tile 32 x 16 = 4 x 2 m8n8 tiles
     const int wm = (warp & 1) * 32, wn = (warp >> 1) * 16;
     const int r = lane >> 2, q = lane & 3;
@@ -487,16 +518,31 @@ __global__ void __launch_bounds__(256) gemm_kernel(int M, int N, int K, const do
             acc[i][j][0] = (gm < M && gn < N) ? C[(long long)gn * lda + gm] : 0.0;
             acc[i][j][1] = (gm < M && gn + 1 < N) ? C[(long long)(gn + 1) * lda + gm] : 0.0;
         }
-    for (int ks = 0; ks < K; ks += 4) {
-        double a[4], b[NJ];
+    // K (<= 64) is consumed in halves of kNB through the same shared-memory stage; C stays in registers
+    for (int kh = 0; kh < K; kh += kNB) {
+        const int kc = min(kNB, K - kh);
+        if (kh) __syncthreads();
+        // stage A: columns k are contiguous in m
+        for (int e = tid; e < kNB * kGM; e += 256) {
+            const int k = e / kGM, m = e - k * kGM;
+            As[k * kLdA + m] = (k < kc && m0 + m < M) ? -Ap[(long long)(kh + k) * lda + m0 + m] : 0.0;     // negated: C += (-A) B
+        }
+        for (int e = tid; e < kGN * kNB; e += 256) {
+            const int nn = e / kNB, k = e - nn * kNB;
+            Bs[nn * kLdB + k] = (k < kc && n0 + nn < N) ? Bp[(long long)(n0 + nn) * lda + kh + k] : 0.0;
+        }
+        __syncthreads();
+        for (int ks = 0; ks < kNB; ks += 4) {
+            double a[4], b[NJ];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) a[i] = As[(ks + q) * kLdA + wm + 8 * i + r];
+            for (int i = 0; i < 4; ++i) a[i] = As[(ks + q) * kLdA + wm + 8 * i + r];
 #pragma unroll
-        for (int j = 0; j < NJ; ++j) b[j] = Bs[(wn + 8 * j + r) * kLdB + ks + q];
+            for (int j = 0; j < NJ; ++j) b[j] = Bs[(wn + 8 * j + r) * kLdB + ks + q];
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int j = 0; j < NJ; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+                for (int j = 0; j < NJ; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -518,19 +564,26 @@ __global__ void __launch_bounds__(1024) apply_kernel(int n, const double* __rest
     const int tid = threadIdx.x, nt = blockDim.x;
     for (int r = 0; r < nrhs; ++r) {
         double* x = b + (long long)r * ldb;
-        // forward: P, L  (same panel schedule as the factorisation)
+        // forward: P, L  (same outer-block schedule as the factorisation: all interchanges of an outer block first,
+        // then its panels one after the other)
+        int next_outer = 0;
         for (int k0 = 0, jb = 0; k0 < n; k0 += jb) {
             jb = panel_width_hd(n, k0, cluster, smem_cap);
             __syncthreads();
+            if (k0 == next_outer) {
+                int w1, w2;
+                outer_widths_hd(n, k0, cluster, smem_cap, w1, w2);
+                if (tid == 0) {
+                    for (int j = k0; j < k0 + w1 + w2; ++j) {
+                        const int p = ipiv[j];
+                        if (p != j) { const double t = x[j]; x[j] = x[p]; x[p] = t; }
+                    }
+                }
+                next_outer = k0 + w1 + w2;
+            }
             for (int e = tid; e < jb * jb; e += nt) {
                 const int c = e / jb, i = e - c * jb;
                 D[i][c] = LU[(long long)(k0 + c) * lda + k0 + i];
-            }
-            if (tid == 0) {
-                for (int j = 0; j < jb; ++j) {
-                    const int p = ipiv[k0 + j];
-                    if (p != k0 + j) { const double t = x[k0 + j]; x[k0 + j] = x[p]; x[p] = t; }
-                }
             }
             __syncthreads();
             if (tid < 32) {
@@ -619,11 +672,6 @@ const PanelConfig& panel_config() {
 
 // Panel width at column k0 of an n x n factorisation.  A pure function of (n, k0) and the device's cluster
 // configuration, so that gpb_lu_apply replays exactly the panels gpb_lu_factor used.
-int panel_width(int n, int k0) {
-    const PanelConfig& cfg = panel_config();
-    return panel_width_hd(n, k0, cfg.cluster, (unsigned long long)cfg.smem_cap);
-}
-
 bool panel_fits_cluster(int n, int k0, int jb) {
     const PanelConfig& cfg = panel_config();
     if (cfg.cluster == 0) return false;
@@ -658,32 +706,61 @@ int launch_panel(int n, int k0, int jb, double* A, int lda, int* ipiv, int* info
 }
 
 
+int launch_swap_trsm(int n, int k0, int wb, int col_begin, int col_end, double* A, int lda, const int* ipiv, double* B,
+                     int ldb, int nrhs, cudaStream_t s) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        GPB_CHECK_CUDA(cudaFuncSetAttribute(swap_trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        attr_set = true;
+    }
+    const int mat_blocks = (col_end > col_begin) ? (col_end - col_begin + 63) / 64 : 0;
+    const int rhs_blocks = (B != nullptr) ? (nrhs + 63) / 64 : 0;
+    if (mat_blocks + rhs_blocks == 0) return GPB_OK;
+    const size_t smem = (size_t)(wb + 64) * (wb + 1) * sizeof(double);
+    swap_trsm_kernel<<<mat_blocks + rhs_blocks, 256, smem, s>>>(n, k0, wb, col_begin, col_end, A, lda, ipiv, mat_blocks, B, ldb, nrhs);
+    GPB_LAUNCH_CHECK();
+    return GPB_OK;
+}
+
+int launch_gemm(int n, int k0, int K, int col_begin, int col_end, double* A, int lda, cudaStream_t s) {
+    // C[k0+K:, col_begin:col_end] -= A[k0+K:, k0:k0+K] * A[k0:k0+K, col_begin:col_end]
+    const int M = n - k0 - K, N = col_end - col_begin;
+    if (M <= 0 || N <= 0) return GPB_OK;
+    dim3 grid((M + kGM - 1) / kGM, (N + kGN - 1) / kGN);
+    gemm_kernel<<<grid, 256, 0, s>>>(M, N, K, A + (long long)k0 * lda + k0 + K, A + (long long)col_begin * lda + k0,
+                                     A + (long long)col_begin * lda + k0 + K, lda);
+    GPB_LAUNCH_CHECK();
+    return GPB_OK;
+}
+
 int factor_blocked(int n, double* A, int lda, int* ipiv, int* info, double* B, int nrhs, int ldb, cudaStream_t s) {
     zero_info_kernel<<<1, 1, 0, s>>>(info);
     GPB_LAUNCH_CHECK();
-    const int rhs_blocks = (B != nullptr) ? (nrhs + 63) / 64 : 0;
+    const PanelConfig& cfg = panel_config();
+    int rc;
     for (int k0 = 0; k0 < n;) {
-        const int jb = panel_width(n, k0);
-        int rc = launch_panel(n, k0, jb, A, lda, ipiv, info, s);
-        if (rc) return rc;
-        const int nright = n - k0 - jb;
-        const int mat_blocks = (nright + 63) / 64;
-        if (mat_blocks + rhs_blocks > 0) {
-            swap_trsm_kernel<<<mat_blocks + rhs_blocks, 256, 0, s>>>(n, k0, jb, A, lda, ipiv, mat_blocks, B, ldb, nrhs);
+        int w1, w2;
+        outer_widths_hd(n, k0, cfg.cluster, (unsigned long long)cfg.smem_cap, w1, w2);
+        const int wb = w1 + w2;
+        // ---- first panel
+        if ((rc = launch_panel(n, k0, w1, A, lda, ipiv, info, s))) return rc;
+        if (w2 > 0) {
+            // ---- bring the second panel's columns up to date (K = w1), factor it, complete the interchanges of
+            //      the first panel's L columns (LAPACK-style inside the outer block)
+            if ((rc = launch_swap_trsm(n, k0, w1, k0 + w1, k0 + wb, A, lda, ipiv, nullptr, 0, 0, s))) return rc;
+            if ((rc = launch_gemm(n, k0, w1, k0 + w1, k0 + wb, A, lda, s))) return rc;
+            if ((rc = launch_panel(n, k0 + w1, w2, A, lda, ipiv, info, s))) return rc;
+            swap_cols_kernel<<<(w1 + 63) / 64, 64, 0, s>>>(A, lda, ipiv, k0 + w1, k0 + wb, k0, k0 + w1);
             GPB_LAUNCH_CHECK();
         }
-        if (nright > 0) {
-            const int M = n - k0 - jb;
-            dim3 grid((M + kGM - 1) / kGM, (nright + kGN - 1) / kGN);
-            gemm_kernel<<<grid, 256, 0, s>>>(M, nright, jb, A + (long long)k0 * lda + k0 + jb,
-                                             A + (long long)(k0 + jb) * lda + k0, A + (long long)(k0 + jb) * lda + k0 + jb, lda);
+        // ---- everything right of the outer block (and the right-hand sides): interchanges, U12, trailing update (K = wb)
+        if ((rc = launch_swap_trsm(n, k0, wb, k0 + wb, n, A, lda, ipiv, B, ldb, nrhs, s))) return rc;
+        if ((rc = launch_gemm(n, k0, wb, k0 + wb, n, A, lda, s))) return rc;
+        if (B != nullptr && n - k0 - wb > 0) {
+            rhs_update_kernel<<<(n - k0 - wb + 255) / 256, 256, 0, s>>>(n, k0, wb, A, lda, B, ldb, nrhs);
             GPB_LAUNCH_CHECK();
-            if (B != nullptr) {
-                rhs_update_kernel<<<(M + 255) / 256, 256, 0, s>>>(n, k0, jb, A, lda, B, ldb, nrhs);
-                GPB_LAUNCH_CHECK();
-            }
         }
-        k0 += jb;
+        k0 += wb;
     }
     return GPB_OK;
 }
