@@ -83,3 +83,47 @@ extern "C" int gpb_bench_dfma(int iters, double* tflops_host, void* stream) {
     cudaFree(d);
     return GPB_OK;
 }
+
+// ---- FP64 tensor-core (DMMA m8n8k4) microbenchmark: is mma.sync f64 faster than the DFMA pipe on this part? ----
+__global__ void __launch_bounds__(256) dmma_chain_kernel(double* out, int iters, double a, double b) {
+    double c[8][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { c[i][0] = threadIdx.x * 1e-3 + i; c[i][1] = c[i][0] + 0.5; }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(c[i][0]), "+d"(c[i][1]) : "d"(a), "d"(b));
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += c[i][0] + c[i][1];
+    if (s == 123.456) out[0] = s;
+}
+
+extern "C" int gpb_bench_dmma(int iters, double* tflops_host, void* stream) {
+    GPB_REQUIRE(iters > 0 && tflops_host, "bad arguments");
+    cudaStream_t s = (cudaStream_t)stream;
+    double* d = nullptr;
+    GPB_CHECK_CUDA(cudaMalloc((void**)&d, sizeof(double)));
+    const int blocks = gpb_sm_count() * 8;
+    cudaEvent_t e0, e1;
+    GPB_CHECK_CUDA(cudaEventCreate(&e0));
+    GPB_CHECK_CUDA(cudaEventCreate(&e1));
+    dmma_chain_kernel<<<blocks, 256, 0, s>>>(d, iters / 10 + 1, 1e-3, 1e-3);
+    GPB_LAUNCH_CHECK();
+    GPB_CHECK_CUDA(cudaEventRecord(e0, s));
+    dmma_chain_kernel<<<blocks, 256, 0, s>>>(d, iters, 1e-3, 1e-3);
+    GPB_LAUNCH_CHECK();
+    GPB_CHECK_CUDA(cudaEventRecord(e1, s));
+    GPB_CHECK_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    GPB_CHECK_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    // one m8n8k4 = 8*8*4 FMA = 512 flop per warp instruction
+    const double flops = 512.0 * 8.0 * (double)iters * 8.0 * (double)blocks;
+    *tflops_host = flops / (ms * 1e-3) / 1e12;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    return GPB_OK;
+}

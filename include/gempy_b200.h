@@ -84,6 +84,9 @@ long long gpb_launch_count(void);
 /* Measured FP64 FMA throughput of the current device (register-resident DFMA chains, 8 per thread), in
  * TFLOP/s (FMA = 2).  Used as the roofline denominator of the evaluation kernel.  Synchronises. (host out) */
 int gpb_bench_dfma(int iters, double* tflops_host, void* stream);
+/* Same for the FP64 tensor-core path (mma.sync m8n8k4 chains): decides whether the LU trailing update belongs on
+ * DMMA or on the DFMA pipe on this part. */
+int gpb_bench_dmma(int iters, double* tflops_host, void* stream);
 
 /* ---- (1) covariance assembly  [engine stage "kernel_constructor", SURVEY 8a2 row (1)] ------------ */
 /* n = 3*n_ori + n_rest + n_drift + n_faults.  Writes the full symmetric n x n matrix A (lda >= n) and the
