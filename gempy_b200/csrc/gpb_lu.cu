@@ -347,6 +347,140 @@ panel_cluster_kernel(int n, int k0, int jb, double* __restrict__ A, int lda, int
     cluster.sync();                                // no CTA exits while a neighbour may still address its smem
 }
 
+
+// -----------------------------------------------------------------------------------------------------
+// Register-resident cluster panel (m <= cluster * 512 rows): every thread owns ONE row of the panel and keeps its
+// jb <= 32 entries in registers for the whole factorisation of the panel, so the rank-1 update is 32 predicated FMAs
+// per column with no shared-memory traffic for the panel itself.  Exchange protocol as in panel_cluster_kernel
+// (one cluster barrier per column).
+// -----------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kPanelThreads, 1)
+panel_reg_kernel(int n, int k0, int jb, double* __restrict__ A, int lda, int* __restrict__ ipiv, int* __restrict__ info, int R) {
+    __shared__ PanelExchange ex[2];
+    __shared__ __align__(16) double crow[kNB];     // this CTA's candidate row
+    __shared__ __align__(16) double trow[kNB];     // the current top row (written by its owner thread)
+    __shared__ double red_v[kPanelThreads / 32];
+    __shared__ int red_i[kPanelThreads / 32];
+    __shared__ double loc_v;
+    __shared__ int loc_i, win_s, piv_s;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int C = (int)cluster.num_blocks();
+    const int rank = (int)cluster.block_rank();
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int r0 = k0 + rank * R;
+    const int nrows = max(0, min(n, r0 + R) - r0);
+    const bool have = tid < nrows;
+    const int gi = r0 + tid;                        // this thread's global row
+
+    double v[kNB];
+#pragma unroll
+    for (int c = 0; c < kNB; ++c) v[c] = (have && c < jb) ? A[(long long)(k0 + c) * lda + gi] : 0.0;
+    double cur = v[0];                              // this row's entry in the current column
+    cluster.sync();
+
+    for (int j = 0; j < jb; ++j) {
+        const int kj = k0 + j;
+        const int buf = j & 1;
+        // ---- (1) CTA-wide pivot candidate among rows >= kj
+        double best = (have && gi >= kj) ? fabs(cur) : -1.0;
+        int bi = (have && gi >= kj) ? gi : n;
+        for (int o = 16; o > 0; o >>= 1)
+            better(best, bi, __shfl_down_sync(0xffffffffu, best, o), __shfl_down_sync(0xffffffffu, bi, o));
+        if (lane == 0) { red_v[warp] = best; red_i[warp] = bi; }
+        __syncthreads();
+        if (warp == 0) {
+            double bv = lane < kPanelThreads / 32 ? red_v[lane] : -1.0;
+            int ii = lane < kPanelThreads / 32 ? red_i[lane] : n;
+            for (int o = 8; o > 0; o >>= 1)
+                better(bv, ii, __shfl_down_sync(0xffffffffu, bv, o), __shfl_down_sync(0xffffffffu, ii, o));
+            if (lane == 0) { loc_v = bv; loc_i = ii; }
+        }
+        __syncthreads();
+        const double my_v = loc_v;
+        const int my_i = loc_i;
+        const int owner_t = (kj - k0) / R;
+        // ---- (2) stage the candidate row / the top row from their owner threads' registers
+        if (have && gi == my_i) {
+#pragma unroll
+            for (int c = 0; c < kNB; ++c) crow[c] = v[c];
+        }
+        if (have && gi == kj) {
+#pragma unroll
+            for (int c = 0; c < kNB; ++c) trow[c] = v[c];
+        }
+        __syncthreads();
+        for (int e = tid; e < C * jb; e += kPanelThreads) {
+            const int dst = e / jb, c = e - dst * jb;
+            PanelExchange* rx = cluster.map_shared_rank(&ex[buf], dst);
+            rx->cand_row[rank][c] = (my_i < n) ? crow[c] : 0.0;
+            if (rank == owner_t) rx->top_row[c] = trow[c];
+        }
+        if (tid < C) {
+            PanelExchange* rx = cluster.map_shared_rank(&ex[buf], tid);
+            rx->cand_v[rank] = my_v;
+            rx->cand_i[rank] = my_i;
+        }
+        cluster.sync();                            // the only cluster barrier of this column
+        // ---- (3) election by one warp
+        if (warp == 0) {
+            double gv = lane < C ? ex[buf].cand_v[lane] : -1.0;
+            int gp = lane < C ? ex[buf].cand_i[lane] : n;
+            int gw = lane;
+            for (int o = 8; o > 0; o >>= 1) {
+                const double ov = __shfl_down_sync(0xffffffffu, gv, o);
+                const int oi = __shfl_down_sync(0xffffffffu, gp, o);
+                const int ow = __shfl_down_sync(0xffffffffu, gw, o);
+                if (ov > gv || (ov == gv && oi < gp)) { gv = ov; gp = oi; gw = ow; }
+            }
+            if (lane == 0) {
+                win_s = gw;
+                piv_s = gp;
+                if (rank == 0) {
+                    ipiv[kj] = gp;
+                    if (gv == 0.0 && info && *info == 0) *info = kj + 1;
+                }
+            }
+        }
+        __syncthreads();
+        const int p = piv_s;
+        const double* prow = ex[buf].cand_row[win_s];
+        // ---- (4) interchange: the owner of row kj takes the pivot row, the owner of row p the old top row
+        if (p != kj && have) {
+            if (gi == kj) {
+#pragma unroll
+                for (int c = 0; c < kNB; ++c) v[c] = prow[c];
+            } else if (gi == p) {
+#pragma unroll
+                for (int c = 0; c < kNB; ++c) {
+                    v[c] = ex[buf].top_row[c];
+                    if (c == j) cur = v[c];
+                }
+            }
+        }
+        // ---- (5) rank-1 update of this thread's row (pivot row read with 16-byte broadcast loads); remember its
+        //      entry in the next column
+        const double pvj = prow[j];
+        const double inv = pvj != 0.0 ? 1.0 / pvj : 0.0;
+        if (have && gi > kj) {
+            const double l = cur * inv;
+#pragma unroll
+            for (int c = 0; c < kNB; c += 2) {
+                const double2 t2 = *reinterpret_cast<const double2*>(prow + c);
+                if (c == j) v[c] = l;
+                else if (c > j) v[c] = fma(-l, t2.x, v[c]);
+                if (c == j + 1) cur = v[c];
+                if (c + 1 == j) v[c + 1] = l;
+                else if (c + 1 > j) v[c + 1] = fma(-l, t2.y, v[c + 1]);
+                if (c + 1 == j + 1) cur = v[c + 1];
+            }
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < kNB; ++c)
+        if (have && c < jb) A[(long long)(k0 + c) * lda + gi] = v[c];
+    cluster.sync();
+}
+
 // Apply the interchanges ipiv[k0 .. k0+wb) to the matrix columns [col_begin, col_end) and solve
 // U12 = L11^-1 A12 with the wb x wb unit-lower block at (k0, k0).  One CTA handles 64 columns.
 // Blocks beyond the matrix' own column blocks work on the right-hand sides B (n x nrhs, ldb): the forward
@@ -649,6 +783,7 @@ const PanelConfig& panel_config() {
         return cfg;
     }
     cudaFuncSetAttribute(panel_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    cudaFuncSetAttribute(panel_reg_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     cudaGetLastError();
     for (int c : {16, 8, 4, 2}) {
         cudaLaunchConfig_t lc{};
@@ -690,6 +825,20 @@ int launch_panel(int n, int k0, int jb, double* A, int lda, int* ipiv, int* info
     const int m = n - k0;
     int R = (m + cfg.cluster - 1) / cfg.cluster;
     if (R < 1) R = 1;
+    if (R <= kPanelThreads) {                       // one row per thread: register-resident panel
+        cudaLaunchConfig_t lr{};
+        lr.gridDim = dim3(cfg.cluster);
+        lr.blockDim = dim3(kPanelThreads);
+        lr.dynamicSmemBytes = 0;
+        lr.stream = s;
+        cudaLaunchAttribute ar[1];
+        ar[0].id = cudaLaunchAttributeClusterDimension;
+        ar[0].val.clusterDim.x = cfg.cluster; ar[0].val.clusterDim.y = 1; ar[0].val.clusterDim.z = 1;
+        lr.attrs = ar; lr.numAttrs = 1;
+        GPB_CHECK_CUDA(cudaLaunchKernelEx(&lr, panel_reg_kernel, n, k0, jb, A, lda, ipiv, info, R));
+        ++g_gpb_launches;
+        return GPB_OK;
+    }
     const int ldp = (R + 1) & ~1;
     cudaLaunchConfig_t lc{};
     lc.gridDim = dim3(cfg.cluster);
