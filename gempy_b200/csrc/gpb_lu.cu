@@ -233,8 +233,8 @@ panel_cluster_kernel(int n, int k0, int jb, double* __restrict__ A, int lda, int
     __shared__ PanelExchange ex[2];                // double buffered by column parity
     __shared__ double red_v[kPanelThreads / 32];
     __shared__ int red_i[kPanelThreads / 32];
-    __shared__ double loc_v;
-    __shared__ int loc_i;
+    __shared__ double loc_v, inv_s;
+    __shared__ int loc_i, win_s, piv_s;
     cg::cluster_group cluster = cg::this_cluster();
     const int C = (int)cluster.num_blocks();
     const int rank = (int)cluster.block_rank();
@@ -288,19 +288,31 @@ panel_cluster_kernel(int n, int k0, int jb, double* __restrict__ A, int lda, int
             rx->cand_i[rank] = my_i;
         }
         cluster.sync();                            // the only cluster barrier of this column
-        // ---- (3) everybody elects the same pivot
-        double gv = ex[buf].cand_v[0];
-        int p = ex[buf].cand_i[0], win = 0;
-        for (int c = 1; c < C; ++c) {
-            const double cv = ex[buf].cand_v[c];
-            const int ci = ex[buf].cand_i[c];
-            if (cv > gv || (cv == gv && ci < p)) { gv = cv; p = ci; win = c; }
+        // ---- (3) one warp elects the pivot (every CTA arrives at the same answer) and inverts it
+        if (warp == 0) {
+            double gv = lane < C ? ex[buf].cand_v[lane] : -1.0;
+            int gp = lane < C ? ex[buf].cand_i[lane] : n;
+            int gw = lane;
+            for (int o = 8; o > 0; o >>= 1) {
+                const double ov = __shfl_down_sync(0xffffffffu, gv, o);
+                const int oi = __shfl_down_sync(0xffffffffu, gp, o);
+                const int ow = __shfl_down_sync(0xffffffffu, gw, o);
+                if (ov > gv || (ov == gv && oi < gp)) { gv = ov; gp = oi; gw = ow; }
+            }
+            if (lane == 0) {
+                win_s = gw;
+                piv_s = gp;
+                const double pvv = ex[buf].cand_row[gw][j];
+                inv_s = pvv != 0.0 ? 1.0 / pvv : 0.0;
+                if (rank == 0) {
+                    ipiv[kj] = gp;
+                    if (gv == 0.0 && info && *info == 0) *info = kj + 1;
+                }
+            }
         }
-        const double* prow = ex[buf].cand_row[win];
-        if (rank == 0 && tid == 0) {
-            ipiv[kj] = p;
-            if (gv == 0.0 && info && *info == 0) *info = kj + 1;
-        }
+        __syncthreads();
+        const int p = piv_s;
+        const double* prow = ex[buf].cand_row[win_s];
         const int owner_p = (p - k0) / R;
         if (p != kj && tid < jb) {
             if (rank == owner_t) P[tid * ldp + (kj - r0)] = prow[tid];
@@ -308,8 +320,7 @@ panel_cluster_kernel(int n, int k0, int jb, double* __restrict__ A, int lda, int
         }
         __syncthreads();
         // ---- (4) rank-1 update of this CTA's rows, fused with the candidate search of column j + 1
-        const double pv = prow[j];
-        const double inv = pv != 0.0 ? 1.0 / pv : 0.0;
+        const double inv = inv_s;
         best = -1.0;
         bi = n;
         for (int i = tid; i < nrows; i += kPanelThreads) {
@@ -348,193 +359,141 @@ panel_cluster_kernel(int n, int k0, int jb, double* __restrict__ A, int lda, int
 }
 
 
-// -----------------------------------------------------------------------------------------------------
-// Register-resident cluster panel (m <= cluster * 512 rows): every thread owns ONE row of the panel and keeps its
-// jb <= 32 entries in registers for the whole factorisation of the panel, so the rank-1 update is 32 predicated FMAs
-// per column with no shared-memory traffic for the panel itself.  Exchange protocol as in panel_cluster_kernel
-// (one cluster barrier per column).
-// -----------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kPanelThreads, 1)
-panel_reg_kernel(int n, int k0, int jb, double* __restrict__ A, int lda, int* __restrict__ ipiv, int* __restrict__ info, int R) {
-    __shared__ PanelExchange ex[2];
-    __shared__ __align__(16) double crow[kNB];     // this CTA's candidate row
-    __shared__ __align__(16) double trow[kNB];     // the current top row (written by its owner thread)
-    __shared__ double red_v[kPanelThreads / 32];
-    __shared__ int red_i[kPanelThreads / 32];
-    __shared__ double loc_v;
-    __shared__ int loc_i, win_s, piv_s;
-    cg::cluster_group cluster = cg::this_cluster();
-    const int C = (int)cluster.num_blocks();
-    const int rank = (int)cluster.block_rank();
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int r0 = k0 + rank * R;
-    const int nrows = max(0, min(n, r0 + R) - r0);
-    const bool have = tid < nrows;
-    const int gi = r0 + tid;                        // this thread's global row
-
-    double v[kNB];
-#pragma unroll
-    for (int c = 0; c < kNB; ++c) v[c] = (have && c < jb) ? A[(long long)(k0 + c) * lda + gi] : 0.0;
-    double cur = v[0];                              // this row's entry in the current column
-    cluster.sync();
-
-    for (int j = 0; j < jb; ++j) {
-        const int kj = k0 + j;
-        const int buf = j & 1;
-        // ---- (1) CTA-wide pivot candidate among rows >= kj
-        double best = (have && gi >= kj) ? fabs(cur) : -1.0;
-        int bi = (have && gi >= kj) ? gi : n;
-        for (int o = 16; o > 0; o >>= 1)
-            better(best, bi, __shfl_down_sync(0xffffffffu, best, o), __shfl_down_sync(0xffffffffu, bi, o));
-        if (lane == 0) { red_v[warp] = best; red_i[warp] = bi; }
-        __syncthreads();
-        if (warp == 0) {
-            double bv = lane < kPanelThreads / 32 ? red_v[lane] : -1.0;
-            int ii = lane < kPanelThreads / 32 ? red_i[lane] : n;
-            for (int o = 8; o > 0; o >>= 1)
-                better(bv, ii, __shfl_down_sync(0xffffffffu, bv, o), __shfl_down_sync(0xffffffffu, ii, o));
-            if (lane == 0) { loc_v = bv; loc_i = ii; }
-        }
-        __syncthreads();
-        const double my_v = loc_v;
-        const int my_i = loc_i;
-        const int owner_t = (kj - k0) / R;
-        // ---- (2) stage the candidate row / the top row from their owner threads' registers
-        if (have && gi == my_i) {
-#pragma unroll
-            for (int c = 0; c < kNB; ++c) crow[c] = v[c];
-        }
-        if (have && gi == kj) {
-#pragma unroll
-            for (int c = 0; c < kNB; ++c) trow[c] = v[c];
-        }
-        __syncthreads();
-        for (int e = tid; e < C * jb; e += kPanelThreads) {
-            const int dst = e / jb, c = e - dst * jb;
-            PanelExchange* rx = cluster.map_shared_rank(&ex[buf], dst);
-            rx->cand_row[rank][c] = (my_i < n) ? crow[c] : 0.0;
-            if (rank == owner_t) rx->top_row[c] = trow[c];
-        }
-        if (tid < C) {
-            PanelExchange* rx = cluster.map_shared_rank(&ex[buf], tid);
-            rx->cand_v[rank] = my_v;
-            rx->cand_i[rank] = my_i;
-        }
-        cluster.sync();                            // the only cluster barrier of this column
-        // ---- (3) election by one warp
-        if (warp == 0) {
-            double gv = lane < C ? ex[buf].cand_v[lane] : -1.0;
-            int gp = lane < C ? ex[buf].cand_i[lane] : n;
-            int gw = lane;
-            for (int o = 8; o > 0; o >>= 1) {
-                const double ov = __shfl_down_sync(0xffffffffu, gv, o);
-                const int oi = __shfl_down_sync(0xffffffffu, gp, o);
-                const int ow = __shfl_down_sync(0xffffffffu, gw, o);
-                if (ov > gv || (ov == gv && oi < gp)) { gv = ov; gp = oi; gw = ow; }
-            }
-            if (lane == 0) {
-                win_s = gw;
-                piv_s = gp;
-                if (rank == 0) {
-                    ipiv[kj] = gp;
-                    if (gv == 0.0 && info && *info == 0) *info = kj + 1;
-                }
-            }
-        }
-        __syncthreads();
-        const int p = piv_s;
-        const double* prow = ex[buf].cand_row[win_s];
-        // ---- (4) interchange: the owner of row kj takes the pivot row, the owner of row p the old top row
-        if (p != kj && have) {
-            if (gi == kj) {
-#pragma unroll
-                for (int c = 0; c < kNB; ++c) v[c] = prow[c];
-            } else if (gi == p) {
-#pragma unroll
-                for (int c = 0; c < kNB; ++c) {
-                    v[c] = ex[buf].top_row[c];
-                    if (c == j) cur = v[c];
-                }
-            }
-        }
-        // ---- (5) rank-1 update of this thread's row (pivot row read with 16-byte broadcast loads); remember its
-        //      entry in the next column
-        const double pvj = prow[j];
-        const double inv = pvj != 0.0 ? 1.0 / pvj : 0.0;
-        if (have && gi > kj) {
-            const double l = cur * inv;
-#pragma unroll
-            for (int c = 0; c < kNB; c += 2) {
-                const double2 t2 = *reinterpret_cast<const double2*>(prow + c);
-                if (c == j) v[c] = l;
-                else if (c > j) v[c] = fma(-l, t2.x, v[c]);
-                if (c == j + 1) cur = v[c];
-                if (c + 1 == j) v[c + 1] = l;
-                else if (c + 1 > j) v[c + 1] = fma(-l, t2.y, v[c + 1]);
-                if (c + 1 == j + 1) cur = v[c + 1];
-            }
+// inv(L11) of the wb x wb unit-lower block at (k0, k0): one thread per column, forward substitution in shared
+// memory.  U12 = L11^-1 A12 then becomes a small matrix product inside swap_trsm_kernel (the usual "TRSM through
+// the inverse of the diagonal block"; |l_ij| <= 1 under partial pivoting, so the inverse is benign).
+constexpr int kWB = 64;          // maximum outer block width
+__global__ void __launch_bounds__(kWB) trinv_kernel(const double* __restrict__ A, int lda, int k0, int wb,
+                                                    double* __restrict__ Linv) {
+    // S[i][j], i > j : L(i, j);  S[j][i], i > j : X(i, j) = inv(L)(i, j)  (the inverse is unit lower too, so it fits
+    // in the unused upper triangle, transposed: thread c owns row c of the upper part)
+    __shared__ double S[kWB][kWB + 1];
+    const int c = threadIdx.x;
+    for (int e = c; e < wb * wb; e += kWB) {
+        const int j = e / wb, i = e - j * wb;
+        if (i > j) S[i][j] = A[(long long)(k0 + j) * lda + k0 + i];
+    }
+    __syncthreads();
+    if (c < wb) {
+        for (int i = c + 1; i < wb; ++i) {
+            double acc = S[i][c];                       // k = c term: L(i, c) * X(c, c) = L(i, c)
+            for (int k = c + 1; k < i; ++k) acc = fma(S[i][k], S[c][k], acc);
+            S[c][i] = -acc;
         }
     }
-#pragma unroll
-    for (int c = 0; c < kNB; ++c)
-        if (have && c < jb) A[(long long)(k0 + c) * lda + gi] = v[c];
-    cluster.sync();
+    __syncthreads();
+    for (int e = c; e < wb * wb; e += kWB) {
+        const int j = e / wb, i = e - j * wb;
+        Linv[j * kWB + i] = (i > j) ? S[j][i] : (i == j ? 1.0 : 0.0);     // column-major, ld = kWB
+    }
 }
 
-// Apply the interchanges ipiv[k0 .. k0+wb) to the matrix columns [col_begin, col_end) and solve
-// U12 = L11^-1 A12 with the wb x wb unit-lower block at (k0, k0).  One CTA handles 64 columns.
-// Blocks beyond the matrix' own column blocks work on the right-hand sides B (n x nrhs, ldb): the forward
-// substitution of gpb_lu_solve is carried along with the factorisation.
-constexpr int kWB = 64;          // maximum outer block width
+// Apply the interchanges ipiv[k0 .. k0+wb) to the matrix columns [col_begin, col_end) and form
+// U12 = inv(L11) * A12.  One CTA handles 64 columns; blocks beyond the matrix' own column blocks work on the
+// right-hand sides B (n x nrhs, ldb): the forward substitution of gpb_lu_solve rides along with the factorisation.
+//   1. the wb top rows of the 64 columns are staged in shared memory (coalesced);
+//   2. the rows p >= k0 + wb touched by the interchanges are gathered in parallel (they are distinct unless
+//      `dup` says otherwise, in which case the gather is serialised per column);
+//   3. each column replays the interchange sequence in shared memory;
+//   4. the displaced values go back to their rows, U12 = Linv * T is computed from shared memory (4 x 4 register
+//      tiles) and written back.
 __global__ void __launch_bounds__(256) swap_trsm_kernel(int n, int k0, int wb, int col_begin, int col_end,
                                                         double* __restrict__ A, int lda, const int* __restrict__ ipiv,
-                                                        int n_mat_blocks, double* __restrict__ B, int ldb, int nrhs) {
+                                                        const double* __restrict__ Linv, int n_mat_blocks,
+                                                        double* __restrict__ B, int ldb, int nrhs) {
     extern __shared__ double sm_st[];
-    const int ldl = wb + 1;
-    double* L = sm_st;                         // [wb][ldl]
-    double* T = sm_st + wb * ldl;              // [64][ldl]
+    constexpr int LD = kWB + 1;
+    double* Li = sm_st;                        // [k][i] : Linv(i, k) at Li[k * LD + i]
+    double* T = sm_st + kWB * LD;              // [c][i] : top rows of column c
+    double* G = sm_st + 2 * kWB * LD;          // [c][j] : value living at row ipiv[k0 + j] of column c
     __shared__ int piv[kWB];
+    __shared__ int dup;
     const int tid = threadIdx.x;
     const bool on_rhs = (int)blockIdx.x >= n_mat_blocks;
     const int c0 = on_rhs ? ((int)blockIdx.x - n_mat_blocks) * 64 : col_begin + blockIdx.x * 64;
     const int ncol = on_rhs ? min(64, nrhs - c0) : min(64, col_end - c0);
     double* const M = on_rhs ? B : A;              // the columns this block transforms
     const int ldm = on_rhs ? ldb : lda;
-    for (int e = tid; e < wb * wb; e += 256) {
-        const int j = e / wb, i = e - j * wb;
-        L[i * ldl + j] = A[(long long)(k0 + j) * lda + k0 + i];
-    }
+    if (tid == 0) dup = 0;
     if (tid < wb) piv[tid] = ipiv[k0 + tid];
+    for (int e = tid; e < wb * wb; e += 256) {
+        const int k = e / wb, i = e - k * wb;
+        Li[k * LD + i] = Linv[k * kWB + i];
+    }
+    for (int e = tid; e < ncol * wb; e += 256) {
+        const int c = e / wb, i = e - c * wb;
+        T[c * LD + i] = M[(long long)(c0 + c) * ldm + k0 + i];
+    }
     __syncthreads();
-    // interchanges: one thread per column, sequential over the block's pivots
+    // a row below the block that is the target of two interchanges makes the gather order-dependent
+    if (tid < wb && piv[tid] >= k0 + wb)
+        for (int j2 = 0; j2 < tid; ++j2)
+            if (piv[j2] == piv[tid]) dup = 1;
+    __syncthreads();
+    const bool serial = dup != 0;
+    if (!serial) {
+        for (int e = tid; e < ncol * wb; e += 256) {
+            const int c = e / wb, j = e - c * wb;
+            if (piv[j] >= k0 + wb) G[c * LD + j] = M[(long long)(c0 + c) * ldm + piv[j]];
+        }
+    }
+    __syncthreads();
     if (tid < ncol) {
-        double* c = M + (long long)(c0 + tid) * ldm;
+        const int c = tid;
+        double* col = M + (long long)(c0 + c) * ldm;
         for (int j = 0; j < wb; ++j) {
             const int p = piv[j];
-            if (p != k0 + j) { const double t = c[k0 + j]; c[k0 + j] = c[p]; c[p] = t; }
-        }
-    }
-    __syncthreads();
-    for (int e = tid; e < ncol * wb; e += 256) {
-        const int c = e / wb, i = e - c * wb;
-        T[c * ldl + i] = M[(long long)(c0 + c) * ldm + k0 + i];
-    }
-    __syncthreads();
-    // 4 threads per column: the updates of rows i > k are split over them
-    {
-        const int c = tid >> 2, part = tid & 3;
-        for (int k = 0; k < wb; ++k) {
-            if (c < ncol) {
-                const double xk = T[c * ldl + k];
-                for (int i = k + 1 + part; i < wb; i += 4) T[c * ldl + i] = fma(-L[i * ldl + k], xk, T[c * ldl + i]);
+            if (p == k0 + j) continue;
+            if (p < k0 + wb) {
+                const double t = T[c * LD + j];
+                T[c * LD + j] = T[c * LD + (p - k0)];
+                T[c * LD + (p - k0)] = t;
+            } else if (!serial) {
+                const double t = T[c * LD + j];
+                T[c * LD + j] = G[c * LD + j];
+                G[c * LD + j] = t;
+            } else {
+                const double t = T[c * LD + j];
+                T[c * LD + j] = col[p];
+                col[p] = t;
             }
-            __syncwarp();
         }
     }
     __syncthreads();
-    for (int e = tid; e < ncol * wb; e += 256) {
-        const int c = e / wb, i = e - c * wb;
-        M[(long long)(c0 + c) * ldm + k0 + i] = T[c * ldl + i];
+    if (!serial) {
+        for (int e = tid; e < ncol * wb; e += 256) {
+            const int c = e / wb, j = e - c * wb;
+            if (piv[j] >= k0 + wb && piv[j] != k0 + j) M[(long long)(c0 + c) * ldm + piv[j]] = G[c * LD + j];
+        }
+    }
+    // U = Linv * T : thread (ti, tc) -> rows 4 ti .. 4 ti + 3, columns 4 tc .. 4 tc + 3
+    const int ti = tid & 15, tc = tid >> 4;
+    double acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b2 = 0; b2 < 4; ++b2) acc[a][b2] = 0.0;
+    for (int k = 0; k < wb; ++k) {
+        double lv[4], tv[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) lv[a] = Li[k * LD + 4 * ti + a];
+#pragma unroll
+        for (int b2 = 0; b2 < 4; ++b2) tv[b2] = T[(4 * tc + b2) * LD + k];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b2 = 0; b2 < 4; ++b2) acc[a][b2] = fma(lv[a], tv[b2], acc[a][b2]);
+    }
+#pragma unroll
+    for (int b2 = 0; b2 < 4; ++b2) {
+        const int c = 4 * tc + b2;
+        if (c < ncol) {
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                const int i = 4 * ti + a;
+                if (i < wb) M[(long long)(c0 + c) * ldm + k0 + i] = acc[a][b2];
+            }
+        }
     }
 }
 
@@ -628,64 +587,86 @@ __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, do
                  : "d"(a), "d"(b));
 }
 
-constexpr int kGM = 64, kGN = 64;       // CTA tile
-constexpr int kLdA = kGM + 8;           // As[k][m]: ld = 8 mod 16 doubles -> 2 wavefronts per fragment load (optimal)
-constexpr int kLdB = kNB + 4;           // Bs[n][k]: ld = 4 mod 16 doubles
+// ---- DMMA trailing update, 128 x 64 CTA tile, K in stages of 32 double-buffered with cp.async --------------
+// acc = L21 * U12 is accumulated from zero in registers (4 x 4 m8n8 tiles per warp) while the next K stage streams
+// into the other shared-memory buffer; C is read once at the end: C -= acc.
+constexpr int kTM = 128, kTN = 64;
+constexpr int kLdA2 = kTM + 8;          // 8 mod 16 doubles
+constexpr int kLdB2 = kNB + 4;          // 4 mod 16 doubles
+constexpr int kStageDoubles = kNB * kLdA2 + kTN * kLdB2;
 
-__global__ void __launch_bounds__(256) gemm_kernel(int M, int N, int K, const double* __restrict__ Ap, const double* __restrict__ Bp,
-                                                   double* __restrict__ C, int lda) {
-    __shared__ double As[kNB * kLdA];
-    __shared__ double Bs[kGN * kLdB];
+__device__ __forceinline__ void cp_async8(double* dst_smem, const double* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(gpb_smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__global__ void __launch_bounds__(256) gemm128_kernel(int M, int N, int K, const double* __restrict__ Ap,
+                                                      const double* __restrict__ Bp, double* __restrict__ C, int lda) {
+    extern __shared__ double sm_g[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int m0 = blockIdx.x * kGM, n0 = blockIdx.y * kGN;
-    // 8 warps: 2 along M (32 rows each) x 4 along N (16 cols each); warp tile 32 x 16 = 4 x 2 m8n8 tiles
-    const int wm = (warp & 1) * 32, wn = (warp >> 1) * 16;
+    const int m0 = blockIdx.x * kTM, n0 = blockIdx.y * kTN;
+    const int wm = (warp & 3) * 32, wn = (warp >> 2) * 32;
     const int r = lane >> 2, q = lane & 3;
-    constexpr int NJ = 2;
-    double acc[4][NJ][2];
+
+    auto stage_in = [&](int st, int kh) {
+        double* As = sm_g + st * kStageDoubles;
+        double* Bs = As + kNB * kLdA2;
+        const int kc = min(kNB, K - kh);
+        for (int e = tid; e < kNB * kTM; e += 256) {
+            const int k = e / kTM, m = e - k * kTM;
+            if (k < kc && m0 + m < M) cp_async8(As + k * kLdA2 + m, Ap + (long long)(kh + k) * lda + m0 + m);
+            else As[k * kLdA2 + m] = 0.0;
+        }
+        for (int e = tid; e < kTN * kNB; e += 256) {
+            const int nn = e / kNB, k = e - nn * kNB;
+            if (k < kc && n0 + nn < N) cp_async8(Bs + nn * kLdB2 + k, Bp + (long long)(n0 + nn) * lda + kh + k);
+            else Bs[nn * kLdB2 + k] = 0.0;
+        }
+        cp_async_commit();
+    };
+
+    double acc[4][4][2];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < NJ; ++j) {
-            const int gm = m0 + wm + 8 * i + r;
-            const int gn = n0 + wn + 8 * j + 2 * q;
-            acc[i][j][0] = (gm < M && gn < N) ? C[(long long)gn * lda + gm] : 0.0;
-            acc[i][j][1] = (gm < M && gn + 1 < N) ? C[(long long)(gn + 1) * lda + gm] : 0.0;
-        }
-    // K (<= 64) is consumed in halves of kNB through the same shared-memory stage; C stays in registers
-    for (int kh = 0; kh < K; kh += kNB) {
-        const int kc = min(kNB, K - kh);
-        if (kh) __syncthreads();
-        // stage A: columns k are contiguous in m
-        for (int e = tid; e < kNB * kGM; e += 256) {
-            const int k = e / kGM, m = e - k * kGM;
-            As[k * kLdA + m] = (k < kc && m0 + m < M) ? -Ap[(long long)(kh + k) * lda + m0 + m] : 0.0;     // negated: C += (-A) B
-        }
-        for (int e = tid; e < kGN * kNB; e += 256) {
-            const int nn = e / kNB, k = e - nn * kNB;
-            Bs[nn * kLdB + k] = (k < kc && n0 + nn < N) ? Bp[(long long)(n0 + nn) * lda + kh + k] : 0.0;
+        for (int j = 0; j < 4; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+
+    const int n_stages = (K + kNB - 1) / kNB;
+    stage_in(0, 0);
+    for (int st = 0; st < n_stages; ++st) {
+        if (st + 1 < n_stages) {
+            stage_in((st + 1) & 1, (st + 1) * kNB);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
         }
         __syncthreads();
+        const double* As = sm_g + (st & 1) * kStageDoubles;
+        const double* Bs = As + kNB * kLdA2;
+#pragma unroll 2
         for (int ks = 0; ks < kNB; ks += 4) {
-            double a[4], b[NJ];
+            double a[4], b[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) a[i] = As[(ks + q) * kLdA + wm + 8 * i + r];
+            for (int i = 0; i < 4; ++i) a[i] = As[(ks + q) * kLdA2 + wm + 8 * i + r];
 #pragma unroll
-            for (int j = 0; j < NJ; ++j) b[j] = Bs[(wn + 8 * j + r) * kLdB + ks + q];
+            for (int j = 0; j < 4; ++j) b[j] = Bs[(wn + 8 * j + r) * kLdB2 + ks + q];
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int j = 0; j < NJ; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+                for (int j = 0; j < 4; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
         }
+        __syncthreads();               // the buffer may be refilled two stages later
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < NJ; ++j) {
+        for (int j = 0; j < 4; ++j) {
             const int gm = m0 + wm + 8 * i + r;
             const int gn = n0 + wn + 8 * j + 2 * q;
-            if (gm < M && gn < N) C[(long long)gn * lda + gm] = acc[i][j][0];
-            if (gm < M && gn + 1 < N) C[(long long)(gn + 1) * lda + gm] = acc[i][j][1];
+            if (gm < M && gn < N) C[(long long)gn * lda + gm] -= acc[i][j][0];
+            if (gm < M && gn + 1 < N) C[(long long)(gn + 1) * lda + gm] -= acc[i][j][1];
         }
 }
 
@@ -783,7 +764,6 @@ const PanelConfig& panel_config() {
         return cfg;
     }
     cudaFuncSetAttribute(panel_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-    cudaFuncSetAttribute(panel_reg_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     cudaGetLastError();
     for (int c : {16, 8, 4, 2}) {
         cudaLaunchConfig_t lc{};
@@ -825,20 +805,6 @@ int launch_panel(int n, int k0, int jb, double* A, int lda, int* ipiv, int* info
     const int m = n - k0;
     int R = (m + cfg.cluster - 1) / cfg.cluster;
     if (R < 1) R = 1;
-    if (R <= kPanelThreads) {                       // one row per thread: register-resident panel
-        cudaLaunchConfig_t lr{};
-        lr.gridDim = dim3(cfg.cluster);
-        lr.blockDim = dim3(kPanelThreads);
-        lr.dynamicSmemBytes = 0;
-        lr.stream = s;
-        cudaLaunchAttribute ar[1];
-        ar[0].id = cudaLaunchAttributeClusterDimension;
-        ar[0].val.clusterDim.x = cfg.cluster; ar[0].val.clusterDim.y = 1; ar[0].val.clusterDim.z = 1;
-        lr.attrs = ar; lr.numAttrs = 1;
-        GPB_CHECK_CUDA(cudaLaunchKernelEx(&lr, panel_reg_kernel, n, k0, jb, A, lda, ipiv, info, R));
-        ++g_gpb_launches;
-        return GPB_OK;
-    }
     const int ldp = (R + 1) & ~1;
     cudaLaunchConfig_t lc{};
     lc.gridDim = dim3(cfg.cluster);
@@ -855,18 +821,21 @@ int launch_panel(int n, int k0, int jb, double* A, int lda, int* ipiv, int* info
 }
 
 
-int launch_swap_trsm(int n, int k0, int wb, int col_begin, int col_end, double* A, int lda, const int* ipiv, double* B,
-                     int ldb, int nrhs, cudaStream_t s) {
+int launch_swap_trsm(int n, int k0, int wb, int col_begin, int col_end, double* A, int lda, const int* ipiv, double* Linv,
+                     double* B, int ldb, int nrhs, cudaStream_t s) {
     static bool attr_set = false;
     if (!attr_set) {
-        GPB_CHECK_CUDA(cudaFuncSetAttribute(swap_trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        GPB_CHECK_CUDA(cudaFuncSetAttribute(swap_trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
         attr_set = true;
     }
     const int mat_blocks = (col_end > col_begin) ? (col_end - col_begin + 63) / 64 : 0;
     const int rhs_blocks = (B != nullptr) ? (nrhs + 63) / 64 : 0;
     if (mat_blocks + rhs_blocks == 0) return GPB_OK;
-    const size_t smem = (size_t)(wb + 64) * (wb + 1) * sizeof(double);
-    swap_trsm_kernel<<<mat_blocks + rhs_blocks, 256, smem, s>>>(n, k0, wb, col_begin, col_end, A, lda, ipiv, mat_blocks, B, ldb, nrhs);
+    trinv_kernel<<<1, kWB, 0, s>>>(A, lda, k0, wb, Linv);
+    GPB_LAUNCH_CHECK();
+    const size_t smem = (size_t)3 * kWB * (kWB + 1) * sizeof(double);
+    swap_trsm_kernel<<<mat_blocks + rhs_blocks, 256, smem, s>>>(n, k0, wb, col_begin, col_end, A, lda, ipiv, Linv, mat_blocks,
+                                                                B, ldb, nrhs);
     GPB_LAUNCH_CHECK();
     return GPB_OK;
 }
@@ -875,9 +844,15 @@ int launch_gemm(int n, int k0, int K, int col_begin, int col_end, double* A, int
     // C[k0+K:, col_begin:col_end] -= A[k0+K:, k0:k0+K] * A[k0:k0+K, col_begin:col_end]
     const int M = n - k0 - K, N = col_end - col_begin;
     if (M <= 0 || N <= 0) return GPB_OK;
-    dim3 grid((M + kGM - 1) / kGM, (N + kGN - 1) / kGN);
-    gemm_kernel<<<grid, 256, 0, s>>>(M, N, K, A + (long long)k0 * lda + k0 + K, A + (long long)col_begin * lda + k0,
-                                     A + (long long)col_begin * lda + k0 + K, lda);
+    static bool attr_set = false;
+    const size_t smem = (size_t)2 * kStageDoubles * sizeof(double);
+    if (!attr_set) {
+        GPB_CHECK_CUDA(cudaFuncSetAttribute(gemm128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    dim3 grid((M + kTM - 1) / kTM, (N + kTN - 1) / kTN);
+    gemm128_kernel<<<grid, 256, smem, s>>>(M, N, K, A + (long long)k0 * lda + k0 + K, A + (long long)col_begin * lda + k0,
+                                           A + (long long)col_begin * lda + k0 + K, lda);
     GPB_LAUNCH_CHECK();
     return GPB_OK;
 }
@@ -887,6 +862,8 @@ int factor_blocked(int n, double* A, int lda, int* ipiv, int* info, double* B, i
     GPB_LAUNCH_CHECK();
     const PanelConfig& cfg = panel_config();
     int rc;
+    double* Linv = nullptr;                          // inverse of the current diagonal block (kWB x kWB)
+    GPB_CHECK_CUDA(cudaMallocAsync((void**)&Linv, sizeof(double) * kWB * kWB, s));
     for (int k0 = 0; k0 < n;) {
         int w1, w2;
         outer_widths_hd(n, k0, cfg.cluster, (unsigned long long)cfg.smem_cap, w1, w2);
@@ -896,14 +873,14 @@ int factor_blocked(int n, double* A, int lda, int* ipiv, int* info, double* B, i
         if (w2 > 0) {
             // ---- bring the second panel's columns up to date (K = w1), factor it, complete the interchanges of
             //      the first panel's L columns (LAPACK-style inside the outer block)
-            if ((rc = launch_swap_trsm(n, k0, w1, k0 + w1, k0 + wb, A, lda, ipiv, nullptr, 0, 0, s))) return rc;
+            if ((rc = launch_swap_trsm(n, k0, w1, k0 + w1, k0 + wb, A, lda, ipiv, Linv, nullptr, 0, 0, s))) return rc;
             if ((rc = launch_gemm(n, k0, w1, k0 + w1, k0 + wb, A, lda, s))) return rc;
             if ((rc = launch_panel(n, k0 + w1, w2, A, lda, ipiv, info, s))) return rc;
             swap_cols_kernel<<<(w1 + 63) / 64, 64, 0, s>>>(A, lda, ipiv, k0 + w1, k0 + wb, k0, k0 + w1);
             GPB_LAUNCH_CHECK();
         }
         // ---- everything right of the outer block (and the right-hand sides): interchanges, U12, trailing update (K = wb)
-        if ((rc = launch_swap_trsm(n, k0, wb, k0 + wb, n, A, lda, ipiv, B, ldb, nrhs, s))) return rc;
+        if ((rc = launch_swap_trsm(n, k0, wb, k0 + wb, n, A, lda, ipiv, Linv, B, ldb, nrhs, s))) return rc;
         if ((rc = launch_gemm(n, k0, wb, k0 + wb, n, A, lda, s))) return rc;
         if (B != nullptr && n - k0 - wb > 0) {
             rhs_update_kernel<<<(n - k0 - wb + 255) / 256, 256, 0, s>>>(n, k0, wb, A, lda, B, ldb, nrhs);
@@ -911,6 +888,7 @@ int factor_blocked(int n, double* A, int lda, int* ipiv, int* info, double* B, i
         }
         k0 += wb;
     }
+    GPB_CHECK_CUDA(cudaFreeAsync(Linv, s));
     return GPB_OK;
 }
 
