@@ -34,15 +34,6 @@ __host__ __device__ inline int panel_width_hd(int n, int k0, int cluster, unsign
     return (n - k0 < jb) ? n - k0 : jb;
 }
 
-// Outer block at column k0 = two consecutive panels (w1 + w2 <= 64 columns).  Interchanges are LAPACK-style inside an
-// outer block and LINPACK-style across outer blocks; the trailing update uses K = w1 + w2.  Systems that take the
-// shared-memory path (n <= kSmallN) use single 32-column blocks.
-__host__ __device__ inline void outer_widths_hd(int n, int k0, int cluster, unsigned long long smem_cap, int& w1, int& w2) {
-    w1 = panel_width_hd(n, k0, cluster, smem_cap);
-    w2 = 0;
-    if (n > kSmallN && k0 + w1 < n) w2 = panel_width_hd(n, k0 + w1, cluster, smem_cap);
-}
-
 // =====================================================================================================
 // small systems: one CTA, matrix in shared memory
 // =====================================================================================================
@@ -358,161 +349,59 @@ panel_cluster_kernel(int n, int k0, int jb, double* __restrict__ A, int lda, int
     cluster.sync();                                // no CTA exits while a neighbour may still address its smem
 }
 
-
-// inv(L11) of the wb x wb unit-lower block at (k0, k0): one thread per column, forward substitution in shared
-// memory.  U12 = L11^-1 A12 then becomes a small matrix product inside swap_trsm_kernel (the usual "TRSM through
-// the inverse of the diagonal block"; |l_ij| <= 1 under partial pivoting, so the inverse is benign).
-constexpr int kWB = 64;          // maximum outer block width
-__global__ void __launch_bounds__(kWB) trinv_kernel(const double* __restrict__ A, int lda, int k0, int wb,
-                                                    double* __restrict__ Linv) {
-    // S[i][j], i > j : L(i, j);  S[j][i], i > j : X(i, j) = inv(L)(i, j)  (the inverse is unit lower too, so it fits
-    // in the unused upper triangle, transposed: thread c owns row c of the upper part)
-    __shared__ double S[kWB][kWB + 1];
-    const int c = threadIdx.x;
-    for (int e = c; e < wb * wb; e += kWB) {
-        const int j = e / wb, i = e - j * wb;
-        if (i > j) S[i][j] = A[(long long)(k0 + j) * lda + k0 + i];
-    }
-    __syncthreads();
-    if (c < wb) {
-        for (int i = c + 1; i < wb; ++i) {
-            double acc = S[i][c];                       // k = c term: L(i, c) * X(c, c) = L(i, c)
-            for (int k = c + 1; k < i; ++k) acc = fma(S[i][k], S[c][k], acc);
-            S[c][i] = -acc;
-        }
-    }
-    __syncthreads();
-    for (int e = c; e < wb * wb; e += kWB) {
-        const int j = e / wb, i = e - j * wb;
-        Linv[j * kWB + i] = (i > j) ? S[j][i] : (i == j ? 1.0 : 0.0);     // column-major, ld = kWB
-    }
-}
-
-// Apply the interchanges ipiv[k0 .. k0+wb) to the matrix columns [col_begin, col_end) and form
-// U12 = inv(L11) * A12.  One CTA handles 64 columns; blocks beyond the matrix' own column blocks work on the
-// right-hand sides B (n x nrhs, ldb): the forward substitution of gpb_lu_solve rides along with the factorisation.
-//   1. the wb top rows of the 64 columns are staged in shared memory (coalesced);
-//   2. the rows p >= k0 + wb touched by the interchanges are gathered in parallel (they are distinct unless
-//      `dup` says otherwise, in which case the gather is serialised per column);
-//   3. each column replays the interchange sequence in shared memory;
-//   4. the displaced values go back to their rows, U12 = Linv * T is computed from shared memory (4 x 4 register
-//      tiles) and written back.
-__global__ void __launch_bounds__(256) swap_trsm_kernel(int n, int k0, int wb, int col_begin, int col_end,
-                                                        double* __restrict__ A, int lda, const int* __restrict__ ipiv,
-                                                        const double* __restrict__ Linv, int n_mat_blocks,
+// Apply the panel's interchanges to the columns right of the panel and solve U12 = L11^-1 A12.
+// One CTA handles 64 columns.
+// Blocks beyond the matrix' own column blocks work on the right-hand sides B (n x nrhs, ldb): the forward
+// substitution of gpb_lu_solve is carried along with the factorisation.
+__global__ void __launch_bounds__(256) swap_trsm_kernel(int n, int k0, int jb, double* __restrict__ A, int lda,
+                                                        const int* __restrict__ ipiv, int n_mat_blocks,
                                                         double* __restrict__ B, int ldb, int nrhs) {
-    extern __shared__ double sm_st[];
-    constexpr int LD = kWB + 1;
-    double* Li = sm_st;                        // [k][i] : Linv(i, k) at Li[k * LD + i]
-    double* T = sm_st + kWB * LD;              // [c][i] : top rows of column c
-    double* G = sm_st + 2 * kWB * LD;          // [c][j] : value living at row ipiv[k0 + j] of column c
-    __shared__ int piv[kWB];
-    __shared__ int dup;
+    __shared__ double L[kNB][kNB + 1];
+    __shared__ double T[64][kNB + 1];
+    __shared__ int piv[kNB];
     const int tid = threadIdx.x;
     const bool on_rhs = (int)blockIdx.x >= n_mat_blocks;
-    const int c0 = on_rhs ? ((int)blockIdx.x - n_mat_blocks) * 64 : col_begin + blockIdx.x * 64;
-    const int ncol = on_rhs ? min(64, nrhs - c0) : min(64, col_end - c0);
+    const int c0 = on_rhs ? ((int)blockIdx.x - n_mat_blocks) * 64 : k0 + jb + blockIdx.x * 64;
+    const int ncol = on_rhs ? min(64, nrhs - c0) : min(64, n - c0);
     double* const M = on_rhs ? B : A;              // the columns this block transforms
     const int ldm = on_rhs ? ldb : lda;
-    if (tid == 0) dup = 0;
-    if (tid < wb) piv[tid] = ipiv[k0 + tid];
-    for (int e = tid; e < wb * wb; e += 256) {
-        const int k = e / wb, i = e - k * wb;
-        Li[k * LD + i] = Linv[k * kWB + i];
+    for (int e = tid; e < jb * jb; e += 256) {
+        const int j = e / jb, i = e - j * jb;
+        L[i][j] = A[(long long)(k0 + j) * lda + k0 + i];
     }
-    for (int e = tid; e < ncol * wb; e += 256) {
-        const int c = e / wb, i = e - c * wb;
-        T[c * LD + i] = M[(long long)(c0 + c) * ldm + k0 + i];
-    }
+    if (tid < jb) piv[tid] = ipiv[k0 + tid];
     __syncthreads();
-    // a row below the block that is the target of two interchanges makes the gather order-dependent
-    if (tid < wb && piv[tid] >= k0 + wb)
-        for (int j2 = 0; j2 < tid; ++j2)
-            if (piv[j2] == piv[tid]) dup = 1;
-    __syncthreads();
-    const bool serial = dup != 0;
-    if (!serial) {
-        for (int e = tid; e < ncol * wb; e += 256) {
-            const int c = e / wb, j = e - c * wb;
-            if (piv[j] >= k0 + wb) G[c * LD + j] = M[(long long)(c0 + c) * ldm + piv[j]];
+    // interchanges: one thread per column, sequential over the panel's pivots
+    if (tid < ncol) {
+        double* c = M + (long long)(c0 + tid) * ldm;
+        for (int j = 0; j < jb; ++j) {
+            const int p = piv[j];
+            if (p != k0 + j) { const double t = c[k0 + j]; c[k0 + j] = c[p]; c[p] = t; }
         }
+    }
+    __syncthreads();
+    for (int e = tid; e < ncol * jb; e += 256) {
+        const int c = e / jb, i = e - c * jb;
+        T[c][i] = M[(long long)(c0 + c) * ldm + k0 + i];
     }
     __syncthreads();
     if (tid < ncol) {
-        const int c = tid;
-        double* col = M + (long long)(c0 + c) * ldm;
-        for (int j = 0; j < wb; ++j) {
-            const int p = piv[j];
-            if (p == k0 + j) continue;
-            if (p < k0 + wb) {
-                const double t = T[c * LD + j];
-                T[c * LD + j] = T[c * LD + (p - k0)];
-                T[c * LD + (p - k0)] = t;
-            } else if (!serial) {
-                const double t = T[c * LD + j];
-                T[c * LD + j] = G[c * LD + j];
-                G[c * LD + j] = t;
-            } else {
-                const double t = T[c * LD + j];
-                T[c * LD + j] = col[p];
-                col[p] = t;
-            }
+        for (int k = 0; k < jb; ++k) {
+            const double xk = T[tid][k];
+            for (int i = k + 1; i < jb; ++i) T[tid][i] = fma(-L[i][k], xk, T[tid][i]);
         }
     }
     __syncthreads();
-    if (!serial) {
-        for (int e = tid; e < ncol * wb; e += 256) {
-            const int c = e / wb, j = e - c * wb;
-            if (piv[j] >= k0 + wb && piv[j] != k0 + j) M[(long long)(c0 + c) * ldm + piv[j]] = G[c * LD + j];
-        }
-    }
-    // U = Linv * T : thread (ti, tc) -> rows 4 ti .. 4 ti + 3, columns 4 tc .. 4 tc + 3
-    const int ti = tid & 15, tc = tid >> 4;
-    double acc[4][4];
-#pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b2 = 0; b2 < 4; ++b2) acc[a][b2] = 0.0;
-    for (int k = 0; k < wb; ++k) {
-        double lv[4], tv[4];
-#pragma unroll
-        for (int a = 0; a < 4; ++a) lv[a] = Li[k * LD + 4 * ti + a];
-#pragma unroll
-        for (int b2 = 0; b2 < 4; ++b2) tv[b2] = T[(4 * tc + b2) * LD + k];
-#pragma unroll
-        for (int a = 0; a < 4; ++a)
-#pragma unroll
-            for (int b2 = 0; b2 < 4; ++b2) acc[a][b2] = fma(lv[a], tv[b2], acc[a][b2]);
-    }
-#pragma unroll
-    for (int b2 = 0; b2 < 4; ++b2) {
-        const int c = 4 * tc + b2;
-        if (c < ncol) {
-#pragma unroll
-            for (int a = 0; a < 4; ++a) {
-                const int i = 4 * ti + a;
-                if (i < wb) M[(long long)(c0 + c) * ldm + k0 + i] = acc[a][b2];
-            }
-        }
-    }
-}
-
-// Apply the interchanges ipiv[ks .. ke) to the columns [c_begin, c_end) (second panel's swaps on the first
-// panel's L columns: LAPACK-style inside an outer block).
-__global__ void swap_cols_kernel(double* __restrict__ A, int lda, const int* __restrict__ ipiv, int ks, int ke, int c_begin, int c_end) {
-    const int c = c_begin + blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= c_end) return;
-    double* col = A + (long long)c * lda;
-    for (int j = ks; j < ke; ++j) {
-        const int p = ipiv[j];
-        if (p != j) { const double t = col[j]; col[j] = col[p]; col[p] = t; }
+    for (int e = tid; e < ncol * jb; e += 256) {
+        const int c = e / jb, i = e - c * jb;
+        M[(long long)(c0 + c) * ldm + k0 + i] = T[c][i];
     }
 }
 
 // Right-hand sides: B[k0+jb:, :] -= L21 * B[k0:k0+jb, :]   (the gemv twin of the trailing update)
 __global__ void __launch_bounds__(256) rhs_update_kernel(int n, int k0, int jb, const double* __restrict__ A, int lda,
                                                          double* __restrict__ B, int ldb, int nrhs) {
-    __shared__ double xs[kWB];
+    __shared__ double xs[kNB];
     const int i = k0 + jb + blockIdx.x * 256 + threadIdx.x;
     for (int r = 0; r < nrhs; ++r) {
         double* x = B + (long long)r * ldb;
@@ -587,86 +476,59 @@ __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, do
                  : "d"(a), "d"(b));
 }
 
-// ---- DMMA trailing update, 128 x 64 CTA tile, K in stages of 32 double-buffered with cp.async --------------
-// acc = L21 * U12 is accumulated from zero in registers (4 x 4 m8n8 tiles per warp) while the next K stage streams
-// into the other shared-memory buffer; C is read once at the end: C -= acc.
-constexpr int kTM = 128, kTN = 64;
-constexpr int kLdA2 = kTM + 8;          // 8 mod 16 doubles
-constexpr int kLdB2 = kNB + 4;          // 4 mod 16 doubles
-constexpr int kStageDoubles = kNB * kLdA2 + kTN * kLdB2;
+constexpr int kGM = 64, kGN = 64;       // CTA tile
+constexpr int kLdA = kGM + 8;           // As[k][m]: ld = 8 mod 16 doubles -> 2 wavefronts per fragment load (optimal)
+constexpr int kLdB = kNB + 4;           // Bs[n][k]: ld = 4 mod 16 doubles
 
-__device__ __forceinline__ void cp_async8(double* dst_smem, const double* src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(gpb_smem_u32(dst_smem)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-__global__ void __launch_bounds__(256) gemm128_kernel(int M, int N, int K, const double* __restrict__ Ap,
-                                                      const double* __restrict__ Bp, double* __restrict__ C, int lda) {
-    extern __shared__ double sm_g[];
+__global__ void __launch_bounds__(256) gemm_kernel(int M, int N, int K, const double* __restrict__ Ap, const double* __restrict__ Bp,
+                                                   double* __restrict__ C, int lda) {
+    __shared__ double As[kNB * kLdA];
+    __shared__ double Bs[kGN * kLdB];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int m0 = blockIdx.x * kTM, n0 = blockIdx.y * kTN;
-    const int wm = (warp & 3) * 32, wn = (warp >> 2) * 32;
+    const int m0 = blockIdx.x * kGM, n0 = blockIdx.y * kGN;
+    // stage A: columns k are contiguous in m
+    for (int e = tid; e < K * kGM; e += 256) {
+        const int k = e / kGM, m = e - k * kGM;
+        As[k * kLdA + m] = (m0 + m < M) ? -Ap[(long long)k * lda + m0 + m] : 0.0;     // negated: C += (-A) B
+    }
+    for (int e = tid; e < kGN * K; e += 256) {
+        const int nn = e / K, k = e - nn * K;
+        Bs[nn * kLdB + k] = (n0 + nn < N) ? Bp[(long long)(n0 + nn) * lda + k] : 0.0;
+    }
+    __syncthreads();
+    // 8 warps: 2 along M (32 rows each) x 4 along N (16 cols each); warp tile 32 x 16 = 4 x 2 m8n8 tiles
+    const int wm = (warp & 1) * 32, wn = (warp >> 1) * 16;
     const int r = lane >> 2, q = lane & 3;
-
-    auto stage_in = [&](int st, int kh) {
-        double* As = sm_g + st * kStageDoubles;
-        double* Bs = As + kNB * kLdA2;
-        const int kc = min(kNB, K - kh);
-        for (int e = tid; e < kNB * kTM; e += 256) {
-            const int k = e / kTM, m = e - k * kTM;
-            if (k < kc && m0 + m < M) cp_async8(As + k * kLdA2 + m, Ap + (long long)(kh + k) * lda + m0 + m);
-            else As[k * kLdA2 + m] = 0.0;
-        }
-        for (int e = tid; e < kTN * kNB; e += 256) {
-            const int nn = e / kNB, k = e - nn * kNB;
-            if (k < kc && n0 + nn < N) cp_async8(Bs + nn * kLdB2 + k, Bp + (long long)(n0 + nn) * lda + kh + k);
-            else Bs[nn * kLdB2 + k] = 0.0;
-        }
-        cp_async_commit();
-    };
-
-    double acc[4][4][2];
+    constexpr int NJ = 2;
+    double acc[4][NJ][2];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
-
-    const int n_stages = (K + kNB - 1) / kNB;
-    stage_in(0, 0);
-    for (int st = 0; st < n_stages; ++st) {
-        if (st + 1 < n_stages) {
-            stage_in((st + 1) & 1, (st + 1) * kNB);
-            cp_async_wait<1>();
-        } else {
-            cp_async_wait<0>();
+        for (int j = 0; j < NJ; ++j) {
+            const int gm = m0 + wm + 8 * i + r;
+            const int gn = n0 + wn + 8 * j + 2 * q;
+            acc[i][j][0] = (gm < M && gn < N) ? C[(long long)gn * lda + gm] : 0.0;
+            acc[i][j][1] = (gm < M && gn + 1 < N) ? C[(long long)(gn + 1) * lda + gm] : 0.0;
         }
-        __syncthreads();
-        const double* As = sm_g + (st & 1) * kStageDoubles;
-        const double* Bs = As + kNB * kLdA2;
-#pragma unroll 2
-        for (int ks = 0; ks < kNB; ks += 4) {
-            double a[4], b[4];
+    for (int ks = 0; ks < K; ks += 4) {
+        double a[4], b[NJ];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) a[i] = As[(ks + q) * kLdA2 + wm + 8 * i + r];
+        for (int i = 0; i < 4; ++i) a[i] = As[(ks + q) * kLdA + wm + 8 * i + r];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) b[j] = Bs[(wn + 8 * j + r) * kLdB2 + ks + q];
+        for (int j = 0; j < NJ; ++j) b[j] = Bs[(wn + 8 * j + r) * kLdB + ks + q];
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
-        }
-        __syncthreads();               // the buffer may be refilled two stages later
+            for (int j = 0; j < NJ; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < NJ; ++j) {
             const int gm = m0 + wm + 8 * i + r;
             const int gn = n0 + wn + 8 * j + 2 * q;
-            if (gm < M && gn < N) C[(long long)gn * lda + gm] -= acc[i][j][0];
-            if (gm < M && gn + 1 < N) C[(long long)(gn + 1) * lda + gm] -= acc[i][j][1];
+            if (gm < M && gn < N) C[(long long)gn * lda + gm] = acc[i][j][0];
+            if (gm < M && gn + 1 < N) C[(long long)(gn + 1) * lda + gm] = acc[i][j][1];
         }
 }
 
@@ -679,26 +541,19 @@ __global__ void __launch_bounds__(1024) apply_kernel(int n, const double* __rest
     const int tid = threadIdx.x, nt = blockDim.x;
     for (int r = 0; r < nrhs; ++r) {
         double* x = b + (long long)r * ldb;
-        // forward: P, L  (same outer-block schedule as the factorisation: all interchanges of an outer block first,
-        // then its panels one after the other)
-        int next_outer = 0;
+        // forward: P, L  (same panel schedule as the factorisation)
         for (int k0 = 0, jb = 0; k0 < n; k0 += jb) {
             jb = panel_width_hd(n, k0, cluster, smem_cap);
             __syncthreads();
-            if (k0 == next_outer) {
-                int w1, w2;
-                outer_widths_hd(n, k0, cluster, smem_cap, w1, w2);
-                if (tid == 0) {
-                    for (int j = k0; j < k0 + w1 + w2; ++j) {
-                        const int p = ipiv[j];
-                        if (p != j) { const double t = x[j]; x[j] = x[p]; x[p] = t; }
-                    }
-                }
-                next_outer = k0 + w1 + w2;
-            }
             for (int e = tid; e < jb * jb; e += nt) {
                 const int c = e / jb, i = e - c * jb;
                 D[i][c] = LU[(long long)(k0 + c) * lda + k0 + i];
+            }
+            if (tid == 0) {
+                for (int j = 0; j < jb; ++j) {
+                    const int p = ipiv[k0 + j];
+                    if (p != k0 + j) { const double t = x[k0 + j]; x[k0 + j] = x[p]; x[p] = t; }
+                }
             }
             __syncthreads();
             if (tid < 32) {
@@ -787,6 +642,11 @@ const PanelConfig& panel_config() {
 
 // Panel width at column k0 of an n x n factorisation.  A pure function of (n, k0) and the device's cluster
 // configuration, so that gpb_lu_apply replays exactly the panels gpb_lu_factor used.
+int panel_width(int n, int k0) {
+    const PanelConfig& cfg = panel_config();
+    return panel_width_hd(n, k0, cfg.cluster, (unsigned long long)cfg.smem_cap);
+}
+
 bool panel_fits_cluster(int n, int k0, int jb) {
     const PanelConfig& cfg = panel_config();
     if (cfg.cluster == 0) return false;
@@ -821,74 +681,87 @@ int launch_panel(int n, int k0, int jb, double* A, int lda, int* ipiv, int* info
 }
 
 
-int launch_swap_trsm(int n, int k0, int wb, int col_begin, int col_end, double* A, int lda, const int* ipiv, double* Linv,
-                     double* B, int ldb, int nrhs, cudaStream_t s) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        GPB_CHECK_CUDA(cudaFuncSetAttribute(swap_trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
-        attr_set = true;
+struct LookAhead {
+    cudaStream_t panel_stream = nullptr;
+    cudaEvent_t ready = nullptr, panel_done = nullptr;
+    bool ok = false;
+};
+
+LookAhead& look_ahead() {
+    static LookAhead la;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        la.ok = cudaStreamCreateWithPriority(&la.panel_stream, cudaStreamNonBlocking, hi) == cudaSuccess &&
+                cudaEventCreateWithFlags(&la.ready, cudaEventDisableTiming) == cudaSuccess &&
+                cudaEventCreateWithFlags(&la.panel_done, cudaEventDisableTiming) == cudaSuccess;
+        cudaGetLastError();
     }
-    const int mat_blocks = (col_end > col_begin) ? (col_end - col_begin + 63) / 64 : 0;
-    const int rhs_blocks = (B != nullptr) ? (nrhs + 63) / 64 : 0;
-    if (mat_blocks + rhs_blocks == 0) return GPB_OK;
-    trinv_kernel<<<1, kWB, 0, s>>>(A, lda, k0, wb, Linv);
-    GPB_LAUNCH_CHECK();
-    const size_t smem = (size_t)3 * kWB * (kWB + 1) * sizeof(double);
-    swap_trsm_kernel<<<mat_blocks + rhs_blocks, 256, smem, s>>>(n, k0, wb, col_begin, col_end, A, lda, ipiv, Linv, mat_blocks,
-                                                                B, ldb, nrhs);
-    GPB_LAUNCH_CHECK();
-    return GPB_OK;
+    return la;
 }
 
-int launch_gemm(int n, int k0, int K, int col_begin, int col_end, double* A, int lda, cudaStream_t s) {
-    // C[k0+K:, col_begin:col_end] -= A[k0+K:, k0:k0+K] * A[k0:k0+K, col_begin:col_end]
-    const int M = n - k0 - K, N = col_end - col_begin;
-    if (M <= 0 || N <= 0) return GPB_OK;
-    static bool attr_set = false;
-    const size_t smem = (size_t)2 * kStageDoubles * sizeof(double);
-    if (!attr_set) {
-        GPB_CHECK_CUDA(cudaFuncSetAttribute(gemm128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
-    dim3 grid((M + kTM - 1) / kTM, (N + kTN - 1) / kTN);
-    gemm128_kernel<<<grid, 256, smem, s>>>(M, N, K, A + (long long)k0 * lda + k0 + K, A + (long long)col_begin * lda + k0,
-                                           A + (long long)col_begin * lda + k0 + K, lda);
-    GPB_LAUNCH_CHECK();
-    return GPB_OK;
+void launch_gemm(int n, int k0, int jb, int col_begin, int col_end, double* A, int lda, cudaStream_t s) {
+    const int M = n - k0 - jb, N = col_end - col_begin;
+    if (M <= 0 || N <= 0) return;
+    dim3 grid((M + kGM - 1) / kGM, (N + kGN - 1) / kGN);
+    gemm_kernel<<<grid, 256, 0, s>>>(M, N, jb, A + (long long)k0 * lda + k0 + jb, A + (long long)col_begin * lda + k0,
+                                     A + (long long)col_begin * lda + k0 + jb, lda);
+    ++g_gpb_launches;
 }
 
+// Right-looking blocked LU with one-panel look-ahead: as soon as the columns of panel k+1 have received the update of
+// panel k, panel k+1 is factored on a high-priority side stream (a 16-SM cluster) while the main stream finishes the
+// trailing update of panel k on the rest of the matrix.
 int factor_blocked(int n, double* A, int lda, int* ipiv, int* info, double* B, int nrhs, int ldb, cudaStream_t s) {
     zero_info_kernel<<<1, 1, 0, s>>>(info);
     GPB_LAUNCH_CHECK();
-    const PanelConfig& cfg = panel_config();
-    int rc;
-    double* Linv = nullptr;                          // inverse of the current diagonal block (kWB x kWB)
-    GPB_CHECK_CUDA(cudaMallocAsync((void**)&Linv, sizeof(double) * kWB * kWB, s));
-    for (int k0 = 0; k0 < n;) {
-        int w1, w2;
-        outer_widths_hd(n, k0, cfg.cluster, (unsigned long long)cfg.smem_cap, w1, w2);
-        const int wb = w1 + w2;
-        // ---- first panel
-        if ((rc = launch_panel(n, k0, w1, A, lda, ipiv, info, s))) return rc;
-        if (w2 > 0) {
-            // ---- bring the second panel's columns up to date (K = w1), factor it, complete the interchanges of
-            //      the first panel's L columns (LAPACK-style inside the outer block)
-            if ((rc = launch_swap_trsm(n, k0, w1, k0 + w1, k0 + wb, A, lda, ipiv, Linv, nullptr, 0, 0, s))) return rc;
-            if ((rc = launch_gemm(n, k0, w1, k0 + w1, k0 + wb, A, lda, s))) return rc;
-            if ((rc = launch_panel(n, k0 + w1, w2, A, lda, ipiv, info, s))) return rc;
-            swap_cols_kernel<<<(w1 + 63) / 64, 64, 0, s>>>(A, lda, ipiv, k0 + w1, k0 + wb, k0, k0 + w1);
-            GPB_LAUNCH_CHECK();
-        }
-        // ---- everything right of the outer block (and the right-hand sides): interchanges, U12, trailing update (K = wb)
-        if ((rc = launch_swap_trsm(n, k0, wb, k0 + wb, n, A, lda, ipiv, Linv, B, ldb, nrhs, s))) return rc;
-        if ((rc = launch_gemm(n, k0, wb, k0 + wb, n, A, lda, s))) return rc;
-        if (B != nullptr && n - k0 - wb > 0) {
-            rhs_update_kernel<<<(n - k0 - wb + 255) / 256, 256, 0, s>>>(n, k0, wb, A, lda, B, ldb, nrhs);
-            GPB_LAUNCH_CHECK();
-        }
-        k0 += wb;
+    LookAhead& la = look_ahead();
+    const bool ahead = la.ok;
+    cudaStream_t ps = ahead ? la.panel_stream : s;
+    const int rhs_blocks = (B != nullptr) ? (nrhs + 63) / 64 : 0;
+    if (ahead) {                                     // the side stream starts after everything queued on s so far
+        GPB_CHECK_CUDA(cudaEventRecord(la.ready, s));
+        GPB_CHECK_CUDA(cudaStreamWaitEvent(ps, la.ready, 0));
     }
-    GPB_CHECK_CUDA(cudaFreeAsync(Linv, s));
+    int rc = launch_panel(n, 0, panel_width(n, 0), A, lda, ipiv, info, ps);
+    if (rc) return rc;
+    for (int k0 = 0; k0 < n;) {
+        const int jb = panel_width(n, k0);
+        const int k1 = k0 + jb;
+        const int jb1 = (k1 < n) ? panel_width(n, k1) : 0;
+        if (ahead) {                                 // panel k0 (side stream) -> main stream
+            GPB_CHECK_CUDA(cudaEventRecord(la.panel_done, ps));
+            GPB_CHECK_CUDA(cudaStreamWaitEvent(s, la.panel_done, 0));
+        }
+        const int nright = n - k1;
+        const int mat_blocks = (nright + 63) / 64;
+        if (mat_blocks + rhs_blocks > 0) {
+            swap_trsm_kernel<<<mat_blocks + rhs_blocks, 256, 0, s>>>(n, k0, jb, A, lda, ipiv, mat_blocks, B, ldb, nrhs);
+            GPB_LAUNCH_CHECK();
+        }
+        if (jb1 > 0) {
+            // columns of the next panel first, then hand them to the side stream
+            launch_gemm(n, k0, jb, k1, k1 + jb1, A, lda, s);
+            if (ahead) {
+                GPB_CHECK_CUDA(cudaEventRecord(la.ready, s));
+                GPB_CHECK_CUDA(cudaStreamWaitEvent(ps, la.ready, 0));
+            }
+            if ((rc = launch_panel(n, k1, jb1, A, lda, ipiv, info, ps))) return rc;
+            launch_gemm(n, k0, jb, k1 + jb1, n, A, lda, s);
+            if (B != nullptr) {
+                rhs_update_kernel<<<(n - k1 + 255) / 256, 256, 0, s>>>(n, k0, jb, A, lda, B, ldb, nrhs);
+                GPB_LAUNCH_CHECK();
+            }
+        }
+        k0 = k1;
+    }
+    if (ahead) {                                     // nothing of the side stream may outlive the call on s
+        GPB_CHECK_CUDA(cudaEventRecord(la.panel_done, ps));
+        GPB_CHECK_CUDA(cudaStreamWaitEvent(s, la.panel_done, 0));
+    }
+    GPB_CHECK_CUDA(cudaGetLastError());
     return GPB_OK;
 }
 
