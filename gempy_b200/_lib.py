@@ -47,6 +47,7 @@ SIGNATURES = {
     "gpb_launch_count": (_LL, []),
     "gpb_bench_dfma": (C.c_int, [C.c_int, C.POINTER(C.c_double), _P]),
     "gpb_bench_dmma": (C.c_int, [C.c_int, C.POINTER(C.c_double), _P]),
+    "gpb_bench_mixed": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), _P]),
     "gpb_system_size": (C.c_int, [C.POINTER(GpbStack)]),
     "gpb_assemble_cov": (C.c_int, [C.POINTER(GpbStack), _P, C.c_int, _P, _P]),
     "gpb_lu_solve": (C.c_int, [C.c_int, _P, C.c_int, _P, C.c_int, C.c_int, _P, _P, _P]),

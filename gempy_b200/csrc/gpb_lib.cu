@@ -127,3 +127,65 @@ extern "C" int gpb_bench_dmma(int iters, double* tflops_host, void* stream) {
     cudaFree(d);
     return GPB_OK;
 }
+
+// ---- do DFMA and DMMA overlap?  Every warp interleaves `ratio` DFMA per DMMA; reports both rates. ----------
+template <int RATIO>
+__global__ void __launch_bounds__(256) mixed_chain_kernel(double* out, int iters, double a, double b) {
+    double c[4][2];
+    double x[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { c[i][0] = threadIdx.x * 1e-3 + i; c[i][1] = c[i][0] + 0.5; }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = threadIdx.x * 1e-3 + i;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(c[i][0]), "+d"(c[i][1]) : "d"(a), "d"(b));
+#pragma unroll
+            for (int r = 0; r < RATIO; ++r) x[(i * RATIO + r) & 7] = fma(x[(i * RATIO + r) & 7], a, b);
+        }
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) s += c[i][0] + c[i][1];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += x[i];
+    if (s == 123.456) out[0] = s;
+}
+
+extern "C" int gpb_bench_mixed(int iters, int ratio, double* dfma_tflops_host, double* dmma_tflops_host, void* stream) {
+    GPB_REQUIRE(iters > 0 && dfma_tflops_host && dmma_tflops_host, "bad arguments");
+    cudaStream_t s = (cudaStream_t)stream;
+    double* d = nullptr;
+    GPB_CHECK_CUDA(cudaMalloc((void**)&d, sizeof(double)));
+    const int blocks = gpb_sm_count() * 8;
+    cudaEvent_t e0, e1;
+    GPB_CHECK_CUDA(cudaEventCreate(&e0));
+    GPB_CHECK_CUDA(cudaEventCreate(&e1));
+    auto run = [&](int it) {
+        switch (ratio) {
+            case 4: mixed_chain_kernel<4><<<blocks, 256, 0, s>>>(d, it, 0.999999, 1e-9); break;
+            case 8: mixed_chain_kernel<8><<<blocks, 256, 0, s>>>(d, it, 0.999999, 1e-9); break;
+            case 16: mixed_chain_kernel<16><<<blocks, 256, 0, s>>>(d, it, 0.999999, 1e-9); break;
+            default: mixed_chain_kernel<32><<<blocks, 256, 0, s>>>(d, it, 0.999999, 1e-9); break;
+        }
+    };
+    run(iters / 10 + 1);
+    GPB_LAUNCH_CHECK();
+    GPB_CHECK_CUDA(cudaEventRecord(e0, s));
+    run(iters);
+    GPB_LAUNCH_CHECK();
+    GPB_CHECK_CUDA(cudaEventRecord(e1, s));
+    GPB_CHECK_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    GPB_CHECK_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    const int r = (ratio == 4 || ratio == 8 || ratio == 16) ? ratio : 32;
+    const double warps = 8.0 * blocks;
+    *dmma_tflops_host = 512.0 * 4.0 * iters * warps / (ms * 1e-3) / 1e12;
+    *dfma_tflops_host = 64.0 * 4.0 * r * (double)iters * warps / (ms * 1e-3) / 1e12;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    return GPB_OK;
+}

@@ -87,6 +87,9 @@ int gpb_bench_dfma(int iters, double* tflops_host, void* stream);
 /* Same for the FP64 tensor-core path (mma.sync m8n8k4 chains): decides whether the LU trailing update belongs on
  * DMMA or on the DFMA pipe on this part. */
 int gpb_bench_dmma(int iters, double* tflops_host, void* stream);
+/* Both at once: every warp issues `ratio` (4, 8, 16 or 32) DFMA per DMMA.  Tells whether the tensor sub-pipe and the
+ * FP64 FMA pipe run concurrently. */
+int gpb_bench_mixed(int iters, int ratio, double* dfma_tflops_host, double* dmma_tflops_host, void* stream);
 
 /* ---- (1) covariance assembly  [engine stage "kernel_constructor", SURVEY 8a2 row (1)] ------------ */
 /* n = 3*n_ori + n_rest + n_drift + n_faults.  Writes the full symmetric n x n matrix A (lda >= n) and the

@@ -14,4 +14,8 @@ for name in ("gpb_bench_dfma", "gpb_bench_dmma"):
         _lib.check(getattr(eng.lib, name)(20000, C.byref(v), eng.stream))
         best = max(best, v.value)
     out[name] = best
+for ratio in (4, 8, 16, 32):
+    a, b = C.c_double(0.0), C.c_double(0.0)
+    _lib.check(eng.lib.gpb_bench_mixed(5000, ratio, C.byref(a), C.byref(b), eng.stream))
+    out[f"mixed_ratio_{ratio}"] = {"dfma_tflops": a.value, "dmma_tflops": b.value, "sum": a.value + b.value}
 print(json.dumps(out))
