@@ -303,13 +303,27 @@ def run_gpu(args):
             cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": f"{args.cpu_sample} of {n_total} grid points ({dt:.1f} s), numpy float64 restatement "
                              "(oracle/), chunked at 500000 kernel-matrix elements, one process per core"}
+        # metric M2 (BASELINE.json): compute_model wall seconds on configs[1] (COMBINATION, octree level 6), this GPU
+        m2 = None
+        if world == 1 and not args.no_m2:
+            from gempy_b200 import examples as ex2
+            gc.compute_model(*ex2.combination(refinement=6).args(), engine=eng)
+            ts = []
+            for _ in range(3):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                gc.compute_model(*ex2.combination(refinement=6).args(), engine=eng)
+                torch.cuda.synchronize()
+                ts.append(time.perf_counter() - t0)
+            m2 = {"model": "COMBINATION octree level 6 (BASELINE configs[1])", "compute_model_wall_s": min(ts),
+                  "restated_numpy_wall_s_recorded": 13.1, "record": "profiles/r1_compute_model_wall.jsonl"}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args, model),
                 "clocks": clocks, "gpu_launches": int(launches),
                 "e2e": None if e2e_val is None else {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d,
                                                     "d2h_bytes_per_step": d2h},
-                "roofline": roof, "cpu_baseline": cpu}
+                "roofline": roof, "cpu_baseline": cpu, "compute_model": m2}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -327,6 +341,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=32768)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-m2", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

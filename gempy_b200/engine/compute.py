@@ -418,7 +418,8 @@ def compute_dense_fields(interpolation_input: InterpolationInput, options: Inter
     i0, i1 = point_range if point_range is not None else (0, g.n_points)
     m = i1 - i0
     st = StackTables(ii, desc, stack, ko, eng.device)
-    if np.asarray(desc.stack_structure.faults_relations)[:, stack].any() if desc.stack_structure.faults_relations is not None else False:
+    fr = desc.stack_structure.faults_relations
+    if fr is not None and np.asarray(fr)[:, stack].any():
         raise ValueError("compute_dense_fields handles fault-free stacks; use compute_model for faulted ones")
     A, b = eng.assemble(st)
     w = eng.solve(A, b)

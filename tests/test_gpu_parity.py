@@ -341,6 +341,121 @@ def test_weights_reused_when_provided():
                                   sol.octrees_output[-1].outputs[0].exported_fields.scalar_field)
 
 
+# ------------------------------------------------------------------------------------------- more model shapes
+def _three_stack_model(relations, refinement=3, degree=1, nugget_jitter=False, gradient=False, kernel=K.cubic):
+    """Three stacked series of one surface each (youngest first), synthetic, with the given relations."""
+    from gempy_b200.engine.data import StackRelationType as R, Transform
+    rng = np.random.default_rng(11)
+    sp, op, og = {}, {}, {}
+    names = ["top", "mid", "low"]
+    for k, nm in enumerate(names):
+        xy = rng.uniform(-0.4, 0.4, size=(25, 2))
+        tilt = [0.6, -0.5, 0.1][k]          # the series cross inside the model: the relations matter
+        z = 0.2 - 0.2 * k + tilt * xy[:, 0] + 0.03 * np.sin(6 * xy[:, 1])
+        sp[nm] = np.column_stack([xy, z])
+        op[nm] = np.array([[0.0, 0.0, 0.2 - 0.2 * k], [0.2, -0.1, 0.2 - 0.2 * k + tilt * 0.2]])
+        g = np.array([-tilt, 0.0, 1.0]) / np.hypot(tilt, 1.0)
+        og[nm] = np.tile(g, (2, 1))
+    ident = Transform(np.zeros(3), np.zeros(3), np.ones(3))
+    stacks = [(f"S{k}", [nm], relations[k]) for k, nm in enumerate(names)]
+    m = ex.build_model("three_stacks", sp, op, og, stacks, [-0.5, 0.5, -0.5, 0.5, -0.5, 0.5], refinement=refinement,
+                       transform=ident, legacy_octree_init=True)
+    m.options.kernel_options.uni_degree = degree
+    m.options.kernel_options.kernel_function = kernel
+    m.options.evaluation_options.compute_scalar_gradient = gradient
+    if nugget_jitter:
+        m.interpolation_input.surface_points.nugget_effect_scalar[:] = 2e-5 * (1 + rng.uniform(0, 4, size=75))
+        m.interpolation_input.orientations.nugget_effect_grad[:] = 0.01 * (1 + rng.uniform(0, 2, size=6))
+    return m
+
+
+def _compare_model(m_gpu, m_cpu, check_grad=False):
+    sol = gc.compute_model(*m_gpu.args())
+    ref = orc.compute_model(*m_cpu.args())
+    for lvl, (a, b) in enumerate(zip(sol.octrees_output, ref.levels)):
+        nv = b.centers.shape[0]
+        assert a.grid_centers.octree_grid.values.shape[0] == nv
+        for i, (oa, ob) in enumerate(zip(a.outputs_centers, b.fields.stacks)):
+            assert _rel_err(oa.exported_fields.scalar_field[:nv], ob.Z[:nv]) < RTOL, (lvl, i)
+            if check_grad:
+                ga = np.stack([oa.exported_fields.gx_field[:nv], oa.exported_fields.gy_field[:nv],
+                               oa.exported_fields.gz_field[:nv]], axis=1)
+                assert _rel_err(ga, ob.G[:nv]) < RTOL, (lvl, i)
+        near = np.zeros(nv, bool)
+        for ob in b.fields.stacks:
+            near |= (np.abs(ob.Z[:nv, None] - ob.isovalues[None, :]) < 1e-6).any(axis=1)
+        np.testing.assert_array_equal(np.rint(a.outputs_centers[-1].block[:nv])[~near], b.fields.lith_ids[:nv][~near])
+        for i, (oa, ob) in enumerate(zip(a.outputs_centers, b.fields.stacks)):
+            np.testing.assert_array_equal(oa.combined_scalar_field.squeezed_mask_array[:nv][~near], ob.squeezed_mask[:nv][~near])
+    return sol, ref
+
+
+def test_onlap_and_erode_relations_match_oracle():
+    from gempy_b200.engine.data import StackRelationType as R
+    for rel in ([R.ERODE, R.ERODE, R.ERODE], [R.ONLAP, R.ERODE, R.ERODE], [R.ONLAP, R.ONLAP, R.ERODE], [R.ERODE, R.ONLAP, R.ERODE]):
+        _compare_model(_three_stack_model(rel), _three_stack_model(rel))
+
+
+def test_degree2_nonuniform_nuggets_and_exported_gradient():
+    from gempy_b200.engine.data import StackRelationType as R
+    rel = [R.ERODE, R.ERODE, R.ERODE]
+    kw = dict(degree=2, nugget_jitter=True, gradient=True)
+    _compare_model(_three_stack_model(rel, **kw), _three_stack_model(rel, **kw), check_grad=True)
+
+
+def test_matern_model_through_compute_model():
+    from gempy_b200.engine.data import StackRelationType as R
+    rel = [R.ERODE, R.ERODE, R.ERODE]
+    _compare_model(_three_stack_model(rel, kernel=K.matern_5_2), _three_stack_model(rel, kernel=K.matern_5_2))
+
+
+def test_topography_sections_and_custom_grids():
+    from gempy_b200.engine.data import GenericGrid
+    rng = np.random.default_rng(2)
+    def build():
+        m = ex.combination(refinement=2)
+        g = m.interpolation_input.grid
+        g.topography = GenericGrid(rng_pts[0])
+        g.sections = GenericGrid(rng_pts[1])
+        g.custom_grid = GenericGrid(rng_pts[2])
+        return m
+    e = ex.combination().interpolation_input.grid.octree_grid.orthogonal_extent
+    rng_pts = [rng.uniform(e[[0, 2, 4]], e[[1, 3, 5]], size=(n, 3)) for n in (37, 1, 130)]
+    sol = gc.compute_model(*build().args())
+    m = build()
+    ii, opt, desc = m.args()
+    for name, pts in (("topography", rng_pts[0]), ("sections", rng_pts[1]), ("custom", rng_pts[2])):
+        f = orc.interpolate_all_fields(ii, opt, desc, pts)
+        got = getattr(sol.raw_arrays, name)
+        near = np.zeros(pts.shape[0], bool)
+        for ob in f.stacks:
+            near |= (np.abs(ob.Z[:pts.shape[0], None] - ob.isovalues[None, :]) < 1e-6).any(axis=1)
+        np.testing.assert_array_equal(got[~near], f.lith_ids[~near])
+    g0 = sol.octrees_output[0].grid_centers
+    assert g0.len_all_grids == 16 + 130 + 37 + 1
+    assert sol.octrees_output[0].outputs_centers[0].exported_fields.scalar_field.shape[0] == 16 + 130 + 37 + 1 + 8 * 16
+
+
+def test_octree_raw_arrays_fill_matches_dense_evaluation():
+    """raw_arrays.lith_block of an octree solution = ids on the finest regular lattice wherever the octree was refined
+    down to the last level (elsewhere the parent voxel's id is kept)."""
+    m = ex.anticline(refinement=4)
+    m.options.mesh_extraction = False
+    sol = gc.compute_model(*m.args())
+    lb = sol.raw_arrays.lith_block
+    assert lb.shape == (16 ** 3,)
+    ii, opt, desc = ex.anticline(refinement=4).args()
+    c, _ = orc.regular_grid_centers(ii.grid.octree_grid.orthogonal_extent, [16, 16, 16])
+    f = orc.interpolate_all_fields(ii, opt, desc, c)
+    leaves = sol.octrees_output[-1].grid_centers.octree_grid.values
+    d = 0.5 / 16
+    e = ii.grid.octree_grid.orthogonal_extent
+    ijk = np.rint((leaves - gc.GRID_SHIFT - e[[0, 2, 4]]) / d - 0.5).astype(int)
+    lin = (ijk[:, 0] * 16 + ijk[:, 1]) * 16 + ijk[:, 2]
+    np.testing.assert_array_equal(lb[lin], f.lith_ids[lin])
+    assert set(np.unique(lb)) <= {1.0, 2.0, 3.0}
+
+
 # ------------------------------------------------------------------------------------------- size-independent properties
 def test_linearity_in_the_weights_at_scale(eng):
     """Z is linear in the packed weights: eval(w1 + w2) == eval(w1) + eval(w2), on 2M points / 2.5k data."""
