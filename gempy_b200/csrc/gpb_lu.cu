@@ -25,12 +25,8 @@ constexpr int kSmallN = 160;     // whole-matrix-in-smem path
 // configuration, evaluated identically by gpb_lu_factor (host) and by the forward substitution of gpb_lu_apply
 // (device), so the interchanges are replayed over exactly the panels that produced them.
 __host__ __device__ inline int panel_width_hd(int n, int k0, int cluster, unsigned long long smem_cap) {
-    int jb = kNB;
-    if (cluster > 0) {
-        const long long m = n - k0;
-        const long long R = (m + cluster - 1) / cluster;
-        while (jb > 8 && (unsigned long long)(R + 2) * jb * sizeof(double) > smem_cap) jb >>= 1;
-    }
+    (void)cluster; (void)smem_cap;               // the panel width no longer depends on the device configuration
+    const int jb = kNB;
     return (n - k0 < jb) ? n - k0 : jb;
 }
 
@@ -219,8 +215,8 @@ __device__ __forceinline__ void better(double& bv, int& bi, double ov, int oi) {
 
 __global__ void __launch_bounds__(kPanelThreads, 1)
 panel_cluster_kernel(int n, int k0, int jb, double* __restrict__ A, int lda, int* __restrict__ ipiv, int* __restrict__ info,
-                     int R, int ldp) {
-    extern __shared__ double P[];                  // [jb][ldp] : this CTA's rows of the panel, column-major
+                     int R, int ldp, int in_smem) {
+    extern __shared__ double P_smem[];             // [jb][ldp] : this CTA's rows of the panel, column-major
     __shared__ PanelExchange ex[2];                // double buffered by column parity
     __shared__ double red_v[kPanelThreads / 32];
     __shared__ int red_i[kPanelThreads / 32];
@@ -232,10 +228,15 @@ panel_cluster_kernel(int n, int k0, int jb, double* __restrict__ A, int lda, int
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int r0 = k0 + rank * R;
     const int nrows = max(0, min(n, r0 + R) - r0);
+    // panels too tall for shared memory (n > ~12 800 at 16 CTAs) are factored in place: same indexing with ldp = lda;
+    // the rows of a CTA are private to it, so only the CTA's own L1/L2 path is involved
+    double* const P = in_smem ? P_smem : A + (long long)k0 * lda + r0;
 
-    for (int e = tid; e < nrows * jb; e += kPanelThreads) {
-        const int c = e / nrows, i = e - c * nrows;
-        P[c * ldp + i] = A[(long long)(k0 + c) * lda + r0 + i];
+    if (in_smem) {
+        for (int e = tid; e < nrows * jb; e += kPanelThreads) {
+            const int c = e / nrows, i = e - c * nrows;
+            P[c * ldp + i] = A[(long long)(k0 + c) * lda + r0 + i];
+        }
     }
     __syncthreads();
     // candidate for column 0
@@ -342,9 +343,11 @@ panel_cluster_kernel(int n, int k0, int jb, double* __restrict__ A, int lda, int
         }
         __syncthreads();
     }
-    for (int e = tid; e < nrows * jb; e += kPanelThreads) {
-        const int c = e / nrows, i = e - c * nrows;
-        A[(long long)(k0 + c) * lda + r0 + i] = P[c * ldp + i];
+    if (in_smem) {
+        for (int e = tid; e < nrows * jb; e += kPanelThreads) {
+            const int c = e / nrows, i = e - c * nrows;
+            A[(long long)(k0 + c) * lda + r0 + i] = P[c * ldp + i];
+        }
     }
     cluster.sync();                                // no CTA exits while a neighbour may still address its smem
 }
@@ -656,30 +659,30 @@ bool panel_fits_cluster(int n, int k0, int jb) {
 }
 
 int launch_panel(int n, int k0, int jb, double* A, int lda, int* ipiv, int* info, cudaStream_t s) {
-    if (!panel_fits_cluster(n, k0, jb)) {
+    const PanelConfig& cfg = panel_config();
+    if (cfg.cluster == 0) {
         panel_kernel<<<1, 1024, 0, s>>>(n, k0, jb, A, lda, ipiv, info);
         GPB_LAUNCH_CHECK();
         return GPB_OK;
     }
-    const PanelConfig& cfg = panel_config();
     const int m = n - k0;
     int R = (m + cfg.cluster - 1) / cfg.cluster;
     if (R < 1) R = 1;
-    const int ldp = (R + 1) & ~1;
+    const bool in_smem = panel_fits_cluster(n, k0, jb);
+    const int ldp = in_smem ? ((R + 1) & ~1) : lda;
     cudaLaunchConfig_t lc{};
     lc.gridDim = dim3(cfg.cluster);
     lc.blockDim = dim3(kPanelThreads);
-    lc.dynamicSmemBytes = (size_t)ldp * jb * sizeof(double);
+    lc.dynamicSmemBytes = in_smem ? (size_t)ldp * jb * sizeof(double) : 0;
     lc.stream = s;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = cfg.cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     lc.attrs = at; lc.numAttrs = 1;
-    GPB_CHECK_CUDA(cudaLaunchKernelEx(&lc, panel_cluster_kernel, n, k0, jb, A, lda, ipiv, info, R, ldp));
+    GPB_CHECK_CUDA(cudaLaunchKernelEx(&lc, panel_cluster_kernel, n, k0, jb, A, lda, ipiv, info, R, ldp, in_smem ? 1 : 0));
     ++g_gpb_launches;
     return GPB_OK;
 }
-
 
 struct LookAhead {
     cudaStream_t panel_stream = nullptr;
