@@ -126,6 +126,11 @@ class StackTables:
         # gather indices of rest / ref points inside the stack's surface-point table (for the fault tables)
         self.rest_idx = torch.as_tensor(np.nonzero(~is_ref)[0], device=device)
         self.ref_idx = torch.as_tensor(np.repeat(starts, reps), device=device)
+        self.ref_local_dev = torch.as_tensor(starts, device=device)
+        fr = ss.faults_relations
+        active = np.nonzero(np.asarray(fr)[:, i])[0] if fr is not None else np.zeros(0, dtype=np.int64)
+        self.active_faults = active
+        self.active_faults_dev = torch.as_tensor(active, device=device) if active.size else None
         self.ko = ko
         self.fault_rest = None
         self.fault_ref = None
@@ -153,6 +158,17 @@ class StackTables:
     @property
     def n(self) -> int:
         return 3 * self.n_ori + self.n_rest + self.n_drift + self.n_faults
+
+
+class ModelTables(list):
+    """Per-stack device tables plus the model-wide constants (all surface points, unit ids), uploaded once per
+    ``compute_model`` call: no host-to-device copy is issued inside the per-level loop, so the host runs ahead of the
+    GPU instead of synchronising on every small pageable copy."""
+
+    def __init__(self, ii: InterpolationInput, desc: InputDataDescriptor, ko, device):
+        super().__init__(StackTables(ii, desc, i, ko, device) for i in range(desc.stack_structure.n_stacks))
+        self.sp_all = torch.as_tensor(np.ascontiguousarray(ii.surface_points.sp_coords.T), dtype=F64, device=device)
+        self.unit_values = torch.as_tensor(np.asarray(ii.unit_values, dtype=np.float64), device=device)
 
 
 # ------------------------------------------------------------------------------------------------ engine
@@ -257,8 +273,9 @@ class B200Engine:
         ss = desc.stack_structure
         n_st = ss.n_stacks
         rel = [_rel_code(r) for r in ss.masking_descriptor]
-        fr = np.asarray(ss.faults_relations) if ss.faults_relations is not None else np.zeros((n_st, n_st), bool)
-        sp_all = torch.as_tensor(np.ascontiguousarray(ii.surface_points.sp_coords.T), dtype=F64, device=self.device)
+        if tables is None or not isinstance(tables, ModelTables):
+            tables = ModelTables(ii, desc, ko, self.device)
+        sp_all = tables.sp_all
         n_sp = sp_all.shape[1]
         gsz = sum(s.m for s in segments)
         L = gsz + n_sp
@@ -267,19 +284,16 @@ class B200Engine:
         G = self.empty(n_st, 3, L) if gradient else None
         block = self.empty(n_st, L)
         values_everywhere = self.empty(n_st, L)
-        unit_values = torch.as_tensor(np.asarray(ii.unit_values, dtype=np.float64), device=self.device)
+        unit_values = tables.unit_values
         iso_min = self.empty(n_st)
         iso_max = self.empty(n_st)
         isos, conds, srcs = [], [], []
         tmp_min = self.empty(1)
-        if tables is None:
-            tables = [StackTables(ii, desc, i, ko, self.device) for i in range(n_st)]
         for i in range(n_st):
             st = tables[i]
-            active = np.nonzero(fr[:, i])[0]
             f_every = None
-            if active.size:
-                f_every = values_everywhere.index_select(0, torch.as_tensor(active, device=self.device)).contiguous()
+            if st.active_faults_dev is not None:
+                f_every = values_everywhere.index_select(0, st.active_faults_dev).contiguous()
                 st.set_faults(f_every[:, gsz:][:, st.sp_slice])
             else:
                 st.set_faults(None)
@@ -306,8 +320,7 @@ class B200Engine:
             for seg in segments:
                 self.evaluate_segment(st, src, seg, off, Z[i], Gi, f_every)
                 off += seg.m
-            ref_global = torch.as_tensor(gsz + st.sp_slice.start + st.ref_local, device=self.device)
-            iso = Z[i].index_select(0, ref_global).contiguous()
+            iso = Z[i, gsz + st.sp_slice.start:gsz + st.sp_slice.stop].index_select(0, st.ref_local_dev).contiguous()
             isos.append(iso)
             iso_min[i] = iso.min()
             iso_max[i] = iso.max()
@@ -490,6 +503,7 @@ def _fill_regular_from_octree(levels_host, base_shape: np.ndarray, key) -> np.nd
     dense = vals
     for lvl in range(1, len(levels_host)):
         sel = levels_host[lvl - 1]["selected"]
+        sel = sel.get() if isinstance(sel, Deferred) else sel
         dense = dense.repeat(2, axis=0).repeat(2, axis=1).repeat(2, axis=2)
         parents = ijk[sel]
         off = np.array([[i, j, k] for i in (0, 1) for j in (0, 1) for k in (0, 1)])
@@ -568,7 +582,7 @@ def compute_model(interpolation_input: InterpolationInput, options: Interpolatio
         for i, w in enumerate(ii.weights):
             if w is not None and len(w):
                 cache[i] = torch.as_tensor(np.asarray(w, dtype=np.float64), device=eng.device)
-    tables = [StackTables(ii, desc, i, ko, eng.device) for i in range(n_st)]
+    tables = ModelTables(ii, desc, ko, eng.device)
 
     n_levels = int(eo.number_octree_levels)
     dc_level = min(int(eo.number_octree_levels_surface), n_levels) - 1 if eo.mesh_extraction else -1
@@ -644,8 +658,8 @@ def compute_model(interpolation_input: InterpolationInput, options: Interpolatio
             dc_payload = (centers, d.copy(), corners, f)
         if lvl == n_levels - 1:
             break
-        level.marked_voxels = _np(mark_full).astype(bool)
-        host["selected"] = level.marked_voxels
+        level._marked_voxels = Deferred(lambda mk=mark_full: _np(mk).astype(bool))
+        host["selected"] = level._marked_voxels
         centers = eng.emit(centers, d, mark_full)
         d = d / 2
 

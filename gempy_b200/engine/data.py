@@ -661,7 +661,12 @@ class OctreeLevel:
     outputs_centers: List[InterpOutput]
     _grid_corners: object = None
     outputs_corners: Optional[List[InterpOutput]] = None
-    marked_voxels: Optional[np.ndarray] = None      # refine mask over this level's voxels
+    _marked_voxels: object = None                   # refine mask over this level's voxels (lazy)
+
+    @property
+    def marked_voxels(self) -> Optional[np.ndarray]:
+        self._marked_voxels = _res(self._marked_voxels)
+        return self._marked_voxels
 
     @property
     def grid_corners(self) -> Optional[EngineGrid]:
