@@ -29,6 +29,8 @@ struct EvalParams {
     const double* src;       // packed table
     long long n_sps_pad;
     long long n_ori_pad;
+    long long n_sps;         // actual number of surface-point sources (rest points + one per surface)
+    long long n_ori;         // actual number of orientations
     int n_drift;
     int n_faults;
     // points
@@ -128,6 +130,18 @@ eval_kernel(const EvalParams prm) {
         }
     };
 
+    // Small tables (<= 2 tiles: every reference example model) are loaded once and stay resident in the two stage
+    // buffers; larger ones are streamed per chunk, double buffered.
+    const bool resident = n_tiles <= 2;
+    if (resident && n_tiles > 0) {
+        if (tid == 0) {
+            issue(0, 0);
+            if (n_tiles > 1) issue(1, 1);
+        }
+        gpb_mbar_wait(&full[0], 0);
+        if (n_tiles > 1) gpb_mbar_wait(&full[1], 0);
+    }
+
     for (long long c = blockIdx.x; c < n_chunks; c += gridDim.x) {
         // ---- this thread's P points -------------------------------------------------------------------
         double X[P], Y[P], Zc[P];
@@ -159,18 +173,22 @@ eval_kernel(const EvalParams prm) {
             accZ[k] = 0.0; hx[k] = 0.0; hy[k] = 0.0; hz[k] = 0.0;
         }
 
-        if (tid == 0 && n_tiles > 0) issue(0, gt);
+        if (!resident && tid == 0 && n_tiles > 0) issue(0, gt);
 
         for (long long j = 0; j < n_tiles; ++j, ++gt) {
-            if (tid == 0 && j + 1 < n_tiles) issue(j + 1, gt + 1);
-            const int b = (int)(gt & 1);
-            gpb_mbar_wait(&full[b], (uint32_t)((gt >> 1) & 1));
+            int b = (int)j;
+            if (!resident) {
+                if (tid == 0 && j + 1 < n_tiles) issue(j + 1, gt + 1);
+                b = (int)(gt & 1);
+                gpb_mbar_wait(&full[b], (uint32_t)((gt >> 1) & 1));
+            }
             const double* s = stage[b];
 
             if (j < n_sp_tiles) {
                 // ---- surface-point sources: {X, Y, Z, W} -----------------------------------------------
+                const int cnt_sp = (int)min((long long)kTileSp, (prm.n_sps - j * kTileSp + 1) & ~1LL);
 #pragma unroll 2
-                for (int q = 0; q < kTileSp; ++q) {
+                for (int q = 0; q < cnt_sp; ++q) {
                     const double2 a0 = *reinterpret_cast<const double2*>(s + 4 * q);
                     const double2 a1 = *reinterpret_cast<const double2*>(s + 4 * q + 2);
 #pragma unroll
@@ -198,8 +216,9 @@ eval_kernel(const EvalParams prm) {
                 }
             } else {
                 // ---- orientation sources: {X, Y, Z, w'x, w'y, w'z} -------------------------------------
+                const int cnt_or = (int)min((long long)kTileOri, (prm.n_ori - (j - n_sp_tiles) * kTileOri + 1) & ~1LL);
 #pragma unroll 2
-                for (int q = 0; q < kTileOri; ++q) {
+                for (int q = 0; q < cnt_or; ++q) {
                     const double2 a0 = *reinterpret_cast<const double2*>(s + 6 * q);
                     const double2 a1 = *reinterpret_cast<const double2*>(s + 6 * q + 2);
                     const double2 a2 = *reinterpret_cast<const double2*>(s + 6 * q + 4);
@@ -221,7 +240,7 @@ eval_kernel(const EvalParams prm) {
                     }
                 }
             }
-            __syncthreads();     // everyone is done with stage[b] before thread 0 refills it
+            if (!resident) __syncthreads();     // everyone is done with stage[b] before thread 0 refills it
         }
 
         // ---- drift, faults, store -------------------------------------------------------------------------
@@ -361,6 +380,18 @@ eval_zrun_kernel(const EvalParams prm) {
         }
     };
 
+    // Small tables (<= 2 tiles: every reference example model) are loaded once and stay resident in the two stage
+    // buffers; larger ones are streamed per chunk, double buffered.
+    const bool resident = n_tiles <= 2;
+    if (resident && n_tiles > 0) {
+        if (tid == 0) {
+            issue(0, 0);
+            if (n_tiles > 1) issue(1, 1);
+        }
+        gpb_mbar_wait(&full[0], 0);
+        if (n_tiles > 1) gpb_mbar_wait(&full[1], 0);
+    }
+
     for (long long c = blockIdx.x; c < n_chunks; c += gridDim.x) {
         const long long run = c * kThreads + tid;
         const bool live = run < n_runs;
@@ -380,15 +411,19 @@ eval_zrun_kernel(const EvalParams prm) {
             accZ[k] = 0.0; hx[k] = 0.0; hy[k] = 0.0; hz[k] = 0.0;
         }
 
-        if (tid == 0 && n_tiles > 0) issue(0, gt);
+        if (!resident && tid == 0 && n_tiles > 0) issue(0, gt);
         for (long long j = 0; j < n_tiles; ++j, ++gt) {
-            if (tid == 0 && j + 1 < n_tiles) issue(j + 1, gt + 1);
-            const int b = (int)(gt & 1);
-            gpb_mbar_wait(&full[b], (uint32_t)((gt >> 1) & 1));
+            int b = (int)j;
+            if (!resident) {
+                if (tid == 0 && j + 1 < n_tiles) issue(j + 1, gt + 1);
+                b = (int)(gt & 1);
+                gpb_mbar_wait(&full[b], (uint32_t)((gt >> 1) & 1));
+            }
             const double* s = stage[b];
             if (j < n_sp_tiles) {
+                const int cnt_sp = (int)min((long long)kTileSp, (prm.n_sps - j * kTileSp + 1) & ~1LL);
 #pragma unroll 2
-                for (int q = 0; q < kTileSp; ++q) {
+                for (int q = 0; q < cnt_sp; ++q) {
                     const double2 a0 = *reinterpret_cast<const double2*>(s + 4 * q);
                     const double2 a1 = *reinterpret_cast<const double2*>(s + 4 * q + 2);
                     const double dx = X - a0.x, dy = Y - a0.y;
@@ -417,8 +452,9 @@ eval_zrun_kernel(const EvalParams prm) {
                     }
                 }
             } else {
+                const int cnt_or = (int)min((long long)kTileOri, (prm.n_ori - (j - n_sp_tiles) * kTileOri + 1) & ~1LL);
 #pragma unroll 2
-                for (int q = 0; q < kTileOri; ++q) {
+                for (int q = 0; q < cnt_or; ++q) {
                     const double2 a0 = *reinterpret_cast<const double2*>(s + 6 * q);
                     const double2 a1 = *reinterpret_cast<const double2*>(s + 6 * q + 2);
                     const double2 a2 = *reinterpret_cast<const double2*>(s + 6 * q + 4);
@@ -443,7 +479,7 @@ eval_zrun_kernel(const EvalParams prm) {
                     }
                 }
             }
-            __syncthreads();
+            if (!resident) __syncthreads();
         }
 
         const double inv_agi = tail[19];
@@ -574,6 +610,8 @@ int fill_common(const gpb_stack* st, const double* src, EvalParams& prm) {
     prm.src = src;
     prm.n_sps_pad = gpb_round_up((long long)st->n_rest + st->n_surf, kTileSp);
     prm.n_ori_pad = gpb_round_up(st->n_ori, kTileOri);
+    prm.n_sps = (long long)st->n_rest + st->n_surf;
+    prm.n_ori = st->n_ori;
     prm.n_drift = st->n_drift;
     prm.n_faults = st->n_faults;
     prm.inv_a = 1.0 / st->range;

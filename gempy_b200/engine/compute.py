@@ -169,6 +169,7 @@ class ModelTables(list):
         super().__init__(StackTables(ii, desc, i, ko, device) for i in range(desc.stack_structure.n_stacks))
         self.sp_all = torch.as_tensor(np.ascontiguousarray(ii.surface_points.sp_coords.T), dtype=F64, device=device)
         self.unit_values = torch.as_tensor(np.asarray(ii.unit_values, dtype=np.float64), device=device)
+        self.src_cache = {}            # stack -> packed evaluation table (the weights do not change between levels)
 
 
 # ------------------------------------------------------------------------------------------------ engine
@@ -311,7 +312,9 @@ class B200Engine:
             w = weights_cache[i]
             if w.shape[0] != st.n:
                 raise ValueError(f"stack {i}: cached weights have length {w.shape[0]}, system size is {st.n}")
-            src = self.pack(st, w)
+            src = tables.src_cache.get(i)
+            if src is None:
+                src = tables.src_cache[i] = self.pack(st, w)
             srcs.append(src)
             Gi = G[i] if gradient else None
             # surface points first (the isovalues feed the activator), then every grid segment
