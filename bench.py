@@ -290,12 +290,16 @@ def run_gpu(args):
         nominal_peak = eng.sm_count * 64 * 2 * 1.965e9 / 1e12       # 148 SM x 64 FP64 lanes x 2 x 1.965 GHz
         peak_at_clock = eng.sm_count * 64 * 2 * sm_mhz * 1e6 / 1e12
         measured_peak = dfma_peak_tflops(eng)
+        # DRAM traffic of one launch of the dominant kernel on the default workload, from one `ncu --set full` capture
+        # (profiles/r1_eval_zrun_kernel_ncu_full_512.txt): 4.318 GB written + 0.116 GB read vs 4.295 GB algorithmic
+        traffic = 4.317651e9 + 0.116064e9 if (args.grid == 512 and world == 1) else None
         roof = {"bound": "fp64", "achieved": achieved_tf, "peak": measured_peak, "unit": "TFLOP/s",
-                "frac": achieved_tf / measured_peak, "traffic": None,
+                "frac": achieved_tf / measured_peak, "traffic": traffic, "algorithmic_bytes_per_launch": 32 * m,
                 "peak_source": "measured in this run: DFMA-chain microbenchmark gpb_bench_dfma (MEASURED_PEAKS.json has no FP64 entry)",
                 "peak_nominal": nominal_peak, "frac_of_nominal": achieved_tf / nominal_peak,
                 "peak_at_measured_clock": peak_at_clock, "frac_at_measured_clock": achieved_tf / peak_at_clock,
-                "flops_per_point": F, "kernel": "eval_kernel<cubic, grad, regular>",
+                "flops_per_point": F, "kernel": "eval_zrun_kernel<cubic, grad, P=8, T=256>",
+                "bound_note": "neither HBM (0.06 % DRAM utilisation) nor tensor: the FP64 FMA pipe is the binding resource (ncu: 89 % pipe-active)",
                 "hbm": {"achieved_gbs": value / world * 32 / 1e9, "algorithmic_bytes_per_point": 32}}
         cpu = None
         if not args.no_cpu:

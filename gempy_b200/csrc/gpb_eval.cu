@@ -14,7 +14,7 @@
 // Packed table (built by gpb_pack_eval_table), all coordinates divided by the range a:
 //   [ n_sps_pad x {X, Y, Z, W} ]   W = c_o*i_res*w_i for rest points, -c_o*i_res*sum(w) for each reference point
 //   [ n_ori_pad x {X, Y, Z, w'x, w'y, w'z} ]   w' = -(c_o*gi_res/a) * w
-//   [ tail: mu_z[9] (drift, field), mu_g[9] (drift, gradient), scal[6], w_fault[n_faults] ]
+//   [ tail: mu_z[9] (drift, field), mu_g[9] (drift, gradient), scal[2], source moments S0, M1[3], M2, w_fault[n_faults] ]
 #include "gpb_common.cuh"
 #include <cstdlib>
 
@@ -23,7 +23,7 @@ namespace {
 constexpr int kTileSp = 256;                  // sources per tile: 256 * 32 B = 8 KB
 constexpr int kTileOri = 128;                 // 128 * 48 B = 6 KB
 constexpr int kTileBytes = kTileSp * 32;      // stage buffer size
-constexpr int kTailDoubles = 24;              // mu_z[9] mu_g[9] scal[6]
+constexpr int kTailDoubles = 32;              // mu_z[9] mu_g[9] scal[2] moments S0, M1[3], M2 (+pad)
 
 struct EvalParams {
     const double* src;       // packed table
@@ -54,14 +54,18 @@ struct EvalParams {
 //   cval : C(r) (cubic: C - 1, the constant cancels because the source weights sum to zero)
 //   kp   : a^2 * C'(r)/r
 //   dd   : a^2 * (C'(r)/r - C''(r))          (numerator of the regularised gradient-gradient term)
+// Cubic kernel, surface-point sources:  C - 1 = -7 u + t u P(u),   a^2 C'/r = -14 + t Q(u).
+// The parts -7 u and -14 are polynomial in the point coordinates once summed over the sources
+// (sum_s W_s u_s = (|X|^2 + eps) S0 - 2 X.M1 + M2,  sum_s W_s (X - s) = X S0 - M1), so they are added once per point
+// from the source moments S0, M1, M2 (packed in the table tail) instead of once per pair: the pair loop accumulates
+// only  Wt * (u P)  and  Wt * Q * d  with Wt = W t  -- one FP64 instruction less per pair.
+//   returns c = u P(u) / t-free part to be multiplied by W t, kp = Q(u)
 template <int KERNEL>
 __device__ __forceinline__ void cov_sp(double u, double t, double& c, double& kp) {
     if constexpr (KERNEL == GPB_KERNEL_CUBIC) {
-        // C - 1 = u * (-7 + t * (35/4 + u * (-7/2 + 3/4 u)));  kp = -14 + t * (105/4 + u * (-35/2 + 21/4 u))
         const double P = fma(u, fma(0.75, u, -3.5), 8.75);
-        const double Q = fma(u, fma(5.25, u, -17.5), 26.25);
-        c = u * fma(t, P, -7.0);
-        kp = fma(t, Q, -14.0);
+        kp = fma(u, fma(5.25, u, -17.5), 26.25);
+        c = u * P;
     } else if constexpr (KERNEL == GPB_KERNEL_EXPONENTIAL) {
         const double e = exp(-0.5 * u);
         c = e;
@@ -198,9 +202,10 @@ eval_kernel(const EvalParams prm) {
                         const double t = gpb_fast_sqrt(u);
                         double cv, kp;
                         cov_sp<KERNEL>(u, t, cv, kp);
-                        accZ[k] = fma(a1.y, cv, accZ[k]);
+                        const double wq = (KERNEL == GPB_KERNEL_CUBIC) ? a1.y * t : a1.y;     // W t for the cubic split
+                        accZ[k] = fma(wq, cv, accZ[k]);
                         if constexpr (GRAD) {
-                            const double g = a1.y * kp;
+                            const double g = wq * kp;
                             hx[k] = fma(g, dx, hx[k]);
                             hy[k] = fma(g, dy, hy[k]);
                             hz[k] = fma(g, dz, hz[k]);
@@ -208,6 +213,20 @@ eval_kernel(const EvalParams prm) {
                     }
                 }
                 if (j == n_sp_tiles - 1) {
+                    if constexpr (KERNEL == GPB_KERNEL_CUBIC) {      // per-point part of the cubic split (see cov_sp)
+                        const double S0 = tail[20], M1x = tail[21], M1y = tail[22], M1z = tail[23], M2 = tail[24];
+#pragma unroll
+                        for (int k = 0; k < P; ++k) {
+                            const double x2 = fma(X[k], X[k], fma(Y[k], Y[k], fma(Zc[k], Zc[k], prm.eps_u)));
+                            const double xm = fma(X[k], M1x, fma(Y[k], M1y, Zc[k] * M1z));
+                            accZ[k] = fma(-7.0, fma(x2, S0, fma(-2.0, xm, M2)), accZ[k]);
+                            if constexpr (GRAD) {
+                                hx[k] = fma(-14.0, fma(X[k], S0, -M1x), hx[k]);
+                                hy[k] = fma(-14.0, fma(Y[k], S0, -M1y), hy[k]);
+                                hz[k] = fma(-14.0, fma(Zc[k], S0, -M1z), hz[k]);
+                            }
+                        }
+                    }
                     if constexpr (GRAD) {
                         const double r = tail[18];       // gi^2 / i_res : surface-point part into H units
 #pragma unroll
@@ -335,6 +354,24 @@ __global__ void pack_kernel(const PackParams p) {
         }
         tl[18] = st.gi_res * st.gi_res / st.i_res;
         tl[19] = 1.0 / (a * st.gi_res);
+        // moments of the surface-point sources in the packed units (same W and X the pair loop sees)
+        double S0 = 0.0, M1x = 0.0, M1y = 0.0, M1z = 0.0, M2 = 0.0;
+        for (int i = 0; i < st.n_rest; ++i) {
+            const double W = cI * w_i[i];
+            const double x = st.rest[i] * inv_a, y = st.rest[st.n_rest + i] * inv_a, z = st.rest[2LL * st.n_rest + i] * inv_a;
+            S0 += W; M1x = fma(W, x, M1x); M1y = fma(W, y, M1y); M1z = fma(W, z, M1z);
+            M2 = fma(W, fma(x, x, fma(y, y, z * z)), M2);
+        }
+        for (int sidx = 0; sidx < st.n_surf; ++sidx) {
+            double acc = 0.0;
+            for (int r = st.surf_offsets[sidx]; r < st.surf_offsets[sidx + 1]; ++r) acc += w_i[r];
+            const double W = -cI * acc;
+            const double x = st.ref_unique[sidx] * inv_a, y = st.ref_unique[st.n_surf + sidx] * inv_a,
+                         z = st.ref_unique[2 * st.n_surf + sidx] * inv_a;
+            S0 += W; M1x = fma(W, x, M1x); M1y = fma(W, y, M1y); M1z = fma(W, z, M1z);
+            M2 = fma(W, fma(x, x, fma(y, y, z * z)), M2);
+        }
+        tl[20] = S0; tl[21] = M1x; tl[22] = M1y; tl[23] = M1z; tl[24] = M2;
         for (int f = 0; f < st.n_faults; ++f) tl[kTailDoubles + f] = w_f[f];
     }
 }
@@ -435,9 +472,10 @@ eval_zrun_kernel(const EvalParams prm) {
                         const double t = gpb_fast_sqrt(u);
                         double cv, kp;
                         cov_sp<KERNEL>(u, t, cv, kp);
-                        accZ[k] = fma(a1.y, cv, accZ[k]);
+                        const double wq = (KERNEL == GPB_KERNEL_CUBIC) ? a1.y * t : a1.y;     // W t for the cubic split
+                        accZ[k] = fma(wq, cv, accZ[k]);
                         if constexpr (GRAD) {
-                            const double g = a1.y * kp;
+                            const double g = wq * kp;
                             hx[k] = fma(g, dx, hx[k]);
                             hy[k] = fma(g, dy, hy[k]);
                             hz[k] = fma(g, dz, hz[k]);
@@ -445,6 +483,20 @@ eval_zrun_kernel(const EvalParams prm) {
                     }
                 }
                 if (j == n_sp_tiles - 1) {
+                    if constexpr (KERNEL == GPB_KERNEL_CUBIC) {      // per-point part of the cubic split (see cov_sp)
+                        const double S0 = tail[20], M1x = tail[21], M1y = tail[22], M1z = tail[23], M2 = tail[24];
+#pragma unroll
+                        for (int k = 0; k < P; ++k) {
+                            const double x2 = fma(X, X, fma(Y, Y, fma(Zc[k], Zc[k], prm.eps_u)));
+                            const double xm = fma(X, M1x, fma(Y, M1y, Zc[k] * M1z));
+                            accZ[k] = fma(-7.0, fma(x2, S0, fma(-2.0, xm, M2)), accZ[k]);
+                            if constexpr (GRAD) {
+                                hx[k] = fma(-14.0, fma(X, S0, -M1x), hx[k]);
+                                hy[k] = fma(-14.0, fma(Y, S0, -M1y), hy[k]);
+                                hz[k] = fma(-14.0, fma(Zc[k], S0, -M1z), hz[k]);
+                            }
+                        }
+                    }
                     if constexpr (GRAD) {
                         const double rr = tail[18];
 #pragma unroll

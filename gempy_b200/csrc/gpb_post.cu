@@ -40,11 +40,24 @@ __global__ void activate_kernel(const double* __restrict__ Z, long long m, const
     }
     if (threadIdx.x == 0) s_base = ids[n];
     __syncthreads();
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (long long)gridDim.x * blockDim.x) {
-        const double z = Z[i];
-        double v = s_base;
-        for (int j = 0; j < n; ++j) v = fma(s_dif[j], sigmoid(slope * (z - s_iso[j])), v);
-        block[i] = v;
+    // four independent loads in flight per thread (the kernel is a pure HBM stream: 8 B in, 8 B out per point)
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < m; i0 += 4 * stride) {
+        double z[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const long long i = i0 + k * stride;
+            z[k] = (i < m) ? Z[i] : 0.0;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const long long i = i0 + k * stride;
+            if (i < m) {
+                double v = s_base;
+                for (int j = 0; j < n; ++j) v = fma(s_dif[j], sigmoid(slope * (z[k] - s_iso[j])), v);
+                block[i] = v;
+            }
+        }
     }
 }
 
