@@ -187,6 +187,28 @@ def combination(refinement: int = 4, **kw) -> ExampleModel:
     return m
 
 
+def greenstone(refinement: Optional[int] = None, **kw) -> ExampleModel:
+    """The Greenstone model the reference ships as examples/data/gempy_models/Greenstone.gempy
+    (gempy/API/examples_generator.py:489-508): 3 series (EarlyGranite | SimpleMafic2, SimpleBIF | SimpleMafic1), 70 surface
+    points, 41 orientations, extent 51 x 67 x 20 km, octree 6 levels; the stored input transform is used as is."""
+    with open(os.path.join(os.path.dirname(_DATA), "greenstone.json")) as fh:
+        d = json.load(fh)
+    sp, op, og, stacks = {}, {}, {}, []
+    for g in d["groups"]:
+        names = []
+        for e in g["elements"]:
+            nm = e["name"]
+            sp[nm] = np.asarray(e["sp_xyz"], float).reshape(-1, 3)
+            op[nm] = np.asarray(e["ori_xyz"], float).reshape(-1, 3)
+            og[nm] = np.asarray(e["ori_grad"], float).reshape(-1, 3)
+            names.append(nm)
+        stacks.append((g["name"], names, StackRelationType(g["structural_relation"])))
+    t = d["input_transform"]
+    tr = Transform(np.asarray(t["position"], float), np.asarray(t["rotation"], float), np.asarray(t["scale"], float))
+    return build_model("Greenstone", sp, op, og, stacks, d["extent"], refinement=refinement or d["number_octree_levels"],
+                       transform=tr, legacy_octree_init=True, **kw)
+
+
 # ------------------------------------------------------------------------------- synthetic configs
 def synthetic_stress(n_sp_per_surface: int = 1000, n_surfaces: int = 4, n_ori: int = 1000,
                      resolution: Sequence[int] = (512, 512, 512), seed: int = 1234,

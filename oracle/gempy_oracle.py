@@ -33,6 +33,11 @@ PARITY STATUS: PINNED against the reference's own golden vectors (tests/test_ora
     the reference-point convention, the octree leaf order and the corner-id refinement rule, and -- through
     the leaf lists, which depend on the lithology/fault ids of every corner at every level -- the fault
     drift, activator, ERODE/FAULT/BASEMENT masks and the stack combination.
+  * the ENGINE OUTPUTS stored in the header of examples/data/gempy_models/Greenstone.gempy (the model of
+    gempy/API/examples_generator.py:489-508: 3 series, 70 surface points, 41 orientations): the scalar field at the
+    four interfaces, 16 digits each, reproduced to 2e-12 / 3e-13 absolute.  This pins at full double precision the
+    assembly with 26 orientations in one stack, the nuggets, the drift, the solve and the evaluation at the surface
+    points (which are NOT shifted by the 1e-6 the grid points get), and `Transform.from_input_points`.
   * custom-grid lith ids [3,3,3,3,1,1,1,1] (test/test_modules/test_grids/test_custom_grid.py:44-47).
   * HORIZONTAL_STRAT's approved vector is disabled in the reference (test_example_models_I.py:34 ``if False``)
     and stale; the plane solution Z = gi_res * z' is asserted instead.

@@ -273,6 +273,20 @@ def test_compute_model_reproduces_approved_vectors(key, build):
     np.testing.assert_allclose(got, want, rtol=0, atol=5e-8)
 
 
+def test_greenstone_isovalues_stored_by_the_engine_gpu():
+    """Engine outputs kept in the reference's Greenstone.gempy header, reproduced by the CUDA path (assembly with 26
+    orientations in one stack, LU, evaluation at the surface points)."""
+    want = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "greenstone_isovalues.json")))
+    m = ex.greenstone(refinement=2)
+    m.options.mesh_extraction = False
+    sol = gc.compute_model(*m.args())
+    assert len(sol.scalar_field_at_surface_points) == 4
+    for name, got in zip(m.element_names, sol.scalar_field_at_surface_points):
+        assert abs(got - want[name]) < 1e-9, (name, got, want[name])
+    # GemPy reorders the elements of a group by decreasing isovalue (geo_model.py:124-127)
+    assert [o.tolist() for o in sol._ordered_elements] == [[0], [0, 1], [0]]
+
+
 @pytest.mark.parametrize("build", [ex.anticline, ex.one_fault, ex.combination])
 def test_compute_model_matches_oracle_everywhere(build):
     m = build()

@@ -44,6 +44,25 @@ def test_approved_scalar_fields(key, build, with_corners):
     np.testing.assert_allclose(got, want, rtol=0, atol=5e-8)
 
 
+def test_greenstone_isovalues_stored_by_the_engine():
+    """examples/data/gempy_models/Greenstone.gempy keeps, in its header, the scalar field at the interfaces the real
+    engine computed (16 significant digits).  Three series, 70 surface points, 41 orientations."""
+    want = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "greenstone_isovalues.json")))
+    m = ex.greenstone()
+    np.testing.assert_allclose(m.transform.scale, [1.0296222316032248e-05] * 3, rtol=1e-15)
+    ii, opt, desc = m.args()
+    f = orc.interpolate_all_fields(ii, opt, desc, np.zeros((1, 3)))
+    got = {}
+    k = 0
+    for st in f.stacks:
+        for iso in st.isovalues:
+            got[m.element_names[k]] = iso
+            k += 1
+    assert set(got) == set(want)
+    for name, v in want.items():
+        assert abs(got[name] - v) < 1e-11, (name, got[name], v)          # measured: 2e-12 / 3e-13
+
+
 def test_custom_grid_known_answer():
     """test/test_modules/test_grids/test_custom_grid.py:24-47."""
     xyz = np.array([[0, 0, 0], [1000, 0, 0], [0, 1000, 0], [1000, 1000, 0],
