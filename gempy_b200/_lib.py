@@ -67,6 +67,7 @@ SIGNATURES = {
     "gpb_emit_children": (C.c_int, [_P, _LL, _LL, _P, C.c_double, C.c_double, C.c_double, _P, _LL,
                                     C.POINTER(_LL), _P]),
     "gpb_any8": (C.c_int, [_P, _LL, _P, _P]),
+    "gpb_gravity": (C.c_int, [_P, _P, C.c_int, _P, C.c_int, _LL, _P, _P]),
     "gpb_dc_edges": (C.c_int, [_P, _LL, _P, _LL, C.c_double, _P, _P, _P, _P]),
     "gpb_dc_vertices": (C.c_int, [_P, _P, _P, _LL, C.c_double, _P, _P]),
 }

@@ -252,6 +252,28 @@ __global__ void emit_kernel(const double* __restrict__ cen, long long ld_c, long
     }
 }
 
+// ---- forward gravity ---------------------------------------------------------------------------------------
+// out[c] = sum_k tz[k] * density[id(c, k) - 1]; one CTA per device centre, fixed-order (deterministic) reduction
+__global__ void __launch_bounds__(256) gravity_kernel(const double* __restrict__ block, const double* __restrict__ dens,
+                                                      int n_dens, const double* __restrict__ tz, long long n_k,
+                                                      double* __restrict__ out) {
+    __shared__ double red[256];
+    const double* b = block + (long long)blockIdx.x * n_k;
+    double acc = 0.0;
+    for (long long k = threadIdx.x; k < n_k; k += 256) {
+        int id = (int)rint(b[k]);
+        id = id < 1 ? 1 : (id > n_dens ? n_dens : id);
+        acc = fma(dens[id - 1], tz[k], acc);
+    }
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[blockIdx.x] = red[0];
+}
+
 // ---- dual contouring -------------------------------------------------------------------------------------
 __constant__ int c_edge_a[12] = {0, 1, 2, 3, 0, 1, 4, 5, 0, 2, 4, 6};
 __constant__ int c_edge_b[12] = {4, 5, 6, 7, 2, 3, 6, 7, 1, 3, 5, 7};
@@ -421,6 +443,15 @@ extern "C" int gpb_any8(const unsigned char* in, long long nvox, unsigned char* 
     GPB_REQUIRE(in && out && nvox >= 0, "bad arguments");
     if (nvox == 0) return GPB_OK;
     any8_kernel<<<blocks_for(nvox), kT, 0, (cudaStream_t)stream>>>(in, nvox, out);
+    GPB_LAUNCH_CHECK();
+    return GPB_OK;
+}
+
+extern "C" int gpb_gravity(const double* block, const double* densities, int n_dens, const double* tz, int n_centers,
+                           long long n_kernel, double* out, void* stream) {
+    GPB_REQUIRE(block && densities && tz && out && n_dens >= 1 && n_centers >= 0 && n_kernel >= 1, "bad arguments");
+    if (n_centers == 0) return GPB_OK;
+    gravity_kernel<<<n_centers, 256, 0, (cudaStream_t)stream>>>(block, densities, n_dens, tz, n_kernel, out);
     GPB_LAUNCH_CHECK();
     return GPB_OK;
 }

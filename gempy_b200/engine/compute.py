@@ -567,8 +567,10 @@ def compute_model(interpolation_input: InterpolationInput, options: Interpolatio
     select the CUDA device and, for one-process-per-GPU runs, the torch.distributed group).  Every rank returns
     the same, complete ``Solutions``.  Raises ``NotImplementedError`` for geophysics input."""
     comm = comm or Comm()
-    if geophysics_input is not None or interpolation_input.grid.geophysics_grid is not None:
-        raise NotImplementedError("forward gravity is outside the B200 backend's scope (SURVEY.md section 8f)")
+    if geophysics_input is not None and interpolation_input.grid.geophysics_grid is None:
+        raise ValueError("geophysics_input needs a centered (geophysics) grid")
+    if geophysics_input is not None and getattr(geophysics_input, "magnetics_input", None) is not None:
+        raise NotImplementedError("magnetics is outside the B200 backend's scope")
     eng = engine or B200Engine(device)
     ii, desc = interpolation_input, data_descriptor
     eo = options.evaluation_options
@@ -593,7 +595,7 @@ def compute_model(interpolation_input: InterpolationInput, options: Interpolatio
     extra_full: List[Segment] = []
     if grid.dense_grid is not None:
         extra_full.append(Segment("dense_grid", grid.dense_grid.n_points, grid=regular_descriptor(grid.dense_grid)))
-    for name in ("custom_grid", "topography", "sections"):
+    for name in ("custom_grid", "topography", "sections", "geophysics_grid"):
         g = getattr(grid, name)
         if g is not None:
             extra_full.append(Segment(name, g.n_points,
@@ -610,6 +612,7 @@ def compute_model(interpolation_input: InterpolationInput, options: Interpolatio
     levels_host = []
     prev_regular = grid.octree_grid
     dc_payload = None
+    gravity = None
     for lvl in range(n_levels):
         need_corners = (lvl < n_levels - 1) or (lvl == dc_level)
         nv = centers.shape[1]
@@ -642,7 +645,8 @@ def compute_model(interpolation_input: InterpolationInput, options: Interpolatio
             og0 = RegularGrid(grid.octree_grid.orthogonal_extent, grid.octree_grid.regular_grid_shape)
             og0._values, og0._n_points = centers_host, nv
             lvl_grid = EngineGrid(octree_grid=og0, dense_grid=grid.dense_grid, topography=grid.topography,
-                                  sections=grid.sections, custom_grid=grid.custom_grid)
+                                  sections=grid.sections, custom_grid=grid.custom_grid,
+                                  geophysics_grid=grid.geophysics_grid)
         else:
             og = RegularGrid.from_octree_level(centers_host, prev_regular)
             og._dxdydz, og._n_points = d.copy(), nv
@@ -657,6 +661,8 @@ def compute_model(interpolation_input: InterpolationInput, options: Interpolatio
                 "faults": Deferred(lambda o=outs[-1], nv=nv: np.rint(o.combined_scalar_field.faults_block[:nv])),
                 "selected": None}
         levels_host.append(host)
+        if lvl == 0 and geophysics_input is not None:
+            gravity = _forward_gravity(eng, geophysics_input, grid.geophysics_grid, f)
         if lvl == dc_level:
             dc_payload = (centers, d.copy(), corners, f)
         if lvl == n_levels - 1:
@@ -670,9 +676,30 @@ def compute_model(interpolation_input: InterpolationInput, options: Interpolatio
     if eo.mesh_extraction and dc_payload is not None:
         meshes = _dual_contouring(eng, ii, options, desc, tables, cache, dc_payload, grid.octree_grid)
 
-    sol = Solutions(octree_levels, meshes, None, options.block_solutions_type)
+    sol = Solutions(octree_levels, meshes, gravity, options.block_solutions_type)
     sol.raw_arrays = _raw_arrays(sol, levels_host, grid, options, meshes)
     return sol
+
+
+def _forward_gravity(eng: B200Engine, geophysics_input, centered_grid, f: FieldsOnDevice) -> np.ndarray:
+    """gravity[c] = sum_k tz[k] * density[lith id at (centre c, kernel voxel k)] on the (gathered) level-0 fields."""
+    tz = getattr(geophysics_input, "tz", None)
+    dens = getattr(geophysics_input, "densities", None)
+    if tz is None or dens is None:
+        gi = getattr(geophysics_input, "gravity_input", None)
+        tz, dens = gi.tz, gi.densities
+    tz_d = torch.as_tensor(np.ascontiguousarray(tz, dtype=np.float64), device=eng.device)
+    dens_d = torch.as_tensor(np.ascontiguousarray(dens, dtype=np.float64), device=eng.device)
+    n_centers = int(centered_grid.centers.shape[0])
+    n_k = int(centered_grid.kernel_grid_centers.shape[0])
+    if tz_d.shape[0] != n_k:
+        raise ValueError(f"tz has {tz_d.shape[0]} entries, the centered grid kernel has {n_k} voxels")
+    sl = f.seg_slice("geophysics_grid")
+    block = f.final_block[sl].contiguous()
+    out = eng.empty(n_centers)
+    _lib.check(eng.lib.gpb_gravity(_ptr(block), _ptr(dens_d), int(dens_d.shape[0]), _ptr(tz_d), n_centers, n_k, _ptr(out),
+                                   eng.stream))
+    return _np(out)
 
 
 def _dual_contouring(eng: B200Engine, ii, options, desc, tables, cache, payload, root_grid) -> List[DualContouringMesh]:

@@ -200,12 +200,27 @@ class GenericGrid:
 
 @dataclass
 class CenteredGrid:
-    """engine_grid.CenteredGrid(centers, radius, resolution) (_engine_factory.py:82-87).
-    Geophysics is outside this backend's scope; the class exists so the
-    bridge's constructor call succeeds and ``compute_model`` can reject it explicitly."""
+    """engine_grid.CenteredGrid(centers, radius, resolution) (_engine_factory.py:82-87): the voxelised kernel of the
+    forward-gravity computation, repeated around every device centre."""
     centers: np.ndarray
     radius: np.ndarray
     resolution: np.ndarray
+
+    def __post_init__(self):
+        from .geophysics import centered_grid_kernel
+        self.centers = np.ascontiguousarray(self.centers, dtype=np.float64).reshape(-1, 3)
+        self.radius = np.broadcast_to(np.asarray(self.radius, dtype=np.float64).ravel(), (3,)).copy()
+        self.resolution = np.asarray(self.resolution, dtype=np.int64).reshape(3)
+        self.kernel_grid_centers, self.kernel_dxyz_left, self.kernel_dxyz_right = centered_grid_kernel(
+            self.resolution, self.radius)
+
+    @property
+    def values(self) -> np.ndarray:
+        return (self.centers[:, None, :] + self.kernel_grid_centers[None, :, :]).reshape(-1, 3)
+
+    @property
+    def n_points(self) -> int:
+        return self.centers.shape[0] * self.kernel_grid_centers.shape[0]
 
 
 @dataclass
@@ -219,7 +234,7 @@ class EngineGrid:
     custom_grid: Optional[GenericGrid] = None
     geophysics_grid: Optional[CenteredGrid] = None
 
-    _ORDER = ("octree_grid", "dense_grid", "custom_grid", "topography", "sections")
+    _ORDER = ("octree_grid", "dense_grid", "custom_grid", "topography", "sections", "geophysics_grid")
 
     def parts(self):
         """[(name, grid)] of the active point sets in evaluation order."""
@@ -238,6 +253,7 @@ class EngineGrid:
     custom_grid_slice = property(lambda self: self._slice_of("custom_grid"))
     topography_slice = property(lambda self: self._slice_of("topography"))
     sections_slice = property(lambda self: self._slice_of("sections"))
+    geophysics_grid_slice = property(lambda self: self._slice_of("geophysics_grid"))
 
     @property
     def len_all_grids(self) -> int:

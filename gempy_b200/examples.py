@@ -23,7 +23,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 
-from .engine.data import (EngineGrid, GenericGrid, InputDataDescriptor, InterpolationInput, InterpolationOptions,
+from .engine.data import (CenteredGrid, EngineGrid, GenericGrid, InputDataDescriptor, InterpolationInput, InterpolationOptions,
                           Orientations, RegularGrid, StackRelationType, StacksStructure, SurfacePoints,
                           TensorsStructure, Transform, BlockSolutionType, AvailableKernelFunctions)
 
@@ -76,7 +76,8 @@ def build_model(name: str, sp_xyz: Dict[str, np.ndarray], ori_xyz: Dict[str, np.
                 resolution: Optional[Sequence[int]] = None, fault_relations: Optional[np.ndarray] = None,
                 custom_xyz: Optional[np.ndarray] = None, options: Optional[InterpolationOptions] = None,
                 transform: Optional[Transform] = None, sp_nugget: float = DEFAULT_SP_NUGGET,
-                ori_nugget: float = DEFAULT_ORI_NUGGET, legacy_octree_init: bool = False) -> ExampleModel:
+                ori_nugget: float = DEFAULT_ORI_NUGGET, legacy_octree_init: bool = False,
+                centered: Optional[Tuple[np.ndarray, np.ndarray, np.ndarray]] = None) -> ExampleModel:
     """``stacks`` = [(group name, [element names in order], relation)] from youngest to oldest."""
     elements = [e for _, els, _ in stacks for e in els]
     sp = np.concatenate([np.asarray(sp_xyz[e], float).reshape(-1, 3) for e in elements])
@@ -103,7 +104,12 @@ def build_model(name: str, sp_xyz: Dict[str, np.ndarray], ori_xyz: Dict[str, np.
             options = InterpolationOptions.init_octree_options(refinement=refinement or 1)
     octree = RegularGrid(ext_t, base)
     custom = GenericGrid(transform.apply(custom_xyz)) if custom_xyz is not None else None
-    grid = EngineGrid(octree_grid=octree, dense_grid=dense, custom_grid=custom)
+    geo = None
+    if centered is not None:                      # _engine_factory.py:82-87
+        c_xyz, c_radius, c_res = centered
+        geo = CenteredGrid(transform.apply(np.asarray(c_xyz, float).reshape(-1, 3)),
+                           transform.scale_points(np.atleast_2d(np.asarray(c_radius, float)))[0], np.asarray(c_res, int))
+    grid = EngineGrid(octree_grid=octree, dense_grid=dense, custom_grid=custom, geophysics_grid=geo)
     options.block_solutions_type = BlockSolutionType.DENSE_GRID if dense is not None else BlockSolutionType.OCTREE
 
     n_elem = len(elements)
@@ -185,6 +191,21 @@ def combination(refinement: int = 4, **kw) -> ExampleModel:
                     fault_relations=np.array([[0, 1, 1], [0, 0, 0], [0, 0, 0]]), **kw)
     m.options.evaluation_options.number_octree_levels_surface = 4
     return m
+
+
+def two_layers_gravity(resolution=(500, 1, 500)):
+    """The model of test/test_modules/test_geophysics/test_gravity.py:10-89: two horizontal surfaces, one device at
+    (6, 0, 4) with a [10, 10, 100] kernel of radius 16000, densities [2.6, 2.4, 3.2].  Returns (model, geophysics_input);
+    the reference's known answer is gravity = [-1624.1714]."""
+    from .engine.geophysics import GeophysicsInput, calculate_gravity_gradient
+    sp = {"surface1": np.array([[3, 0, 3.05], [9, 0, 3.05]]), "surface2": np.array([[3, 0, 1.02], [9, 0, 1.02]])}
+    op = {"surface1": np.array([[6.0, 0.0, 4.0]])}
+    og = {"surface1": np.array([[0.0, 0.0, 1.0]])}
+    centers, radius, res = np.array([[6.0, 0.0, 4.0]]), np.array([16000.0, 16000.0, 16000.0]), np.array([10, 10, 100])
+    m = build_model("2-layers", sp, op, og, [("default", ["surface1", "surface2"], E)], [0, 12, -2, 2, 0, 4],
+                    resolution=resolution, centered=(centers, radius, res))
+    tz = calculate_gravity_gradient(CenteredGrid(centers, radius, res))     # real coordinates, as gp.calculate_gravity_gradient
+    return m, GeophysicsInput(tz=tz, densities=np.array([2.6, 2.4, 3.2]))
 
 
 def greenstone(refinement: Optional[int] = None, **kw) -> ExampleModel:

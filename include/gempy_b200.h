@@ -156,6 +156,11 @@ int gpb_emit_children(const double* centers, long long ld_c, long long nvox, con
 /* out[v] = 1 if any of in[8v .. 8v+7] is non-zero (voxel ownership from the squeezed mask at its corners). */
 int gpb_any8(const unsigned char* in, long long nvox, unsigned char* out, void* stream);
 
+/* ---- forward gravity  [engine stage "geophysics"; known answer test_gravity.py:89] ----------- */
+/* out[c] = sum_k tz[k] * densities[id(c,k) - 1], id = rint(block[c * n_kernel + k]) clamped to 1..n_dens. */
+int gpb_gravity(const double* block, const double* densities, int n_dens, const double* tz, int n_centers,
+                long long n_kernel, double* out, void* stream);
+
 /* ---- (4c) dual contouring  [engine stage "dual_contouring"] ---------------------------------------- */
 /* Edge crossings of one isovalue: for voxel v and edge e (x x x x y y y y z z z z) valid[v*12+e] and the
  * crossing xyz_edge[3][12*nvox]; masked-out voxels (voxel_mask[v]==0) get no crossings. */

@@ -676,6 +676,19 @@ def _stack_gradient_at(interp_input, options, descriptor, i, pts, weights_cache,
 
 
 # ----------------------------------------------------------------------------------------------
+# forward gravity
+# ----------------------------------------------------------------------------------------------
+def forward_gravity(interp_input, options, descriptor, tz, densities) -> np.ndarray:
+    """gravity[c] = sum_k tz[k] * density[lith id at (centre c + kernel voxel k)]
+    (known answer: test/test_modules/test_geophysics/test_gravity.py:89)."""
+    g = interp_input.grid.geophysics_grid
+    f = interpolate_all_fields(interp_input, options, descriptor, g.values, gradient=False)
+    ids = np.clip(f.lith_ids.astype(int), 1, len(densities))
+    dens = np.asarray(densities, float)[ids - 1].reshape(g.centers.shape[0], -1)
+    return (dens * np.asarray(tz, float)[None, :]).sum(axis=1)
+
+
+# ----------------------------------------------------------------------------------------------
 # entry
 # ----------------------------------------------------------------------------------------------
 @dataclasses.dataclass

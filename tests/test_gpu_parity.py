@@ -321,6 +321,16 @@ def test_custom_grid_known_answer_gpu():
     np.testing.assert_array_equal(sol.raw_arrays.custom, np.array([3., 3., 3., 3., 1., 1., 1., 1.]))
 
 
+def test_gravity_known_answer_gpu():
+    """The reference's forward-gravity known answer through compute_model (dense 500 x 1 x 500 + centered grid)."""
+    m, geo = ex.two_layers_gravity()
+    sol = gc.compute_model(*m.args(), geophysics_input=geo)
+    np.testing.assert_almost_equal(sol.gravity, np.array([-1624.1714]), decimal=4)
+    assert sol.raw_arrays.lith_block.shape == (250000,)
+    ids, counts = np.unique(sol.raw_arrays.lith_block, return_counts=True)
+    assert ids.tolist() == [1.0, 2.0, 3.0]
+
+
 def test_dense_grid_solution_shape_and_ids():
     m = ex.combination(resolution=(20, 10, 10))
     m.options.mesh_extraction = False

@@ -63,6 +63,17 @@ def test_greenstone_isovalues_stored_by_the_engine():
         assert abs(got[name] - v) < 1e-11, (name, got[name], v)          # measured: 2e-12 / 3e-13
 
 
+def test_gravity_known_answer():
+    """test/test_modules/test_geophysics/test_gravity.py:89: np.testing.assert_almost_equal(gravity, [-1624.1714], 4)."""
+    m, geo = ex.two_layers_gravity(resolution=(10, 1, 10))
+    ii, opt, desc = m.args()
+    g = orc.forward_gravity(ii, opt, desc, geo.tz, geo.densities)
+    np.testing.assert_almost_equal(g, np.array([-1624.1714]), decimal=4)
+    # the stored isovalues of the same model (2-layers.approved.txt): 0.09000000000000002 and -0.2483333333333333
+    f = orc.interpolate_all_fields(ii, opt, desc, np.zeros((1, 3)))
+    np.testing.assert_allclose(f.stacks[0].isovalues, [0.09000000000000002, -0.2483333333333333], rtol=0, atol=1e-12)
+
+
 def test_custom_grid_known_answer():
     """test/test_modules/test_grids/test_custom_grid.py:24-47."""
     xyz = np.array([[0, 0, 0], [1000, 0, 0], [0, 1000, 0], [1000, 1000, 0],
