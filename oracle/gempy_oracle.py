@@ -93,7 +93,10 @@ def _kernel_name(k) -> str:
 
 
 def kernel_terms(r: np.ndarray, a: float, kind="cubic"):
-    """Return (C, C'/r, C'') at distance r for range a."""
+    """Return (C, C'/r, C'') at distance r for range a.
+    Follows: engine kernel_functions (absent from the tree); "kernel_function": "cubic" is the only kernel the
+    reference's fixtures select (test/test_modules/test_serialize_model.*.verify/*.approved.txt, kernel_options);
+    cubic pinned by the approved vectors and the Greenstone isovalues, exponential / Matern unpinned."""
     kind = _kernel_name(kind)
     if kind == "cubic":
         t = r / a
@@ -177,7 +180,10 @@ class StackData:
 
 
 def prepare_stack(sp, sp_nugget, n_per_surface, ori_pos, ori_grad, ori_nugget, fault_on_sp=None) -> StackData:
-    """ref/rest split: the first point of each surface is its reference point."""
+    """ref/rest split: the first point of each surface is its reference point.
+    Inputs as built by gempy/modules/data_manipulation/_engine_factory.py:26-37 (SurfacePoints / Orientations) and
+    gempy/core/data/structural_frame.py:333-350 (points per element / group); point order = group order, then element
+    order, then table order (structural_frame.py:377-381)."""
     sp = np.asarray(sp, float).reshape(-1, 3)
     n_per_surface = np.asarray(n_per_surface, int)
     starts = np.concatenate([[0], np.cumsum(n_per_surface)[:-1]]).astype(int)
@@ -211,6 +217,9 @@ def system_size(st: StackData, ko) -> int:
 
 
 def assemble_covariance(st: StackData, ko) -> np.ndarray:
+    """The saddle-point matrix of one stack (engine stage "kernel_constructor"; call site
+    gempy/API/compute_API.py:68-73).  Every constant here is pinned by test/test_model_types/*.approved.txt and by the
+    isovalues in examples/data/gempy_models/Greenstone.gempy (see the module header)."""
     a, c_o, gi, ires, kind = ko.range, ko.c_o, ko.gi_res, ko.i_res, ko.kernel_function
     n_o, n_r = st.n_o, st.n_rest
     nu = n_drift_terms(ko.uni_degree)
@@ -271,6 +280,7 @@ def rhs(st: StackData, ko) -> np.ndarray:
 
 
 def solve(A: np.ndarray, b: np.ndarray) -> np.ndarray:
+    """kernel_solver = 1 (direct dense solve, serialization golden kernel_options.kernel_solver): LAPACK gesv."""
     return np.linalg.solve(A, b)
 
 
@@ -330,7 +340,9 @@ def _sig(x):
 
 
 def activate(Z: np.ndarray, isovalues: np.ndarray, ids: np.ndarray, slope: float) -> np.ndarray:
-    """block(Z) = sum_k ids[k] * (sigma(l (Z - lower_k)) - sigma(l (Z - upper_k))).
+    """Engine stage "activator" (SURVEY.md 8a2 row 4a); sigmoid_slope = 5e6 from the serialization golden; unit ids from
+    gempy/core/data/structural_frame.py:367-370; known answer test/test_modules/test_grids/test_custom_grid.py:44-47.
+    block(Z) = sum_k ids[k] * (sigma(l (Z - lower_k)) - sigma(l (Z - upper_k))).
     Interval k lies between isovalues[k-1] (upper) and isovalues[k] (lower); the first has no upper
     bound, the last no lower bound.  ids has len(isovalues)+1 entries."""
     iso = np.asarray(isovalues, float)
@@ -492,6 +504,8 @@ def voxel_children(centers: np.ndarray, dxdydz: np.ndarray) -> np.ndarray:
 
 
 def mark_voxels_by_corners(ids_corners: np.ndarray) -> np.ndarray:
+    """Refine a voxel when its 8 corner ids differ (engine stage "octrees_topology"; the rule
+    that reproduces the leaf lists behind test/test_model_types/*.approved.txt)."""
     u = ids_corners.reshape(-1, 8)
     return (u != u[:, :1]).any(axis=1)
 
@@ -518,6 +532,9 @@ class OracleLevel:
 
 
 def interpolate_n_octree_levels(interp_input, options, descriptor) -> List[OracleLevel]:
+    """Level loop (docs/developers_notes/dev_log/log_2024-05.md:7-8, log_2024-06.md:27-39); root grid = regular grid of
+    the octree base resolution (gempy/core/data/grid.py:127-151, _engine_factory.py:88-96); levels below
+    evaluation_options.octree_min_level are refined everywhere."""
     eo = options.evaluation_options
     og = interp_input.grid.octree_grid
     centers, d = regular_grid_centers(og.orthogonal_extent, og.regular_grid_shape)
@@ -579,6 +596,7 @@ def edge_intersections(corners_xyz: np.ndarray, Z_corners: np.ndarray, iso: floa
 
 
 def dual_contour_vertices(valid: np.ndarray, xyz: np.ndarray, grads: np.ndarray, bias_strength: float = 1.0):
+    # engine stage "dual_contouring" (SURVEY.md 8a2 row 4c); consumers: gempy/core/data/geo_model.py:110-121.  Unpinned.
     """QEF per voxel: 12 edge planes (normal = raw gradient at the crossing) + 3 axis planes through the
     mass point.  Coordinates that are within 1e-8 of zero are ignored by the mass point (upstream quirk)."""
     vv = valid.any(axis=1)
