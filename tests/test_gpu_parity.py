@@ -481,6 +481,40 @@ def test_octree_raw_arrays_fill_matches_dense_evaluation():
 
 
 # ------------------------------------------------------------------------------------------- size-independent properties
+def test_benchmark_workload_sampled_against_oracle(eng):
+    """BASELINE configs[2] data (4000 surface points + 1000 orientations, n = 6999) solved and evaluated on a 256^3 grid
+    by the CUDA path (z-run kernel); 3000 grid points drawn at random are re-evaluated by the oracle with the same
+    weights: field and gradient within 1e-9 of the field's range."""
+    m = ex.synthetic_stress(n_sp_per_surface=1000, n_surfaces=4, n_ori=1000, resolution=(256, 256, 256))
+    ii, opt, desc = m.args()
+    ko = opt.kernel_options
+    st = gc.StackTables(ii, desc, 0, ko, eng.device)
+    A, b = eng.assemble(st)
+    w = eng.solve(A, b)
+    del A
+    g = ii.grid.dense_grid
+    seg = gc.Segment("r", g.n_points, grid=gc.regular_descriptor(g))
+    Z = eng.empty(seg.m)
+    G = eng.empty(3, seg.m)
+    eng.evaluate_segment(st, eng.pack(st, w), seg, 0, Z, G, None)
+    rng = np.random.default_rng(9)
+    idx = np.sort(rng.choice(g.n_points, size=3000, replace=False))
+    ix, rem = np.divmod(idx, 256 * 256)
+    iy, iz = np.divmod(rem, 256)
+    ax = g.axis_coords()
+    xyz = np.stack([ax[0][ix], ax[1][iy], ax[2][iz]], axis=1) + gc.GRID_SHIFT
+    Zr, Gr = orc.evaluate(_oracle_stack(m), ko, w.cpu().numpy(), xyz, gradient=True)
+    it = torch.as_tensor(idx, device=eng.device)
+    Zs = Z.index_select(0, it).cpu().numpy()
+    Gs = G.index_select(1, it).cpu().numpy().T
+    assert _rel_err(Zs, Zr) < RTOL
+    assert _rel_err(Gs, Gr) < RTOL
+    # the solve itself: residual of the 6999 x 6999 system against a fresh assembly
+    A2, b2 = eng.assemble(st)
+    res = (A2 @ w - b2).abs().max().item()
+    assert res < 1e-10
+
+
 def test_linearity_in_the_weights_at_scale(eng):
     """Z is linear in the packed weights: eval(w1 + w2) == eval(w1) + eval(w2), on 2M points / 2.5k data."""
     m = ex.synthetic_stress(n_sp_per_surface=500, n_surfaces=4, n_ori=500, resolution=(128, 128, 128))
