@@ -345,7 +345,7 @@ def main():
     ap.add_argument("--grid", type=int, default=512)
     ap.add_argument("--sp-per-surface", type=int, default=1000)
     ap.add_argument("--n-ori", type=int, default=1000)
-    ap.add_argument("--cpu-sample", type=int, default=32768)
+    ap.add_argument("--cpu-sample", type=int, default=131072)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-m2", action="store_true")
