@@ -70,6 +70,9 @@ SIGNATURES = {
     "gpb_gravity": (C.c_int, [_P, _P, C.c_int, _P, C.c_int, _LL, _P, _P]),
     "gpb_dc_edges": (C.c_int, [_P, _LL, _P, _LL, C.c_double, _P, _P, _P, _P]),
     "gpb_dc_vertices": (C.c_int, [_P, _P, _P, _LL, C.c_double, _P, _P]),
+    "gpb_mc_scratch_elems": (_LL, [_LL]),
+    "gpb_mc_count": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_double, _P, _P, C.POINTER(_LL), C.POINTER(_LL), _P]),
+    "gpb_mc_emit": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_double] + [C.c_double] * 6 + [_P, _P, _P, _P]),
 }
 
 _lib = None

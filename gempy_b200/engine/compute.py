@@ -656,6 +656,7 @@ def compute_model(interpolation_input: InterpolationInput, options: Interpolatio
         level = OctreeLevel(grid_centers=lvl_grid, outputs_centers=outs,
                             _grid_corners=None if corners is None else
                             Deferred(lambda c=corners: EngineGrid.from_xyz_coords(_np(c).T)))
+        level._device_fields = f
         octree_levels.append(level)
         host = {"lith": Deferred(lambda o=outs[-1], nv=nv: np.rint(o.combined_scalar_field.final_block[:nv])),
                 "faults": Deferred(lambda o=outs[-1], nv=nv: np.rint(o.combined_scalar_field.faults_block[:nv])),

@@ -678,6 +678,7 @@ class OctreeLevel:
     _grid_corners: object = None
     outputs_corners: Optional[List[InterpOutput]] = None
     _marked_voxels: object = None                   # refine mask over this level's voxels (lazy)
+    _device_fields: object = None                   # FieldsOnDevice of this level (device consumers: marching cubes)
 
     @property
     def marked_voxels(self) -> Optional[np.ndarray]:

@@ -171,6 +171,23 @@ int gpb_dc_edges(const double* corners, long long ld_k, const double* Z_corners,
 int gpb_dc_vertices(const unsigned char* valid, const double* xyz_edge, const double* grad_edge, long long nvox,
                     double bias, double* vertices, void* stream);
 
+/* ---- marching cubes on the dense grid (replaces the skimage.measure.marching_cubes call of
+ * gempy/modules/mesh_extranction/marching_cubes.py:82-89) -------------------------------------------------
+ * Z: scalar field on an nx*ny*nz lattice (x slowest, z fastest); mask: one byte per lattice point or NULL; a cube is
+ * processed when the mask is set at its far corner (i+1, j+1, k+1).  "above" = Z > level.
+ * Two calls: gpb_mc_count classifies (flags: m bytes; block_offsets: gpb_mc_scratch_elems(m) long longs), scans and
+ * returns the totals through the two HOST pointers (synchronises the stream); gpb_mc_emit writes
+ * vertices [V][3] = (index + t*axis) * (dx,dy,dz) + (ox,oy,oz) and triangles [T][3] (vertex ids, normals towards
+ * lower values); vbase: m ints of scratch.  Vertex order: owner lattice point, then edge axis; triangle order:
+ * cube, then case-table order. */
+long long gpb_mc_scratch_elems(long long m);
+int gpb_mc_count(const double* Z, const unsigned char* mask, int nx, int ny, int nz, double level,
+                 unsigned char* flags, long long* block_offsets, long long* n_vertices_host,
+                 long long* n_triangles_host, void* stream);
+int gpb_mc_emit(const double* Z, const unsigned char* flags, const long long* block_offsets, int nx, int ny, int nz,
+                double level, double ox, double oy, double oz, double dx, double dy, double dz, int* vbase,
+                double* vertices, int* triangles, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -707,6 +707,152 @@ def forward_gravity(interp_input, options, descriptor, tz, densities) -> np.ndar
 
 
 # ----------------------------------------------------------------------------------------------
+# marching cubes on the dense grid
+# ----------------------------------------------------------------------------------------------
+# The reference's dense-grid mesher (gempy/modules/mesh_extranction/marching_cubes.py:13-101) hands each stack's
+# scalar field on the dense grid, the element's isovalue and the stack's squeezed mask to
+# skimage.measure.marching_cubes(method="lewiner", allow_degenerate=False) -- a third-party routine absent from this
+# image (scikit-image; gempy's optional dependency).  Restated here from its published behaviour:
+#   * one vertex per lattice edge whose end values straddle the level, shared by the cubes around the edge;
+#   * a cube is processed only if the mask is set at its far corner (i+1, j+1, k+1)  [pinned, see below];
+#   * vertex = linear interpolation along the edge, in index units * spacing, then + (extent minima)
+#     (marching_cubes.py:82-95: the half-cell offset of the cell centres is NOT added -- kept as the reference does).
+# PIN: test/test_modules/test_marching_cubes.py:44-47 -- COMBINATION on a dense 40 x 20 x 20 grid gives exactly
+# 600 / 860 / 1256 / 1680 vertices for fault / rock3 / rock2 / rock1; this restatement reproduces all four
+# (tests/test_oracle.py::test_marching_cubes_vertex_counts), which also pins the dense-grid fields, the isovalues
+# and the squeezed ERODE masks.  The TRIANGLE table is not pinned (Lewiner resolves ambiguous faces by an interior
+# test; here ambiguous faces always separate the above-level corners): "parity unpinned" for faces.
+MC_EDGE_CORNERS = ((0, 4), (1, 5), (2, 6), (3, 7), (0, 2), (1, 3), (4, 6), (5, 7), (0, 1), (2, 3), (4, 5), (6, 7))
+
+
+def _mc_faces():
+    """Six faces as corner cycles, counter-clockwise seen from outside.  corner id = 4*x + 2*y + z."""
+    faces = []
+    for axis in range(3):
+        for side in (0, 1):
+            u, v = [(1, 2), (2, 0), (0, 1)][axis]
+            if side == 0:
+                u, v = v, u                     # u x v must be the outward normal
+            cyc = []
+            for (a, b) in ((0, 0), (1, 0), (1, 1), (0, 1)):
+                c = [0, 0, 0]
+                c[axis], c[u], c[v] = side, a, b
+                cyc.append(4 * c[0] + 2 * c[1] + c[2])
+            faces.append(cyc)
+    return faces
+
+
+def marching_cubes_table():
+    """256 cases -> list of triangles (edge-id triples).  On every face the crossings are joined so that each run of
+    above-level corners is cut off by its own segment (ambiguous faces separate the above-level corners); segments
+    run from the edge where the counter-clockwise walk leaves the run to the edge where it entered it, the closed
+    loops are fanned from their lowest edge id, and the winding makes normals point towards lower values."""
+    edge_of = {}
+    for e, (a, b) in enumerate(MC_EDGE_CORNERS):
+        edge_of[(a, b)] = e
+        edge_of[(b, a)] = e
+    faces = _mc_faces()
+    table = []
+    for case in range(256):
+        inside = [(case >> c) & 1 for c in range(8)]
+        nxt = {}
+        for cyc in faces:
+            for q in range(4):
+                # a run of inside corners starts at cyc[q] when the previous corner is outside
+                if inside[cyc[q]] and not inside[cyc[q - 1]]:
+                    entry = edge_of[(cyc[q - 1], cyc[q])]
+                    r = q
+                    while inside[cyc[(r + 1) % 4]]:
+                        r += 1
+                    leave = edge_of[(cyc[r % 4], cyc[(r + 1) % 4])]
+                    nxt[leave] = entry
+        tris, seen = [], set()
+        for e0 in sorted(nxt):
+            if e0 in seen:
+                continue
+            loop, e = [], e0
+            while e not in seen:
+                seen.add(e)
+                loop.append(e)
+                e = nxt[e]
+            for t in range(1, len(loop) - 1):
+                tris.append((loop[0], loop[t + 1], loop[t]))
+        table.append(tris)
+    return table
+
+
+_MC_TABLE = None
+
+
+def marching_cubes(Z, shape, level, mask=None, spacing=(1.0, 1.0, 1.0), origin=(0.0, 0.0, 0.0)):
+    """-> vertices (V,3) float64, triangles (T,3) int64.  Vertex order: owner lattice point (x slowest, z fastest),
+    then edge axis x, y, z; triangle order: cube index, then table order."""
+    global _MC_TABLE
+    if _MC_TABLE is None:
+        _MC_TABLE = marching_cubes_table()
+    nx, ny, nz = (int(v) for v in shape)
+    Z = np.asarray(Z, float).reshape(nx, ny, nz)
+    ins = Z > level
+    ok = np.ones((nx - 1, ny - 1, nz - 1), bool) if mask is None else \
+        np.asarray(mask).reshape(nx, ny, nz)[1:, 1:, 1:].astype(bool)
+    # edges needed by at least one processed cube
+    need = [np.zeros((nx - 1, ny, nz), bool), np.zeros((nx, ny - 1, nz), bool), np.zeros((nx, ny, nz - 1), bool)]
+    for a in (0, 1):
+        for b in (0, 1):
+            need[0][:, a:ny - 1 + a, b:nz - 1 + b] |= ok
+            need[1][a:nx - 1 + a, :, b:nz - 1 + b] |= ok
+            need[2][a:nx - 1 + a, b:ny - 1 + b, :] |= ok
+    present = np.zeros((nx, ny, nz, 3), bool)
+    present[:-1, :, :, 0] = (ins[1:] != ins[:-1]) & need[0]
+    present[:, :-1, :, 1] = (ins[:, 1:] != ins[:, :-1]) & need[1]
+    present[:, :, :-1, 2] = (ins[:, :, 1:] != ins[:, :, :-1]) & need[2]
+    flat = present.reshape(-1)
+    index = np.cumsum(flat) - 1                          # vertex id of (point, axis)
+    pts, axes = np.nonzero(present.reshape(-1, 3))
+    i, rem = np.divmod(pts, ny * nz)
+    j, k = np.divmod(rem, nz)
+    ijk = np.stack([i, j, k], axis=1)
+    nb = ijk.copy()
+    nb[np.arange(len(axes)), axes] += 1
+    z0 = Z[i, j, k]
+    z1 = Z[nb[:, 0], nb[:, 1], nb[:, 2]]
+    t = (level - z0) / (z1 - z0)
+    pos = ijk.astype(float)
+    pos[np.arange(len(axes)), axes] += t
+    verts = pos * np.asarray(spacing, float)[None, :] + np.asarray(origin, float)[None, :]
+    # triangles
+    case = np.zeros((nx - 1, ny - 1, nz - 1), int)
+    for c in range(8):
+        cx, cy, cz = c >> 2, (c >> 1) & 1, c & 1
+        case |= ins[cx:nx - 1 + cx, cy:ny - 1 + cy, cz:nz - 1 + cz].astype(int) << c
+    index3 = index.reshape(nx, ny, nz, 3)
+    tris = []
+    for (ci, cj, ck) in np.argwhere(ok & (case > 0) & (case < 255)):
+        for tri in _MC_TABLE[case[ci, cj, ck]]:
+            row = []
+            for e in tri:
+                c0 = MC_EDGE_CORNERS[e][0]
+                row.append(index3[ci + (c0 >> 2), cj + ((c0 >> 1) & 1), ck + (c0 & 1), e // 4])
+            tris.append(row)
+    return verts, np.asarray(tris, dtype=np.int64).reshape(-1, 3)
+
+
+def marching_cubes_meshes(fields: "FieldsResult", descriptor, dense_shape, dense_slice: slice, real_extent):
+    """What set_meshes_with_marching_cubes leaves on the structural elements (marching_cubes.py:37-55): per stack,
+    per surface, (vertices, triangles) in real coordinates; faults use no mask, other stacks their squeezed mask."""
+    shape = np.asarray(dense_shape, int)
+    ext = np.asarray(real_extent, float)
+    spacing = (ext[1::2] - ext[0::2]) / shape
+    out = []
+    for st in fields.stacks:
+        Z = st.Z[dense_slice]
+        mask = None if st.relation == FAULT else st.squeezed_mask[dense_slice]
+        for iso in st.isovalues:
+            out.append(marching_cubes(Z, shape, iso, mask, spacing, ext[0::2]))
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
 # entry
 # ----------------------------------------------------------------------------------------------
 @dataclasses.dataclass

@@ -155,3 +155,41 @@ def test_dual_contouring_vertices_near_surface():
         iso = f.stacks[0].isovalues[mesh.surface]
         assert np.abs(z - iso).max() < 0.03        # vertices sit on the isosurface to a fraction of a voxel
         assert mesh.edges.max() < mesh.vertices.shape[0]
+
+
+def test_marching_cubes_vertex_counts():
+    """test/test_modules/test_marching_cubes.py:13-47: COMBINATION on a dense 40 x 20 x 20 grid; the reference pins
+    600 / 860 / 1256 / 1680 vertices for fault / rock3 / rock2 / rock1.  Reproducing all four pins the dense-grid
+    fields (fault drift included), the isovalues, the squeezed ERODE masks and the far-corner mask rule."""
+    m = ex.combination(refinement=None, resolution=(40, 20, 20))
+    ii, opt, desc = m.args()
+    g = ii.grid.dense_grid
+    f = orc.interpolate_all_fields(ii, opt, desc, g.values + orc.GRID_SHIFT)
+    meshes = orc.marching_cubes_meshes(f, desc, g.regular_grid_shape, slice(0, g.n_points), m.extent)
+    assert [v.shape[0] for v, _ in meshes] == [600, 860, 1256, 1680]
+    # vertices come back in real coordinates inside the model extent (marching_cubes.py:92-95)
+    for v, t in meshes:
+        assert (v.min(0) >= -1e-9).all() and (v.max(0) <= np.array([2500, 1000, 1000]) + 1e-9).all()
+        assert t.min() == 0 and t.max() == v.shape[0] - 1
+
+
+def test_marching_cubes_table_is_watertight():
+    """Closed surface of a smooth blob: every directed edge is matched by its reverse, Euler characteristic 2,
+    normals towards lower values; the 256-case table never exceeds 5 triangles per cube."""
+    table = orc.marching_cubes_table()
+    assert max(len(t) for t in table) == 5 and len(table[0]) == 0 and len(table[255]) == 0
+    for case in range(256):                      # complementary cases cut the same edges
+        assert sorted({e for t in table[case] for e in t}) == sorted({e for t in table[255 - case] for e in t})
+    n = 20
+    ax = np.linspace(-1, 1, n)
+    X, Y, Z = np.meshgrid(ax, ax, ax, indexing="ij")
+    F = 0.6 - np.sqrt(X ** 2 + 1.3 * Y ** 2 + 0.8 * Z ** 2) + 0.15 * np.sin(5 * X) * np.cos(4 * Y)
+    v, t = orc.marching_cubes(F, (n, n, n), 0.0)
+    edges = np.concatenate([t[:, [0, 1]], t[:, [1, 2]], t[:, [2, 0]]])
+    directed = set(map(tuple, edges.tolist()))
+    assert len(directed) == edges.shape[0]
+    assert all((b, a) in directed for a, b in directed)
+    assert v.shape[0] - len(directed) // 2 + t.shape[0] == 2
+    tri = v[t]
+    nrm = np.cross(tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 0])
+    assert (np.einsum("ij,ij->i", nrm, tri.mean(1) - (n - 1) / 2) > 0).all()
