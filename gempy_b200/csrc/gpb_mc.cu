@@ -13,7 +13,7 @@
 
 namespace {
 
-constexpr int kBlock = 1024;
+constexpr int kBlock = 4096;         // lattice points per CTA
 constexpr int kMaxTri = 5;
 
 __constant__ unsigned char c_ntri[256];
@@ -110,10 +110,34 @@ int upload_case_table() {
 }
 
 // ---- device helpers -----------------------------------------------------------------------------------------
+// One CTA = kBlock consecutive lattice points.  The emit kernels run kThreads threads x kPts consecutive points each:
+// flag bytes move as one 128-bit word per thread, first-vertex ids as 128-bit stores, and the CTA-wide scan runs over
+// the per-thread partial sums.  The classify kernel (order-free: it only needs CTA totals) strides its kClassifyThreads
+// threads over the CTA's points so that every access of a warp is contiguous.
+constexpr int kPts = 16;
+constexpr int kThreads = kBlock / kPts;
+constexpr int kClassifyThreads = 256;
+
 struct Lattice {
     int nx, ny, nz;
     long long m;
 };
+
+__device__ __forceinline__ void decompose(const Lattice& L, long long p, int& i, int& j, int& k) {
+    if (L.m <= 0x7fffffffLL) {                       // 32-bit divisions (the 64-bit ones cost ~10x more)
+        const unsigned pp = (unsigned)p;
+        const unsigned r = pp / (unsigned)L.nz;
+        k = (int)(pp - r * (unsigned)L.nz);
+        const unsigned q = r / (unsigned)L.ny;
+        j = (int)(r - q * (unsigned)L.ny);
+        i = (int)q;
+    } else {
+        k = (int)(p % L.nz);
+        const long long r = p / L.nz;
+        j = (int)(r % L.ny);
+        i = (int)(r / L.ny);
+    }
+}
 
 // is the cube whose origin corner is (i, j, k) processed?  (inside the lattice and mask set at its far corner)
 __device__ __forceinline__ bool cube_on(const Lattice& L, const unsigned char* __restrict__ mask, int i, int j, int k) {
@@ -121,12 +145,9 @@ __device__ __forceinline__ bool cube_on(const Lattice& L, const unsigned char* _
     return mask == nullptr || mask[((long long)(i + 1) * L.ny + (j + 1)) * L.nz + (k + 1)] != 0;
 }
 
-// flag byte of lattice point p: bits 0..2 = vertex on the +x/+y/+z edge, bits 3..5 = triangles of its cube
+// flag byte of lattice point p = (i, j, k): bits 0..2 = vertex on the +x/+y/+z edge, bits 3..5 = triangles of its cube
 __device__ __forceinline__ unsigned classify(const Lattice& L, const double* __restrict__ Z, const unsigned char* __restrict__ mask,
-                                             double level, long long p) {
-    const int k = (int)(p % L.nz);
-    const long long r = p / L.nz;
-    const int j = (int)(r % L.ny), i = (int)(r / L.ny);
+                                             double level, long long p, int i, int j, int k) {
     const long long sy = L.nz, sx = (long long)L.ny * L.nz;
     const bool hx = i + 1 < L.nx, hy = j + 1 < L.ny, hz = k + 1 < L.nz;
     const bool s0 = Z[p] > level;
@@ -145,7 +166,7 @@ __device__ __forceinline__ unsigned classify(const Lattice& L, const double* __r
     if (hz && c[1] != s0 &&
         (cube_on(L, mask, i - 1, j - 1, k) || cube_on(L, mask, i - 1, j, k) || cube_on(L, mask, i, j - 1, k) || cube_on(L, mask, i, j, k)))
         flags |= 4u;
-    if (hx && hy && hz && cube_on(L, mask, i, j, k)) {
+    if (hx && hy && hz) {
         c[6] = Z[p + sx + sy] > level;
         c[5] = Z[p + sx + 1] > level;
         c[3] = Z[p + sy + 1] > level;
@@ -153,7 +174,7 @@ __device__ __forceinline__ unsigned classify(const Lattice& L, const double* __r
         unsigned cs = 0;
 #pragma unroll
         for (int q = 0; q < 8; ++q) cs |= (c[q] ? 1u : 0u) << q;
-        flags |= (unsigned)c_ntri[cs] << 3;
+        if (cs != 0u && cs != 255u && cube_on(L, mask, i, j, k)) flags |= (unsigned)c_ntri[cs] << 3;
     }
     return flags;
 }
@@ -161,8 +182,23 @@ __device__ __forceinline__ unsigned classify(const Lattice& L, const double* __r
 __device__ __forceinline__ int nverts_of(unsigned f) { return __popc(f & 7u); }
 __device__ __forceinline__ int ntris_of(unsigned f) { return (int)(f >> 3); }
 
-// block-wide exclusive scan of one int per thread (1024 threads); returns the exclusive prefix, total in *total
-__device__ __forceinline__ int block_exclusive_scan(int v, int* warp_sums, int* total) {
+// the kPts flag bytes of a thread, as one 128-bit word when the run is complete and aligned
+__device__ __forceinline__ void load_flags(const unsigned char* __restrict__ flags, long long p, long long m, unsigned f[kPts]) {
+    static_assert(kPts == 16, "one uint4 of flag bytes per thread");
+    if (p + kPts <= m && (reinterpret_cast<uintptr_t>(flags) & 15u) == 0) {
+        const uint4 w4 = *reinterpret_cast<const uint4*>(flags + p);
+        const unsigned w[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+        for (int q = 0; q < kPts; ++q) f[q] = (w[q >> 2] >> (8 * (q & 3))) & 255u;
+    } else {
+#pragma unroll
+        for (int q = 0; q < kPts; ++q) f[q] = (p + q < m) ? flags[p + q] : 0u;
+    }
+}
+
+// CTA-wide exclusive scan of one int per thread (kThreads threads); returns the exclusive prefix
+__device__ __forceinline__ int block_exclusive_scan(int v, int* warp_sums) {
+    constexpr int kWarps = kThreads / 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int incl = v;
 #pragma unroll
@@ -173,64 +209,107 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int* warp_sums, int* 
     if (lane == 31) warp_sums[warp] = incl;
     __syncthreads();
     if (warp == 0) {
-        int w = warp_sums[lane];
+        const int w = (lane < kWarps) ? warp_sums[lane] : 0;
         int wi = w;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
+        for (int o = 1; o < kWarps; o <<= 1) {
             const int t = __shfl_up_sync(0xffffffffu, wi, o);
             if (lane >= o) wi += t;
         }
-        warp_sums[lane] = wi - w;                // exclusive over warps
-        if (lane == 31) *total = wi;
+        if (lane < kWarps) warp_sums[lane] = wi - w;                // exclusive over warps
     }
     __syncthreads();
-    const int r = warp_sums[warp] + incl - v;
-    __syncthreads();
-    return r;
+    return warp_sums[warp] + incl - v;
 }
 
-__global__ void __launch_bounds__(kBlock) mc_classify_kernel(Lattice L, const double* __restrict__ Z, const unsigned char* __restrict__ mask,
-                                                             double level, unsigned char* __restrict__ flags,
-                                                             long long* __restrict__ block_counts, long long nblocks) {
-    __shared__ int ws[32];
-    __shared__ int tv, tt;
-    const long long p = (long long)blockIdx.x * kBlock + threadIdx.x;
-    unsigned f = 0;
+__global__ void __launch_bounds__(kClassifyThreads) mc_classify_kernel(Lattice L, const double* __restrict__ Z, const unsigned char* __restrict__ mask,
+                                                               double level, unsigned char* __restrict__ flags,
+                                                               long long* __restrict__ block_counts, long long nblocks) {
+    __shared__ int red[kClassifyThreads / 32];
+    // coalesced mapping (only the CTA totals are needed here, so the order inside the CTA is free):
+    // thread t takes points base + t, base + t + 256, ... -> every Z / mask / flag access of a warp is contiguous;
+    // per-thread maxima 16 x 3 vertices and 16 x 5 triangles keep the packed halves apart up to the CTA total
+    // (4096 x 3 and 4096 x 5 < 65536)
+    long long p = (long long)blockIdx.x * kBlock + threadIdx.x;
+    int packed = 0;                                   // vertices in the low half, triangles in the high half
     if (p < L.m) {
-        f = classify(L, Z, mask, level, p);
-        flags[p] = (unsigned char)f;
+        int i, j, k;
+        decompose(L, p, i, j, k);
+#pragma unroll 4
+        for (int q = 0; q < kBlock / kClassifyThreads; ++q) {
+            if (p >= L.m) break;
+            const unsigned f = classify(L, Z, mask, level, p, i, j, k);
+            flags[p] = (unsigned char)f;
+            packed += nverts_of(f) | (ntris_of(f) << 16);
+            p += kClassifyThreads;
+            k += kClassifyThreads;
+            if (k >= L.nz) {
+                const int c = k / L.nz;
+                k -= c * L.nz;
+                j += c;
+                if (j >= L.ny) { const int d = j / L.ny; j -= d * L.ny; i += d; }
+            }
+        }
     }
-    block_exclusive_scan(nverts_of(f), ws, &tv);
-    block_exclusive_scan(ntris_of(f), ws, &tt);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) packed += __shfl_down_sync(0xffffffffu, packed, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = packed;
+    __syncthreads();
     if (threadIdx.x == 0) {
-        block_counts[blockIdx.x] = tv;
-        block_counts[nblocks + 1 + blockIdx.x] = tt;
+        int t = 0;
+#pragma unroll
+        for (int w = 0; w < kClassifyThreads / 32; ++w) t += red[w];
+        block_counts[blockIdx.x] = t & 0xffff;
+        block_counts[nblocks + 1 + blockIdx.x] = t >> 16;
     }
 }
 
-// exclusive scan of two arrays of nblocks entries (each followed by a total slot), one CTA
-__global__ void __launch_bounds__(kBlock) mc_scan_kernel(long long* counts, long long nblocks) {
-    __shared__ long long buf[kBlock];
+// exclusive scan of two arrays of nblocks entries (each followed by a total slot), one CTA,
+// 16 consecutive entries per thread and 16 384 per sweep
+__global__ void __launch_bounds__(1024) mc_scan_kernel(long long* counts, long long nblocks) {
+    constexpr int kPer = 16;
+    __shared__ long long wsum[32];
     __shared__ long long carry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int which = 0; which < 2; ++which) {
         long long* a = counts + which * (nblocks + 1);
         if (threadIdx.x == 0) carry = 0;
         __syncthreads();
-        for (long long base = 0; base < nblocks; base += kBlock) {
-            const long long i = base + threadIdx.x;
-            const long long own = (i < nblocks) ? a[i] : 0;
-            buf[threadIdx.x] = own;
-            __syncthreads();
-            for (int o = 1; o < kBlock; o <<= 1) {
-                const long long t = (threadIdx.x >= o) ? buf[threadIdx.x - o] : 0;
-                __syncthreads();
-                buf[threadIdx.x] += t;
-                __syncthreads();
+        for (long long base = 0; base < nblocks; base += 1024 * kPer) {
+            const long long i0 = base + (long long)threadIdx.x * kPer;
+            long long v[kPer], own = 0;
+#pragma unroll
+            for (int e = 0; e < kPer; ++e) {
+                v[e] = (i0 + e < nblocks) ? a[i0 + e] : 0;
+                own += v[e];
             }
-            const long long incl = buf[threadIdx.x];
-            if (i < nblocks) a[i] = carry + incl - own;
+            long long incl = own;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const long long t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            if (lane == 31) wsum[warp] = incl;
             __syncthreads();
-            if (threadIdx.x == kBlock - 1) carry += incl;
+            if (warp == 0) {
+                const long long w = wsum[lane];
+                long long wi = w;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const long long t = __shfl_up_sync(0xffffffffu, wi, o);
+                    if (lane >= o) wi += t;
+                }
+                wsum[lane] = wi - w;
+            }
+            __syncthreads();
+            long long run = carry + wsum[warp] + incl - own;
+#pragma unroll
+            for (int e = 0; e < kPer; ++e) {
+                if (i0 + e < nblocks) a[i0 + e] = run;
+                run += v[e];
+            }
+            __syncthreads();
+            if (threadIdx.x == 1023) carry = run;
             __syncthreads();
         }
         if (threadIdx.x == 0) a[nblocks] = carry;
@@ -238,65 +317,90 @@ __global__ void __launch_bounds__(kBlock) mc_scan_kernel(long long* counts, long
     }
 }
 
-__global__ void __launch_bounds__(kBlock) mc_vertices_kernel(Lattice L, const double* __restrict__ Z, const unsigned char* __restrict__ flags,
-                                                             const long long* __restrict__ block_offsets, double level,
-                                                             double ox, double oy, double oz, double dx, double dy, double dz,
-                                                             int* __restrict__ vbase, double* __restrict__ vertices) {
-    __shared__ int ws[32];
-    __shared__ int total;
-    const long long p = (long long)blockIdx.x * kBlock + threadIdx.x;
-    const unsigned f = (p < L.m) ? flags[p] : 0u;
-    const int pre = block_exclusive_scan(nverts_of(f), ws, &total);
+__global__ void __launch_bounds__(kThreads) mc_vertices_kernel(Lattice L, const double* __restrict__ Z, const unsigned char* __restrict__ flags,
+                                                               const long long* __restrict__ block_offsets, double level,
+                                                               double ox, double oy, double oz, double dx, double dy, double dz,
+                                                               int* __restrict__ vbase, double* __restrict__ vertices) {
+    __shared__ int ws[kThreads / 32];
+    const long long p = (long long)blockIdx.x * kBlock + (long long)threadIdx.x * kPts;
+    unsigned f[kPts];
+    load_flags(flags, p, L.m, f);
+    int local[kPts], sum = 0;
+#pragma unroll
+    for (int q = 0; q < kPts; ++q) { local[q] = sum; sum += nverts_of(f[q]); }
+    const int pre = block_exclusive_scan(sum, ws);
     if (p >= L.m) return;
-    long long slot = block_offsets[blockIdx.x] + pre;
-    vbase[p] = (int)slot;
-    if ((f & 7u) == 0) return;
-    const int k = (int)(p % L.nz);
-    const long long r = p / L.nz;
-    const int j = (int)(r % L.ny), i = (int)(r / L.ny);
-    const double z0 = Z[p];
+    const long long first = block_offsets[blockIdx.x] + pre;
+    if (p + kPts <= L.m && (reinterpret_cast<uintptr_t>(vbase) & 15u) == 0) {
+#pragma unroll
+        for (int q = 0; q < kPts; q += 4)
+            *reinterpret_cast<int4*>(vbase + p + q) =
+                make_int4((int)first + local[q], (int)first + local[q + 1], (int)first + local[q + 2], (int)first + local[q + 3]);
+    } else {
+#pragma unroll
+        for (int q = 0; q < kPts; ++q)
+            if (p + q < L.m) vbase[p + q] = (int)first + local[q];
+    }
+    if (sum == 0) return;
     const long long sx = (long long)L.ny * L.nz, sy = L.nz;
 #pragma unroll
-    for (int a = 0; a < 3; ++a) {
-        if (!(f & (1u << a))) continue;
-        const double z1 = Z[p + (a == 0 ? sx : (a == 1 ? sy : 1))];
-        const double t = (level - z0) / (z1 - z0);
-        double* o = vertices + 3 * slot;
-        o[0] = ((double)i + (a == 0 ? t : 0.0)) * dx + ox;
-        o[1] = ((double)j + (a == 1 ? t : 0.0)) * dy + oy;
-        o[2] = ((double)k + (a == 2 ? t : 0.0)) * dz + oz;
-        ++slot;
+    for (int q = 0; q < kPts; ++q) {
+        if ((f[q] & 7u) == 0) continue;
+        int i, j, k;
+        decompose(L, p + q, i, j, k);
+        const double z0 = Z[p + q];
+        long long slot = first + local[q];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            if (!(f[q] & (1u << a))) continue;
+            const double z1 = Z[p + q + (a == 0 ? sx : (a == 1 ? sy : 1))];
+            const double t = (level - z0) / (z1 - z0);
+            double* o = vertices + 3 * slot;
+            o[0] = ((double)i + (a == 0 ? t : 0.0)) * dx + ox;
+            o[1] = ((double)j + (a == 1 ? t : 0.0)) * dy + oy;
+            o[2] = ((double)k + (a == 2 ? t : 0.0)) * dz + oz;
+            ++slot;
+        }
     }
 }
 
-__global__ void __launch_bounds__(kBlock) mc_triangles_kernel(Lattice L, const double* __restrict__ Z, const unsigned char* __restrict__ flags,
-                                                              const long long* __restrict__ block_offsets, double level,
-                                                              const int* __restrict__ vbase, int* __restrict__ triangles) {
-    __shared__ int ws[32];
-    __shared__ int total;
-    const long long p = (long long)blockIdx.x * kBlock + threadIdx.x;
-    const unsigned f = (p < L.m) ? flags[p] : 0u;
-    const int nt = ntris_of(f);
-    const int pre = block_exclusive_scan(nt, ws, &total);
-    if (nt == 0) return;
+__global__ void __launch_bounds__(kThreads) mc_triangles_kernel(Lattice L, const double* __restrict__ Z, const unsigned char* __restrict__ flags,
+                                                                const long long* __restrict__ block_offsets, double level,
+                                                                const int* __restrict__ vbase, int* __restrict__ triangles) {
+    __shared__ int ws[kThreads / 32];
+    const long long p = (long long)blockIdx.x * kBlock + (long long)threadIdx.x * kPts;
+    unsigned f[kPts];
+    load_flags(flags, p, L.m, f);
+    int local[kPts], sum = 0;
+#pragma unroll
+    for (int q = 0; q < kPts; ++q) { local[q] = sum; sum += ntris_of(f[q]); }
+    const int pre = block_exclusive_scan(sum, ws);
+    if (sum == 0) return;
     const long long sy = L.nz, sx = (long long)L.ny * L.nz;
-    unsigned cs = 0;
+    const long long first = block_offsets[blockIdx.x] + pre;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-        const long long pq = p + (q >> 2) * sx + ((q >> 1) & 1) * sy + (q & 1);
-        cs |= (Z[pq] > level ? 1u : 0u) << q;
-    }
-    int* o = triangles + 3 * (block_offsets[blockIdx.x] + pre);
-    for (int t = 0; t < nt; ++t)
+    for (int q = 0; q < kPts; ++q) {
+        const int nt = ntris_of(f[q]);
+        if (nt == 0) continue;
+        const long long pq = p + q;
+        unsigned cs = 0;
 #pragma unroll
-        for (int v = 0; v < 3; ++v) {
-            const int e = c_tri[(cs * kMaxTri + t) * 3 + v];
-            const int q = c_edge_corner[e];
-            const int axis = e >> 2;
-            const long long owner = p + (q >> 2) * sx + ((q >> 1) & 1) * sy + (q & 1);
-            const unsigned fo = flags[owner];
-            o[3 * t + v] = vbase[owner] + __popc(fo & ((1u << axis) - 1u));
+        for (int c = 0; c < 8; ++c) {
+            const long long pc = pq + (c >> 2) * sx + ((c >> 1) & 1) * sy + (c & 1);
+            cs |= (Z[pc] > level ? 1u : 0u) << c;
         }
+        int* o = triangles + 3 * (first + local[q]);
+        for (int t = 0; t < nt; ++t)
+#pragma unroll
+            for (int v = 0; v < 3; ++v) {
+                const int e = c_tri[(cs * kMaxTri + t) * 3 + v];
+                const int c = c_edge_corner[e];
+                const int axis = e >> 2;
+                const long long owner = pq + (c >> 2) * sx + ((c >> 1) & 1) * sy + (c & 1);
+                const unsigned fo = flags[owner];
+                o[3 * t + v] = vbase[owner] + __popc(fo & ((1u << axis) - 1u));
+            }
+    }
 }
 
 }  // namespace
@@ -316,9 +420,9 @@ extern "C" int gpb_mc_count(const double* Z, const unsigned char* mask, int nx, 
     cudaStream_t s = (cudaStream_t)stream;
     Lattice L{nx, ny, nz, (long long)nx * ny * nz};
     const long long nblocks = (L.m + kBlock - 1) / kBlock;
-    mc_classify_kernel<<<(unsigned)nblocks, kBlock, 0, s>>>(L, Z, mask, level, flags, block_offsets, nblocks);
+    mc_classify_kernel<<<(unsigned)nblocks, kClassifyThreads, 0, s>>>(L, Z, mask, level, flags, block_offsets, nblocks);
     GPB_LAUNCH_CHECK();
-    mc_scan_kernel<<<1, kBlock, 0, s>>>(block_offsets, nblocks);
+    mc_scan_kernel<<<1, 1024, 0, s>>>(block_offsets, nblocks);
     GPB_LAUNCH_CHECK();
     long long totals[2] = {0, 0};
     GPB_CHECK_CUDA(cudaMemcpyAsync(&totals[0], block_offsets + nblocks, sizeof(long long), cudaMemcpyDeviceToHost, s));
@@ -340,10 +444,10 @@ extern "C" int gpb_mc_emit(const double* Z, const unsigned char* flags, const lo
     Lattice L{nx, ny, nz, (long long)nx * ny * nz};
     const long long nblocks = (L.m + kBlock - 1) / kBlock;
     GPB_REQUIRE(vertices != nullptr, "vertices buffer is null");
-    mc_vertices_kernel<<<(unsigned)nblocks, kBlock, 0, s>>>(L, Z, flags, block_offsets, level, ox, oy, oz, dx, dy, dz, vbase, vertices);
+    mc_vertices_kernel<<<(unsigned)nblocks, kThreads, 0, s>>>(L, Z, flags, block_offsets, level, ox, oy, oz, dx, dy, dz, vbase, vertices);
     GPB_LAUNCH_CHECK();
     if (triangles != nullptr) {
-        mc_triangles_kernel<<<(unsigned)nblocks, kBlock, 0, s>>>(L, Z, flags, block_offsets + nblocks + 1, level, vbase, triangles);
+        mc_triangles_kernel<<<(unsigned)nblocks, kThreads, 0, s>>>(L, Z, flags, block_offsets + nblocks + 1, level, vbase, triangles);
         GPB_LAUNCH_CHECK();
     }
     return GPB_OK;

@@ -47,4 +47,26 @@ n = st.n
 A = eng.empty(n, n); b = eng.empty(n); s = st.struct()
 ms = timed(lambda: _lib.check(eng.lib.gpb_assemble_cov(C.byref(s), A.data_ptr(), n, b.data_ptr(), eng.stream)))
 out["assemble_cov_n6999"] = {"ms": ms, "algorithmic_bytes": 8 * n * n, "gbs": 8 * n * n / ms / 1e6, "frac": 8 * n * n / ms / 1e6 / peak}
+del A, Zs, Bs, fb, fa, sq, mk, block
+# ---- marching cubes on a 512^3 lattice (blob surface), pass by pass
+nn = 512
+ax = torch.linspace(-1, 1, nn, dtype=torch.float64, device=eng.device)
+F = (0.7 - torch.sqrt(ax[:, None, None] ** 2 + 1.3 * ax[None, :, None] ** 2 + 0.8 * ax[None, None, :] ** 2)).contiguous().view(-1)
+msk = torch.ones(m, dtype=torch.uint8, device=eng.device)
+flags = torch.empty(m, dtype=torch.uint8, device=eng.device)
+offs = torch.empty(int(eng.lib.gpb_mc_scratch_elems(m)), dtype=torch.int64, device=eng.device)
+nv, nt = C.c_longlong(), C.c_longlong()
+count = lambda: _lib.check(eng.lib.gpb_mc_count(F.data_ptr(), msk.data_ptr(), nn, nn, nn, 0.0, flags.data_ptr(), offs.data_ptr(), C.byref(nv), C.byref(nt), eng.stream))
+ms_c = timed(count)
+vb = torch.empty(m, dtype=torch.int32, device=eng.device)
+V = torch.empty(nv.value, 3, dtype=torch.float64, device=eng.device); T = torch.empty(nt.value, 3, dtype=torch.int32, device=eng.device)
+emit = lambda: _lib.check(eng.lib.gpb_mc_emit(F.data_ptr(), flags.data_ptr(), offs.data_ptr(), nn, nn, nn, 0.0, 0., 0., 0., 1., 1., 1., vb.data_ptr(), V.data_ptr(), T.data_ptr(), eng.stream))
+ms_e = timed(emit)
+b_c = 10 * m
+b_e = 6 * m + 24 * nv.value + 12 * nt.value
+out["marching_cubes_512"] = {"vertices": nv.value, "triangles": nt.value,
+                             "count": {"ms": ms_c, "algorithmic_bytes": b_c, "gbs": b_c / ms_c / 1e6, "frac": b_c / ms_c / 1e6 / peak,
+                                       "note": "classify + scan + host read of the totals; Z 8 B + mask 1 B read, flags 1 B written per point"},
+                             "emit": {"ms": ms_e, "algorithmic_bytes": b_e, "gbs": b_e / ms_e / 1e6, "frac": b_e / ms_e / 1e6 / peak,
+                                      "note": "vertices + triangles passes; flags read twice (2 B), vbase 4 B written per point, plus the mesh"}}
 print(json.dumps(out))
