@@ -356,16 +356,19 @@ panel_cluster_kernel(int n, int k0, int jb, double* __restrict__ A, int lda, int
 // One CTA handles 64 columns.
 // Blocks beyond the matrix' own column blocks work on the right-hand sides B (n x nrhs, ldb): the forward
 // substitution of gpb_lu_solve is carried along with the factorisation.
+// col_begin/col_end bound the matrix columns handled (the outer-blocked path restricts them); do_swap = 0 skips the
+// interchanges (already applied by laswp_kernel).
 __global__ void __launch_bounds__(256) swap_trsm_kernel(int n, int k0, int jb, double* __restrict__ A, int lda,
                                                         const int* __restrict__ ipiv, int n_mat_blocks,
-                                                        double* __restrict__ B, int ldb, int nrhs) {
+                                                        double* __restrict__ B, int ldb, int nrhs,
+                                                        int col_begin, int col_end, int do_swap) {
     __shared__ double L[kNB][kNB + 1];
     __shared__ double T[64][kNB + 1];
     __shared__ int piv[kNB];
     const int tid = threadIdx.x;
     const bool on_rhs = (int)blockIdx.x >= n_mat_blocks;
-    const int c0 = on_rhs ? ((int)blockIdx.x - n_mat_blocks) * 64 : k0 + jb + blockIdx.x * 64;
-    const int ncol = on_rhs ? min(64, nrhs - c0) : min(64, n - c0);
+    const int c0 = on_rhs ? ((int)blockIdx.x - n_mat_blocks) * 64 : col_begin + blockIdx.x * 64;
+    const int ncol = on_rhs ? min(64, nrhs - c0) : min(64, col_end - c0);
     double* const M = on_rhs ? B : A;              // the columns this block transforms
     const int ldm = on_rhs ? ldb : lda;
     for (int e = tid; e < jb * jb; e += 256) {
@@ -375,7 +378,7 @@ __global__ void __launch_bounds__(256) swap_trsm_kernel(int n, int k0, int jb, d
     if (tid < jb) piv[tid] = ipiv[k0 + tid];
     __syncthreads();
     // interchanges: one thread per column, sequential over the panel's pivots
-    if (tid < ncol) {
+    if (do_swap && tid < ncol) {
         double* c = M + (long long)(c0 + tid) * ldm;
         for (int j = 0; j < jb; ++j) {
             const int p = piv[j];
@@ -480,7 +483,7 @@ __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, do
 }
 
 constexpr int kGM = 64, kGN = 64;       // CTA tile
-constexpr int kLdA = kGM + 8;           // As[k][m]: ld = 8 mod 16 doubles -> 2 wavefronts per fragment load (optimal)
+constexpr int kLdA = kGM + 4;           // As[k][m]: ld = 4 mod 16 doubles -> each half-warp of a 64-bit fragment load hits 16 distinct bank pairs
 constexpr int kLdB = kNB + 4;           // Bs[n][k]: ld = 4 mod 16 doubles
 
 __global__ void __launch_bounds__(256) gemm_kernel(int M, int N, int K, const double* __restrict__ Ap, const double* __restrict__ Bp,
@@ -535,43 +538,189 @@ __global__ void __launch_bounds__(256) gemm_kernel(int M, int N, int K, const do
         }
 }
 
+// ---- helpers of the outer-blocked factorisation (large n) ----------------------------------------------
+// Interchanges of columns [k0, k0+jb) applied to the columns [col_begin, col_end) of A (one thread per column) and,
+// by the blocks beyond n_mat_blocks, to the right-hand sides.  npiv <= kOuter.
+constexpr int kOuter = 256;      // outer block width = K of the big trailing update
+__global__ void __launch_bounds__(256) laswp_kernel(int k0, int npiv, double* __restrict__ A, int lda, const int* __restrict__ ipiv,
+                                                    int col_begin, int col_end, int n_mat_blocks,
+                                                    double* __restrict__ B, int ldb, int nrhs) {
+    __shared__ int piv[kOuter];
+    const int tid = threadIdx.x;
+    if (tid < npiv) piv[tid] = ipiv[k0 + tid];
+    __syncthreads();
+    const bool on_rhs = (int)blockIdx.x >= n_mat_blocks;
+    const int c = on_rhs ? ((int)blockIdx.x - n_mat_blocks) * 256 + tid : col_begin + blockIdx.x * 256 + tid;
+    if (c >= (on_rhs ? nrhs : col_end)) return;
+    double* col = on_rhs ? B + (long long)c * ldb : A + (long long)c * lda;
+    for (int j = 0; j < npiv; ++j) {
+        const int p = piv[j];
+        if (p != k0 + j) { const double t = col[k0 + j]; col[k0 + j] = col[p]; col[p] = t; }
+    }
+}
+
+// ---- big trailing update: C[M x N] -= Ap[M x K] * Bp[K x N] for K up to kOuter --------------------------
+// 128 x 128 CTA tile, 8 warps of 64 x 32, K streamed in chunks of 16 through a 3-stage cp.async ring (8-byte copies: the
+// leading dimension n is odd more often than not, so columns are only 8-byte aligned); accumulators in registers.
+// C is never loaded by the SM: the epilogue sends -(A B) to the L2 as fire-and-forget FP64 reductions (RED.ADD.F64).
+// Every element receives exactly one reduction per launch, so the result is the correctly rounded C - A B, bit for bit
+// what a load / subtract / store epilogue gives -- but no warp ever waits for C (ncu on the load-modify-store variants:
+// 37-60 % of the CTA's lifetime went into waiting for the 128 KB C tile with one CTA per SM).
+constexpr int kBM = 128, kBN = 128, kBK = 32, kBStages = 3;
+constexpr int kBTilesPerCta = 1;
+constexpr int kBLdA = kBM + 4;               // As[k][m], ld = 4 mod 16 doubles (conflict-free per half-warp)
+constexpr int kBLdB = kBK + 4;               // Bs[n][k]
+constexpr int kBStageDoubles = kBK * kBLdA + kBN * kBLdB;
+constexpr size_t kBigGemmSmem = (size_t)kBStages * kBStageDoubles * sizeof(double);
+
+__device__ __forceinline__ void cp_async8(double* dst, const double* src, bool valid) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+    const int bytes = valid ? 8 : 0;              // src-size 0 -> the 8 destination bytes are zero-filled
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(src), "r"(bytes) : "memory");
+}
+
+__global__ void __launch_bounds__(256, 1) gemm_big_kernel(int M, int N, int K, const double* __restrict__ Ap,
+                                                          const double* __restrict__ Bp, double* __restrict__ C, int lda, int tiles_per_cta) {
+    extern __shared__ double smem_big[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nchunks = (K + kBK - 1) / kBK;
+    // this CTA owns tiles_per_cta consecutive tiles (m fastest) and streams their K chunks through ONE continuous
+    // cp.async ring, so the first chunks of the next tile are already in flight while the current tile's reductions
+    // leave the SM.  Not fully persistent on purpose: CTAs that retire every few hundred microseconds are what lets
+    // the look-ahead panel (a 16-SM cluster on the high-priority stream) get its SMs.
+    const int tiles_m = (M + kBM - 1) / kBM, tiles_n = (N + kBN - 1) / kBN;
+    const int ntiles = tiles_m * tiles_n;
+    const int first_tile = (int)blockIdx.x * tiles_per_cta;
+    const int my_tiles = min(tiles_per_cta, ntiles - first_tile);
+    const int total = my_tiles * nchunks;
+
+    // producer cursor (tile, chunk) of the next stage_load
+    int p_m0 = (first_tile % tiles_m) * kBM, p_n0 = (first_tile / tiles_m) * kBN, p_tile = first_tile, p_chunk = 0;
+    auto stage_load = [&](int slot) {
+        double* As = smem_big + (size_t)slot * kBStageDoubles;
+        double* Bs = As + kBK * kBLdA;
+        const int kc = p_chunk * kBK;
+        // A chunk: 16 columns (k) x 128 rows (m), m contiguous in memory
+#pragma unroll
+        for (int t = 0; t < kBK * kBM / 256; ++t) {
+            const int e = tid + 256 * t;
+            const int k = e / kBM, m = e % kBM;
+            const bool ok = (kc + k < K) && (p_m0 + m < M);
+            cp_async8(As + k * kBLdA + m, ok ? Ap + (long long)(kc + k) * lda + p_m0 + m : Ap, ok);
+        }
+        // B chunk: 128 columns (n) x 16 rows (k), k contiguous in memory
+#pragma unroll
+        for (int t = 0; t < kBN * kBK / 256; ++t) {
+            const int e = tid + 256 * t;
+            const int nn = e / kBK, k = e % kBK;
+            const bool ok = (kc + k < K) && (p_n0 + nn < N);
+            cp_async8(Bs + nn * kBLdB + k, ok ? Bp + (long long)(p_n0 + nn) * lda + kc + k : Bp, ok);
+        }
+        if (++p_chunk == nchunks) {
+            p_chunk = 0;
+            p_tile += 1;
+            p_m0 = (p_tile % tiles_m) * kBM;
+            p_n0 = (p_tile / tiles_m) * kBN;
+        }
+    };
+
+    // 8 warps: 2 along M (64 rows) x 4 along N (32 columns); warp tile = 8 x 4 m8n8 tiles
+    constexpr int TI = 8;
+    const int wm = (warp & 1) * 64, wn = (warp >> 1) * 32;
+    const int r = lane >> 2, q = lane & 3;
+    double acc[TI][4][2];
+#pragma unroll
+    for (int st = 0; st < kBStages - 1; ++st) {
+        if (st < total) stage_load(st);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+#pragma unroll
+    for (int i = 0; i < TI; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    int c_tile = first_tile, c_chunk = 0, slot = 0;
+    for (int g = 0; g < total; ++g) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(kBStages - 2) : "memory");
+        __syncthreads();
+        // prefetch chunk g + stages - 1 into the slot that was consumed at iteration g - 1
+        if (g + kBStages - 1 < total) stage_load(slot == 0 ? kBStages - 1 : slot - 1);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        const double* As = smem_big + (size_t)slot * kBStageDoubles;
+        const double* Bs = As + kBK * kBLdA;
+#pragma unroll
+        for (int ks = 0; ks < kBK; ks += 4) {
+            double a[TI], b[4];
+#pragma unroll
+            for (int i = 0; i < TI; ++i) a[i] = As[(ks + q) * kBLdA + wm + 8 * i + r];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = Bs[(wn + 8 * j + r) * kBLdB + ks + q];
+#pragma unroll
+            for (int i = 0; i < TI; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
+        if (++slot == kBStages) slot = 0;
+        if (++c_chunk == nchunks) {                  // tile finished: C -= acc as reductions, restart the accumulators
+            const int m0 = (c_tile % tiles_m) * kBM, n0 = (c_tile / tiles_m) * kBN;
+#pragma unroll
+            for (int i = 0; i < TI; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int gm = m0 + wm + 8 * i + r;
+                    const int gn = n0 + wn + 8 * j + 2 * q;
+                    if (gm < M && gn < N) atomicAdd(C + (long long)gn * lda + gm, -acc[i][j][0]);
+                    if (gm < M && gn + 1 < N) atomicAdd(C + (long long)(gn + 1) * lda + gm, -acc[i][j][1]);
+                    acc[i][j][0] = acc[i][j][1] = 0.0;
+                }
+            c_chunk = 0;
+            c_tile += 1;
+        }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
 // ---- triangular solves with the blocked factors (one CTA; panel-by-panel) --------------------------------
 __global__ void __launch_bounds__(1024) apply_kernel(int n, const double* __restrict__ LU, int lda, const int* __restrict__ ipiv,
-                                                      double* __restrict__ b, int nrhs, int ldb, int cluster,
-                                                      unsigned long long smem_cap) {
+                                                      double* __restrict__ b, int nrhs, int ldb, int outer) {
     __shared__ double xs[kNB];
     __shared__ double D[kNB][kNB + 1];
     const int tid = threadIdx.x, nt = blockDim.x;
     for (int r = 0; r < nrhs; ++r) {
         double* x = b + (long long)r * ldb;
-        // forward: P, L  (same panel schedule as the factorisation)
-        for (int k0 = 0, jb = 0; k0 < n; k0 += jb) {
-            jb = panel_width_hd(n, k0, cluster, smem_cap);
+        // forward: P, L  (same schedule as the factorisation: interchanges are replayed per outer block -- which is
+        // one kNB panel unless the outer-blocked path factored the matrix -- then the block's panels are solved)
+        const int ob = outer > 0 ? outer : kNB;
+        for (int K0 = 0; K0 < n; K0 += ob) {
+            const int W = min(ob, n - K0);
             __syncthreads();
-            for (int e = tid; e < jb * jb; e += nt) {
-                const int c = e / jb, i = e - c * jb;
-                D[i][c] = LU[(long long)(k0 + c) * lda + k0 + i];
-            }
             if (tid == 0) {
-                for (int j = 0; j < jb; ++j) {
-                    const int p = ipiv[k0 + j];
-                    if (p != k0 + j) { const double t = x[k0 + j]; x[k0 + j] = x[p]; x[p] = t; }
+                for (int j = 0; j < W; ++j) {
+                    const int p = ipiv[K0 + j];
+                    if (p != K0 + j) { const double t = x[K0 + j]; x[K0 + j] = x[p]; x[p] = t; }
                 }
             }
-            __syncthreads();
-            if (tid < 32) {
-                double v = (tid < jb) ? x[k0 + tid] : 0.0;
-                for (int c = 0; c < jb; ++c) {
-                    const double xc = __shfl_sync(0xffffffffu, v, c);
-                    if (tid > c && tid < jb) v = fma(-D[tid][c], xc, v);
+            for (int k0 = K0; k0 < K0 + W; k0 += kNB) {
+                const int jb = min(kNB, K0 + W - k0);
+                __syncthreads();
+                for (int e = tid; e < jb * jb; e += nt) {
+                    const int c = e / jb, i = e - c * jb;
+                    D[i][c] = LU[(long long)(k0 + c) * lda + k0 + i];
                 }
-                if (tid < jb) { xs[tid] = v; x[k0 + tid] = v; }
-            }
-            __syncthreads();
-            for (int i = k0 + jb + tid; i < n; i += nt) {
-                double v = x[i];
-                for (int c = 0; c < jb; ++c) v = fma(-LU[(long long)(k0 + c) * lda + i], xs[c], v);
-                x[i] = v;
+                __syncthreads();
+                if (tid < 32) {
+                    double v = (tid < jb) ? x[k0 + tid] : 0.0;
+                    for (int c = 0; c < jb; ++c) {
+                        const double xc = __shfl_sync(0xffffffffu, v, c);
+                        if (tid > c && tid < jb) v = fma(-D[tid][c], xc, v);
+                    }
+                    if (tid < jb) { xs[tid] = v; x[k0 + tid] = v; }
+                }
+                __syncthreads();
+                for (int i = k0 + jb + tid; i < n; i += nt) {
+                    double v = x[i];
+                    for (int c = 0; c < jb; ++c) v = fma(-LU[(long long)(k0 + c) * lda + i], xs[c], v);
+                    x[i] = v;
+                }
             }
         }
         // backward: U
@@ -705,8 +854,8 @@ LookAhead& look_ahead() {
     return la;
 }
 
-void launch_gemm(int n, int k0, int jb, int col_begin, int col_end, double* A, int lda, cudaStream_t s) {
-    const int M = n - k0 - jb, N = col_end - col_begin;
+void launch_gemm(int n, int k0, int jb, int col_begin, int col_end, double* A, int lda, cudaStream_t s, int row_end = -1) {
+    const int M = (row_end < 0 ? n : row_end) - k0 - jb, N = col_end - col_begin;
     if (M <= 0 || N <= 0) return;
     dim3 grid((M + kGM - 1) / kGM, (N + kGN - 1) / kGN);
     gemm_kernel<<<grid, 256, 0, s>>>(M, N, jb, A + (long long)k0 * lda + k0 + jb, A + (long long)col_begin * lda + k0,
@@ -717,7 +866,11 @@ void launch_gemm(int n, int k0, int jb, int col_begin, int col_end, double* A, i
 // Right-looking blocked LU with one-panel look-ahead: as soon as the columns of panel k+1 have received the update of
 // panel k, panel k+1 is factored on a high-priority side stream (a 16-SM cluster) while the main stream finishes the
 // trailing update of panel k on the rest of the matrix.
+int factor_outer(int n, double* A, int lda, int* ipiv, int* info, double* B, int nrhs, int ldb, cudaStream_t s);
+int outer_width(int n);
+
 int factor_blocked(int n, double* A, int lda, int* ipiv, int* info, double* B, int nrhs, int ldb, cudaStream_t s) {
+    if (outer_width(n) > 0) return factor_outer(n, A, lda, ipiv, info, B, nrhs, ldb, s);
     zero_info_kernel<<<1, 1, 0, s>>>(info);
     GPB_LAUNCH_CHECK();
     LookAhead& la = look_ahead();
@@ -741,7 +894,7 @@ int factor_blocked(int n, double* A, int lda, int* ipiv, int* info, double* B, i
         const int nright = n - k1;
         const int mat_blocks = (nright + 63) / 64;
         if (mat_blocks + rhs_blocks > 0) {
-            swap_trsm_kernel<<<mat_blocks + rhs_blocks, 256, 0, s>>>(n, k0, jb, A, lda, ipiv, mat_blocks, B, ldb, nrhs);
+            swap_trsm_kernel<<<mat_blocks + rhs_blocks, 256, 0, s>>>(n, k0, jb, A, lda, ipiv, mat_blocks, B, ldb, nrhs, k1, n, 1);
             GPB_LAUNCH_CHECK();
         }
         if (jb1 > 0) {
@@ -761,6 +914,125 @@ int factor_blocked(int n, double* A, int lda, int* ipiv, int* info, double* B, i
         k0 = k1;
     }
     if (ahead) {                                     // nothing of the side stream may outlive the call on s
+        GPB_CHECK_CUDA(cudaEventRecord(la.panel_done, ps));
+        GPB_CHECK_CUDA(cudaStreamWaitEvent(s, la.panel_done, 0));
+    }
+    GPB_CHECK_CUDA(cudaGetLastError());
+    return GPB_OK;
+}
+
+// ---- outer-blocked variant for large n ----------------------------------------------------------------------
+// With kNB-wide updates every panel reads and writes the whole trailing matrix: n^3/6 bytes in total, 1.1 s of HBM time at
+// n = 35 000.  Above outer_min_n() the matrix is factored in outer blocks of kOuter columns: the block's own columns are
+// factored panel by panel (interchanges LAPACK-style inside the block, so its L is in one row order), and the rest of
+// the matrix sees ONE update per block with K = kOuter (gemm_big_kernel) -- 4x less traffic, compute bound.  The next
+// block is factored on the side stream while the main stream finishes the big update (same look-ahead as above).
+int g_outer_min_n = -1;
+int outer_min_n() {
+    if (g_outer_min_n < 0) {
+        const char* e = getenv("GPB_LU_OUTER_MIN_N");
+        g_outer_min_n = e ? atoi(e) : 12288;
+    }
+    return g_outer_min_n;
+}
+int outer_width(int n) { return (n > kSmallN && n >= outer_min_n()) ? kOuter : 0; }
+
+int launch_big_gemm(int n, int K0, int W, int col_begin, int col_end, double* A, int lda, cudaStream_t s) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        GPB_CHECK_CUDA(cudaFuncSetAttribute(gemm_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBigGemmSmem));
+        GPB_CHECK_CUDA(cudaFuncSetAttribute(gemm_big_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        attr_set = true;
+    }
+    const int K1 = K0 + W;
+    const int M = n - K1, N = col_end - col_begin;
+    if (M <= 0 || N <= 0) return GPB_OK;
+    const int ntiles = ((M + kBM - 1) / kBM) * ((N + kBN - 1) / kBN);
+    static const int tiles_per_cta = [] { const char* e = getenv("GPB_LU_GEMM_TILES"); const int v = e ? atoi(e) : kBTilesPerCta; return v > 0 ? v : 1; }();
+    const int grid = (ntiles + tiles_per_cta - 1) / tiles_per_cta;
+    gemm_big_kernel<<<grid, 256, kBigGemmSmem, s>>>(M, N, W, A + (long long)K0 * lda + K1, A + (long long)col_begin * lda + K0,
+                                                    A + (long long)col_begin * lda + K1, lda, tiles_per_cta);
+    GPB_LAUNCH_CHECK();
+    return GPB_OK;
+}
+
+// columns [K0, K0+W): panel by panel, updates confined to the block's own columns
+int factor_outer_panel(int n, int K0, int W, double* A, int lda, int* ipiv, int* info, cudaStream_t q) {
+    for (int k0 = K0; k0 < K0 + W; k0 += kNB) {
+        const int jb = min(kNB, K0 + W - k0);
+        const int k1 = k0 + jb;
+        int rc = launch_panel(n, k0, jb, A, lda, ipiv, info, q);
+        if (rc) return rc;
+        if (k0 > K0) {                               // earlier columns of the block follow the interchanges
+            laswp_kernel<<<1, 256, 0, q>>>(k0, jb, A, lda, ipiv, K0, k0, 1, nullptr, 0, 0);
+            GPB_LAUNCH_CHECK();
+        }
+        if (k1 < K0 + W) {
+            const int nb = (K0 + W - k1 + 63) / 64;
+            swap_trsm_kernel<<<nb, 256, 0, q>>>(n, k0, jb, A, lda, ipiv, nb, nullptr, 0, 0, k1, K0 + W, 1);
+            GPB_LAUNCH_CHECK();
+            launch_gemm(n, k0, jb, k1, K0 + W, A, lda, q);
+        }
+    }
+    return GPB_OK;
+}
+
+int factor_outer(int n, double* A, int lda, int* ipiv, int* info, double* B, int nrhs, int ldb, cudaStream_t s) {
+    zero_info_kernel<<<1, 1, 0, s>>>(info);
+    GPB_LAUNCH_CHECK();
+    LookAhead& la = look_ahead();
+    const bool ahead = la.ok;
+    cudaStream_t ps = ahead ? la.panel_stream : s;
+    if (ahead) {
+        GPB_CHECK_CUDA(cudaEventRecord(la.ready, s));
+        GPB_CHECK_CUDA(cudaStreamWaitEvent(ps, la.ready, 0));
+    }
+    int rc = factor_outer_panel(n, 0, min(kOuter, n), A, lda, ipiv, info, ps);
+    if (rc) return rc;
+    for (int K0 = 0; K0 < n;) {
+        const int W = min(kOuter, n - K0);
+        const int K1 = K0 + W;
+        const int W1 = (K1 < n) ? min(kOuter, n - K1) : 0;
+        if (ahead) {
+            GPB_CHECK_CUDA(cudaEventRecord(la.panel_done, ps));
+            GPB_CHECK_CUDA(cudaStreamWaitEvent(s, la.panel_done, 0));
+        }
+        const int nright = n - K1;
+        {   // all interchanges of the block on the columns right of it and on the right-hand sides
+            const int mb = (nright + 255) / 256, rb = (B != nullptr) ? (nrhs + 255) / 256 : 0;
+            if (mb + rb > 0) {
+                laswp_kernel<<<mb + rb, 256, 0, s>>>(K0, W, A, lda, ipiv, K1, n, mb, B, ldb, nrhs);
+                GPB_LAUNCH_CHECK();
+            }
+        }
+        // U12 = L11^-1 A12 for the kOuter x kOuter unit-lower L11, panel by panel
+        const int mat_blocks = (nright + 63) / 64;
+        const int rhs_blocks = (B != nullptr) ? (nrhs + 63) / 64 : 0;
+        for (int k0 = K0; k0 < K1; k0 += kNB) {
+            const int jb = min(kNB, K1 - k0);
+            const int k1 = k0 + jb;
+            if (mat_blocks + rhs_blocks > 0) {
+                swap_trsm_kernel<<<mat_blocks + rhs_blocks, 256, 0, s>>>(n, k0, jb, A, lda, ipiv, mat_blocks, B, ldb, nrhs, K1, n, 0);
+                GPB_LAUNCH_CHECK();
+            }
+            if (k1 < K1 && nright > 0) launch_gemm(n, k0, jb, K1, n, A, lda, s, K1);
+            if (B != nullptr && k1 < n) {
+                rhs_update_kernel<<<(n - k1 + 255) / 256, 256, 0, s>>>(n, k0, jb, A, lda, B, ldb, nrhs);
+                GPB_LAUNCH_CHECK();
+            }
+        }
+        if (W1 > 0) {
+            if ((rc = launch_big_gemm(n, K0, W, K1, K1 + W1, A, lda, s))) return rc;
+            if (ahead) {
+                GPB_CHECK_CUDA(cudaEventRecord(la.ready, s));
+                GPB_CHECK_CUDA(cudaStreamWaitEvent(ps, la.ready, 0));
+            }
+            if ((rc = factor_outer_panel(n, K1, W1, A, lda, ipiv, info, ps))) return rc;
+            if ((rc = launch_big_gemm(n, K0, W, K1 + W1, n, A, lda, s))) return rc;
+        }
+        K0 = K1;
+    }
+    if (ahead) {
         GPB_CHECK_CUDA(cudaEventRecord(la.panel_done, ps));
         GPB_CHECK_CUDA(cudaStreamWaitEvent(s, la.panel_done, 0));
     }
@@ -796,6 +1068,12 @@ int small_path(int n, double* A, int lda, double* b, int nrhs, int ldb, int* ipi
 
 }  // namespace
 
+extern "C" int gpb_lu_set_outer_min_n(int min_n) {
+    const int prev = outer_min_n();
+    if (min_n >= 0) g_outer_min_n = min_n;
+    return prev;
+}
+
 extern "C" int gpb_lu_factor(int n, double* A, int lda, int* ipiv, int* info, void* stream) {
     GPB_REQUIRE(n > 0 && A && ipiv && lda >= n, "bad arguments");
     if (n <= kSmallN) return small_path(n, A, lda, nullptr, 0, 0, ipiv, info, 0, (cudaStream_t)stream);
@@ -804,9 +1082,7 @@ extern "C" int gpb_lu_factor(int n, double* A, int lda, int* ipiv, int* info, vo
 
 extern "C" int gpb_lu_apply(int n, const double* LU, int lda, const int* ipiv, double* b, int nrhs, int ldb, void* stream) {
     GPB_REQUIRE(n > 0 && LU && ipiv && b && lda >= n && ldb >= n && nrhs >= 1, "bad arguments");
-    const PanelConfig& cfg = panel_config();
-    apply_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(n, LU, lda, ipiv, b, nrhs, ldb, cfg.cluster,
-                                                       (unsigned long long)cfg.smem_cap);
+    apply_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(n, LU, lda, ipiv, b, nrhs, ldb, outer_width(n));
     GPB_LAUNCH_CHECK();
     return GPB_OK;
 }

@@ -32,8 +32,12 @@ def main():
     ap.add_argument("--sp-per-surface", type=int, default=1000)
     ap.add_argument("--n-ori", type=int, default=1000)
     ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--outer-min-n", type=int, default=-1, help="force the outer-blocked schedule from this n on")
+    ap.add_argument("--skip-cusolver", action="store_true")
     args = ap.parse_args()
     eng = gc.B200Engine(0)
+    if args.outer_min_n >= 0:
+        eng.lib.gpb_lu_set_outer_min_n(args.outer_min_n)
     m = ex.synthetic_stress(n_sp_per_surface=args.sp_per_surface, n_surfaces=4, n_ori=args.n_ori, resolution=(4, 4, 4))
     ii, opt, desc = m.args()
     st = gc.StackTables(ii, desc, 0, opt.kernel_options, eng.device)
@@ -53,6 +57,9 @@ def main():
     def clone_only():
         A0.clone(); b0.clone()
 
+    if args.skip_cusolver:
+        def cusolver():
+            out["w_ref"] = out["w"]
     for f in (ours, cusolver, clone_only):
         f()
     t_ours = timed(ours, args.reps)
@@ -62,7 +69,7 @@ def main():
     r = (A0 @ w - b0).abs().max().item()
     r_ref = (A0 @ w_ref - b0).abs().max().item()
     flops = 2.0 / 3.0 * n ** 3
-    print(json.dumps({"n": n, "gpb_lu_solve_ms": t_ours[0] - t_clone[0], "cusolver_getrf_getrs_ms": t_cus[0],
+    print(json.dumps({"n": n, "outer_min_n": int(eng.lib.gpb_lu_set_outer_min_n(-1)), "gpb_lu_solve_ms": t_ours[0] - t_clone[0], "cusolver_getrf_getrs_ms": t_cus[0],
                       "clone_ms": t_clone[0], "gpb_tflops": flops / ((t_ours[0] - t_clone[0]) * 1e-3) / 1e12,
                       "cusolver_tflops": flops / (t_cus[0] * 1e-3) / 1e12, "residual_ours": r, "residual_cusolver": r_ref,
                       "max_rel_diff_weights": ((w - w_ref).abs().max() / w_ref.abs().max()).item()}))

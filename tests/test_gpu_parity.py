@@ -118,6 +118,39 @@ def test_lu_factor_apply_consistent(eng):
     assert (piv >= np.arange(n)).all() and (piv < n).all()
 
 
+@pytest.mark.parametrize("n", [161, 200, 257, 500, 777, 1000, 2049])
+def test_lu_outer_blocked_path(eng, n):
+    """The large-n schedule (outer blocks of 128 columns, one K = 128 DMMA update per block, interchanges LAPACK-style
+    inside a block) forced onto small systems: solve with the right-hand side carried along, and factor + apply."""
+    prev = eng.lib.gpb_lu_set_outer_min_n(161)
+    try:
+        rng = np.random.default_rng(n)
+        A = rng.standard_normal((n, n)) + 0.1 * np.eye(n)
+        B = rng.standard_normal((n, 3))
+        x_ref = np.linalg.solve(A, B)
+        cond = np.linalg.cond(A)
+        Ad = torch.as_tensor(A.T.copy(), device=eng.device)
+        x = eng.solve(Ad, torch.as_tensor(B[:, 0].copy(), device=eng.device)).cpu().numpy()
+        res = np.abs(A @ x - B[:, 0]).max() / (np.abs(A).max() * np.abs(x).max() * n * np.finfo(float).eps)
+        assert res < 50, f"scaled residual {res}"
+        assert np.abs(x - x_ref[:, 0]).max() <= 1e-13 * cond * np.abs(x_ref).max()
+        Ad = torch.as_tensor(A.T.copy(), device=eng.device)
+        ipiv = eng.empty(n, dtype=torch.int32)
+        info = torch.zeros(1, dtype=torch.int32, device=eng.device)
+        _lib.check(eng.lib.gpb_lu_factor(n, Ad.data_ptr(), n, ipiv.data_ptr(), info.data_ptr(), eng.stream))
+        Bd = torch.as_tensor(B.T.copy(), device=eng.device)
+        _lib.check(eng.lib.gpb_lu_apply(n, Ad.data_ptr(), n, ipiv.data_ptr(), Bd.data_ptr(), 3, n, eng.stream))
+        X = Bd.cpu().numpy().T
+        assert int(info.item()) == 0
+        assert np.abs(X - x_ref).max() <= 1e-13 * cond * np.abs(x_ref).max()
+        # P A = L U with the block-LAPACK / across-block-LINPACK storage is what apply replays; the pivots are those of
+        # partial pivoting (same as LAPACK up to ties)
+        piv = ipiv.cpu().numpy()
+        assert (piv >= np.arange(n)).all() and (piv < n).all()
+    finally:
+        eng.lib.gpb_lu_set_outer_min_n(prev)
+
+
 def test_lu_reports_singular(eng):
     n = 40
     A = np.zeros((n, n))
