@@ -52,6 +52,7 @@ SIGNATURES = {
     "gpb_assemble_cov": (C.c_int, [C.POINTER(GpbStack), _P, C.c_int, _P, _P]),
     "gpb_lu_solve": (C.c_int, [C.c_int, _P, C.c_int, _P, C.c_int, C.c_int, _P, _P, _P]),
     "gpb_lu_set_outer_min_n": (C.c_int, [C.c_int]),
+    "gpb_lu_set_outer_width": (C.c_int, [C.c_int]),
     "gpb_lu_factor": (C.c_int, [C.c_int, _P, C.c_int, _P, _P, _P]),
     "gpb_lu_apply": (C.c_int, [C.c_int, _P, C.c_int, _P, _P, C.c_int, C.c_int, _P]),
     "gpb_eval_table_doubles": (_LL, [C.POINTER(GpbStack)]),

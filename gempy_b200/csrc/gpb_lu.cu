@@ -11,6 +11,8 @@
 //     gemm_kernel    A22 -= L21 * U12 on the FP64 tensor cores (mma.sync m8n8k4 DMMA) -- the one dense contraction
 //   Interchanges are applied LAPACK-style inside a panel and LINPACK-style across panels (columns left of a
 //   panel are never permuted); gpb_lu_apply replays them panel by panel, so factor + apply are self-consistent.
+//   n >= 10240: outer blocks of 256 columns (factor_outer): the block is factored panel by panel on the side stream,
+//   the rest of the matrix gets one K = 256 DMMA update per block (gemm_big_kernel, C updated by L2 reductions).
 #include "gpb_common.cuh"
 #include <cooperative_groups.h>
 
@@ -391,10 +393,17 @@ __global__ void __launch_bounds__(256) swap_trsm_kernel(int n, int k0, int jb, d
         T[c][i] = M[(long long)(c0 + c) * ldm + k0 + i];
     }
     __syncthreads();
-    if (tid < ncol) {
+    // forward substitution with four threads per column: thread (c, part) owns rows i = part, part + 4, ... of column c;
+    // after step k the value T[c][k] is final.  (One thread per column took 22 us per call -- 496 dependent
+    // shared-memory FMAs -- and sat on the critical path of every panel.)
+    {
+        const int c = tid >> 2, part = tid & 3;
         for (int k = 0; k < jb; ++k) {
-            const double xk = T[tid][k];
-            for (int i = k + 1; i < jb; ++i) T[tid][i] = fma(-L[i][k], xk, T[tid][i]);
+            if (c < ncol) {
+                const double xk = T[c][k];
+                for (int i = k + 1 + part; i < jb; i += 4) T[c][i] = fma(-L[i][k], xk, T[c][i]);
+            }
+            __syncwarp();
         }
     }
     __syncthreads();
@@ -541,13 +550,13 @@ __global__ void __launch_bounds__(256) gemm_kernel(int M, int N, int K, const do
 // ---- helpers of the outer-blocked factorisation (large n) ----------------------------------------------
 // Interchanges of columns [k0, k0+jb) applied to the columns [col_begin, col_end) of A (one thread per column) and,
 // by the blocks beyond n_mat_blocks, to the right-hand sides.  npiv <= kOuter.
-constexpr int kOuter = 256;      // outer block width = K of the big trailing update
+constexpr int kOuter = 256;      // outer block width = K of the big trailing update (512 measured slower: 1.23 s vs 1.18 s at n = 35k)
 __global__ void __launch_bounds__(256) laswp_kernel(int k0, int npiv, double* __restrict__ A, int lda, const int* __restrict__ ipiv,
                                                     int col_begin, int col_end, int n_mat_blocks,
                                                     double* __restrict__ B, int ldb, int nrhs) {
     __shared__ int piv[kOuter];
     const int tid = threadIdx.x;
-    if (tid < npiv) piv[tid] = ipiv[k0 + tid];
+    for (int j = tid; j < npiv; j += 256) piv[j] = ipiv[k0 + j];
     __syncthreads();
     const bool on_rhs = (int)blockIdx.x >= n_mat_blocks;
     const int c = on_rhs ? ((int)blockIdx.x - n_mat_blocks) * 256 + tid : col_begin + blockIdx.x * 256 + tid;
@@ -560,14 +569,15 @@ __global__ void __launch_bounds__(256) laswp_kernel(int k0, int npiv, double* __
 }
 
 // ---- big trailing update: C[M x N] -= Ap[M x K] * Bp[K x N] for K up to kOuter --------------------------
-// 128 x 128 CTA tile, 8 warps of 64 x 32, K streamed in chunks of 16 through a 3-stage cp.async ring (8-byte copies: the
+// 128 x 64 CTA tile, 8 warps of 32 x 32, two CTAs per SM, K streamed in chunks of 16 through a 3-stage cp.async ring (8-byte copies: the
 // leading dimension n is odd more often than not, so columns are only 8-byte aligned); accumulators in registers.
 // C is never loaded by the SM: the epilogue sends -(A B) to the L2 as fire-and-forget FP64 reductions (RED.ADD.F64).
 // Every element receives exactly one reduction per launch, so the result is the correctly rounded C - A B, bit for bit
 // what a load / subtract / store epilogue gives -- but no warp ever waits for C (ncu on the load-modify-store variants:
 // 37-60 % of the CTA's lifetime went into waiting for the 128 KB C tile with one CTA per SM).
-constexpr int kBM = 128, kBN = 128, kBK = 32, kBStages = 3;
+constexpr int kBM = 128, kBN = 64, kBK = 32, kBStages = 2;
 constexpr int kBTilesPerCta = 1;
+constexpr int kBThreads = 256;
 constexpr int kBLdA = kBM + 4;               // As[k][m], ld = 4 mod 16 doubles (conflict-free per half-warp)
 constexpr int kBLdB = kBK + 4;               // Bs[n][k]
 constexpr int kBStageDoubles = kBK * kBLdA + kBN * kBLdB;
@@ -579,7 +589,7 @@ __device__ __forceinline__ void cp_async8(double* dst, const double* src, bool v
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(src), "r"(bytes) : "memory");
 }
 
-__global__ void __launch_bounds__(256, 1) gemm_big_kernel(int M, int N, int K, const double* __restrict__ Ap,
+__global__ void __launch_bounds__(kBThreads, 2) gemm_big_kernel(int M, int N, int K, const double* __restrict__ Ap,
                                                           const double* __restrict__ Bp, double* __restrict__ C, int lda, int tiles_per_cta) {
     extern __shared__ double smem_big[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -602,16 +612,16 @@ __global__ void __launch_bounds__(256, 1) gemm_big_kernel(int M, int N, int K, c
         const int kc = p_chunk * kBK;
         // A chunk: 16 columns (k) x 128 rows (m), m contiguous in memory
 #pragma unroll
-        for (int t = 0; t < kBK * kBM / 256; ++t) {
-            const int e = tid + 256 * t;
+        for (int t = 0; t < kBK * kBM / kBThreads; ++t) {
+            const int e = tid + kBThreads * t;
             const int k = e / kBM, m = e % kBM;
             const bool ok = (kc + k < K) && (p_m0 + m < M);
             cp_async8(As + k * kBLdA + m, ok ? Ap + (long long)(kc + k) * lda + p_m0 + m : Ap, ok);
         }
         // B chunk: 128 columns (n) x 16 rows (k), k contiguous in memory
 #pragma unroll
-        for (int t = 0; t < kBN * kBK / 256; ++t) {
-            const int e = tid + 256 * t;
+        for (int t = 0; t < kBN * kBK / kBThreads; ++t) {
+            const int e = tid + kBThreads * t;
             const int nn = e / kBK, k = e % kBK;
             const bool ok = (kc + k < K) && (p_n0 + nn < N);
             cp_async8(Bs + nn * kBLdB + k, ok ? Bp + (long long)(p_n0 + nn) * lda + kc + k : Bp, ok);
@@ -624,9 +634,10 @@ __global__ void __launch_bounds__(256, 1) gemm_big_kernel(int M, int N, int K, c
         }
     };
 
-    // 8 warps: 2 along M (64 rows) x 4 along N (32 columns); warp tile = 8 x 4 m8n8 tiles
-    constexpr int TI = 8;
-    const int wm = (warp & 1) * 64, wn = (warp >> 1) * 32;
+    // 8 warps: 4 along M x 2 along N, warp tile 32 x 32 = 4 x 4 m8n8 tiles; two CTAs per SM so that one CTA's
+    // reductions / first operand loads overlap the other's DMMA loop
+    constexpr int TI = 4;
+    const int wm = (warp & 3) * 32, wn = (warp >> 2) * 32;
     const int r = lane >> 2, q = lane & 3;
     double acc[TI][4][2];
 #pragma unroll
@@ -925,17 +936,22 @@ int factor_blocked(int n, double* A, int lda, int* ipiv, int* info, double* B, i
 // With kNB-wide updates every panel reads and writes the whole trailing matrix: n^3/6 bytes in total, 1.1 s of HBM time at
 // n = 35 000.  Above outer_min_n() the matrix is factored in outer blocks of kOuter columns: the block's own columns are
 // factored panel by panel (interchanges LAPACK-style inside the block, so its L is in one row order), and the rest of
-// the matrix sees ONE update per block with K = kOuter (gemm_big_kernel) -- 4x less traffic, compute bound.  The next
+// the matrix sees ONE update per block with K = kOuter (gemm_big_kernel) -- 8x less traffic, compute bound.  The next
 // block is factored on the side stream while the main stream finishes the big update (same look-ahead as above).
 int g_outer_min_n = -1;
 int outer_min_n() {
     if (g_outer_min_n < 0) {
         const char* e = getenv("GPB_LU_OUTER_MIN_N");
-        g_outer_min_n = e ? atoi(e) : 12288;
+        g_outer_min_n = e ? atoi(e) : 10240;
     }
     return g_outer_min_n;
 }
-int outer_width(int n) { return (n > kSmallN && n >= outer_min_n()) ? kOuter : 0; }
+int g_outer_width = 0;           // 0: by n
+int outer_width(int n) {
+    if (n <= kSmallN || n < outer_min_n()) return 0;
+    if (g_outer_width > 0) return g_outer_width;
+    return kOuter;
+}
 
 int launch_big_gemm(int n, int K0, int W, int col_begin, int col_end, double* A, int lda, cudaStream_t s) {
     static bool attr_set = false;
@@ -950,7 +966,7 @@ int launch_big_gemm(int n, int K0, int W, int col_begin, int col_end, double* A,
     const int ntiles = ((M + kBM - 1) / kBM) * ((N + kBN - 1) / kBN);
     static const int tiles_per_cta = [] { const char* e = getenv("GPB_LU_GEMM_TILES"); const int v = e ? atoi(e) : kBTilesPerCta; return v > 0 ? v : 1; }();
     const int grid = (ntiles + tiles_per_cta - 1) / tiles_per_cta;
-    gemm_big_kernel<<<grid, 256, kBigGemmSmem, s>>>(M, N, W, A + (long long)K0 * lda + K1, A + (long long)col_begin * lda + K0,
+    gemm_big_kernel<<<grid, kBThreads, kBigGemmSmem, s>>>(M, N, W, A + (long long)K0 * lda + K1, A + (long long)col_begin * lda + K0,
                                                     A + (long long)col_begin * lda + K1, lda, tiles_per_cta);
     GPB_LAUNCH_CHECK();
     return GPB_OK;
@@ -964,7 +980,8 @@ int factor_outer_panel(int n, int K0, int W, double* A, int lda, int* ipiv, int*
         int rc = launch_panel(n, k0, jb, A, lda, ipiv, info, q);
         if (rc) return rc;
         if (k0 > K0) {                               // earlier columns of the block follow the interchanges
-            laswp_kernel<<<1, 256, 0, q>>>(k0, jb, A, lda, ipiv, K0, k0, 1, nullptr, 0, 0);
+            const int lb = (k0 - K0 + 255) / 256;
+            laswp_kernel<<<lb, 256, 0, q>>>(k0, jb, A, lda, ipiv, K0, k0, lb, nullptr, 0, 0);
             GPB_LAUNCH_CHECK();
         }
         if (k1 < K0 + W) {
@@ -987,12 +1004,13 @@ int factor_outer(int n, double* A, int lda, int* ipiv, int* info, double* B, int
         GPB_CHECK_CUDA(cudaEventRecord(la.ready, s));
         GPB_CHECK_CUDA(cudaStreamWaitEvent(ps, la.ready, 0));
     }
-    int rc = factor_outer_panel(n, 0, min(kOuter, n), A, lda, ipiv, info, ps);
+    const int ow = outer_width(n);
+    int rc = factor_outer_panel(n, 0, min(ow, n), A, lda, ipiv, info, ps);
     if (rc) return rc;
     for (int K0 = 0; K0 < n;) {
-        const int W = min(kOuter, n - K0);
+        const int W = min(ow, n - K0);
         const int K1 = K0 + W;
-        const int W1 = (K1 < n) ? min(kOuter, n - K1) : 0;
+        const int W1 = (K1 < n) ? min(ow, n - K1) : 0;
         if (ahead) {
             GPB_CHECK_CUDA(cudaEventRecord(la.panel_done, ps));
             GPB_CHECK_CUDA(cudaStreamWaitEvent(s, la.panel_done, 0));
@@ -1071,6 +1089,12 @@ int small_path(int n, double* A, int lda, double* b, int nrhs, int ldb, int* ipi
 extern "C" int gpb_lu_set_outer_min_n(int min_n) {
     const int prev = outer_min_n();
     if (min_n >= 0) g_outer_min_n = min_n;
+    return prev;
+}
+
+extern "C" int gpb_lu_set_outer_width(int width) {
+    const int prev = g_outer_width;
+    if (width == 0 || width == kOuter / 2 || width == kOuter) g_outer_width = width;
     return prev;
 }
 

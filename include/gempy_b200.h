@@ -102,11 +102,14 @@ int gpb_assemble_cov(const gpb_stack* st, double* A, int lda, double* b, void* s
  * solves.  A is overwritten with L\U, b (n x nrhs, ldb) with the solution, ipiv (n ints) with the pivot rows.
  * `info` (device int, may be NULL) receives 0 or the 1-based index of a zero pivot. */
 int gpb_lu_solve(int n, double* A, int lda, double* b, int nrhs, int ldb, int* ipiv, int* info, void* stream);
-/* Systems with n >= min_n are factored in outer blocks of 128 columns (one K = 128 trailing update per block instead
- * of four K = 32 ones: 4x less HBM traffic, which is what bounds the solve for n in the tens of thousands).  Default
- * 12288 (or the environment variable GPB_LU_OUTER_MIN_N).  Returns the previous value; min_n < 0 only queries.
+/* Systems with n >= min_n are factored in outer blocks of 256 columns (one K = 256 trailing update per block instead
+ * of eight K = 32 ones: 8x less HBM traffic, which is what bounds the solve for n in the tens of thousands).  Default
+ * 10240 (or the environment variable GPB_LU_OUTER_MIN_N).  Returns the previous value; min_n < 0 only queries.
  * A factorisation and the gpb_lu_apply calls that use it must run under the same setting. (host) */
 int gpb_lu_set_outer_min_n(int min_n);
+/* Outer block width of that schedule: 0 = default (256), or 128 / 256 to force it (tests, tuning); other values are
+ * ignored.  Returns the previous setting. (host) */
+int gpb_lu_set_outer_width(int width);
 /* Factor only / solve only (weight reuse across octree levels, timing against cusolverDnDgetrf/Dgetrs). */
 int gpb_lu_factor(int n, double* A, int lda, int* ipiv, int* info, void* stream);
 int gpb_lu_apply(int n, const double* LU, int lda, const int* ipiv, double* b, int nrhs, int ldb, void* stream);

@@ -34,8 +34,10 @@ def main():
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--outer-min-n", type=int, default=-1, help="force the outer-blocked schedule from this n on")
     ap.add_argument("--skip-cusolver", action="store_true")
+    ap.add_argument("--outer-width", type=int, default=0)
     args = ap.parse_args()
     eng = gc.B200Engine(0)
+    eng.lib.gpb_lu_set_outer_width(args.outer_width)
     if args.outer_min_n >= 0:
         eng.lib.gpb_lu_set_outer_min_n(args.outer_min_n)
     m = ex.synthetic_stress(n_sp_per_surface=args.sp_per_surface, n_surfaces=4, n_ori=args.n_ori, resolution=(4, 4, 4))

@@ -118,11 +118,13 @@ def test_lu_factor_apply_consistent(eng):
     assert (piv >= np.arange(n)).all() and (piv < n).all()
 
 
+@pytest.mark.parametrize("width", [128, 256])
 @pytest.mark.parametrize("n", [161, 200, 257, 500, 777, 1000, 2049])
-def test_lu_outer_blocked_path(eng, n):
+def test_lu_outer_blocked_path(eng, n, width):
     """The large-n schedule (outer blocks of 128 columns, one K = 128 DMMA update per block, interchanges LAPACK-style
     inside a block) forced onto small systems: solve with the right-hand side carried along, and factor + apply."""
     prev = eng.lib.gpb_lu_set_outer_min_n(161)
+    prev_w = eng.lib.gpb_lu_set_outer_width(width)
     try:
         rng = np.random.default_rng(n)
         A = rng.standard_normal((n, n)) + 0.1 * np.eye(n)
@@ -149,6 +151,7 @@ def test_lu_outer_blocked_path(eng, n):
         assert (piv >= np.arange(n)).all() and (piv < n).all()
     finally:
         eng.lib.gpb_lu_set_outer_min_n(prev)
+        eng.lib.gpb_lu_set_outer_width(prev_w)
 
 
 def test_lu_reports_singular(eng):
