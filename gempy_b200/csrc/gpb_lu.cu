@@ -810,12 +810,9 @@ int panel_width(int n, int k0) {
     return panel_width_hd(n, k0, cfg.cluster, (unsigned long long)cfg.smem_cap);
 }
 
-bool panel_fits_cluster(int n, int k0, int jb) {
-    const PanelConfig& cfg = panel_config();
-    if (cfg.cluster == 0) return false;
-    const long long m = n - k0;
-    const long long R = (m + cfg.cluster - 1) / cfg.cluster;
-    return (size_t)(R + 2) * jb * sizeof(double) <= cfg.smem_cap;
+int panel_rows_cap() {
+    static const int v = [] { const char* e = getenv("GPB_LU_PANEL_ROWS_CAP"); return e ? atoi(e) : 256; }();
+    return v;
 }
 
 int launch_panel(int n, int k0, int jb, double* A, int lda, int* ipiv, int* info, cudaStream_t s) {
@@ -826,18 +823,22 @@ int launch_panel(int n, int k0, int jb, double* A, int lda, int* ipiv, int* info
         return GPB_OK;
     }
     const int m = n - k0;
-    int R = (m + cfg.cluster - 1) / cfg.cluster;
+    // short panels run on a smaller cluster (cheaper barrier per column) as long as a CTA keeps at most
+    // panel_rows_cap() rows
+    int cl = cfg.cluster;
+    while (cl > 2 && (m + cl / 2 - 1) / (cl / 2) <= panel_rows_cap()) cl /= 2;
+    int R = (m + cl - 1) / cl;
     if (R < 1) R = 1;
-    const bool in_smem = panel_fits_cluster(n, k0, jb);
+    const bool in_smem = (size_t)(R + 2) * jb * sizeof(double) <= cfg.smem_cap;
     const int ldp = in_smem ? ((R + 1) & ~1) : lda;
     cudaLaunchConfig_t lc{};
-    lc.gridDim = dim3(cfg.cluster);
+    lc.gridDim = dim3(cl);
     lc.blockDim = dim3(kPanelThreads);
     lc.dynamicSmemBytes = in_smem ? (size_t)ldp * jb * sizeof(double) : 0;
     lc.stream = s;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = cfg.cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    at[0].val.clusterDim.x = cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     lc.attrs = at; lc.numAttrs = 1;
     GPB_CHECK_CUDA(cudaLaunchKernelEx(&lc, panel_cluster_kernel, n, k0, jb, A, lda, ipiv, info, R, ldp, in_smem ? 1 : 0));
     ++g_gpb_launches;
