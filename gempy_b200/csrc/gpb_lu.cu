@@ -858,6 +858,7 @@ LookAhead& look_ahead() {
         tried = true;
         int lo = 0, hi = 0;
         cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        if (getenv("GPB_LU_NO_LOOKAHEAD") != nullptr) return la;      // diagnostic: everything on the caller's stream
         la.ok = cudaStreamCreateWithPriority(&la.panel_stream, cudaStreamNonBlocking, hi) == cudaSuccess &&
                 cudaEventCreateWithFlags(&la.ready, cudaEventDisableTiming) == cudaSuccess &&
                 cudaEventCreateWithFlags(&la.panel_done, cudaEventDisableTiming) == cudaSuccess;

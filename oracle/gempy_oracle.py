@@ -707,6 +707,52 @@ def forward_gravity(interp_input, options, descriptor, tz, densities) -> np.ndar
 
 
 # ----------------------------------------------------------------------------------------------
+# condition number and its derivative with respect to the surface-point nuggets
+# ----------------------------------------------------------------------------------------------
+def condition_number_and_gradient(interp_input, options, descriptor, i: int, fd: bool = False):
+    """2-norm condition number of stack i's matrix (no fault columns: the reference optimises one group in isolation,
+    gempy/modules/optimize_nuggets/_optimizer.py:48-52) and d cond / d nugget of the stack's surface points.
+    Gradient from the extreme eigenpairs of the symmetric matrix; ``fd=True`` returns central finite differences
+    instead (the check of the analytic form).  Parity unpinned (engine definition absent from the reference tree)."""
+    ko = options.kernel_options
+    sp0, or0, su0 = _stack_slices(descriptor)
+    sl_sp, sl_or, sl_su = slice(sp0[i], sp0[i + 1]), slice(or0[i], or0[i + 1]), slice(su0[i], su0[i + 1])
+    nps = np.asarray(descriptor.tensors_structure.number_of_points_per_surface[sl_su], dtype=int)
+
+    def matrix(nug):
+        st = prepare_stack(interp_input.surface_points.sp_coords[sl_sp], nug, nps,
+                           interp_input.orientations.dip_positions[sl_or], interp_input.orientations.dip_gradients[sl_or],
+                           interp_input.orientations.nugget_effect_grad[sl_or])
+        return assemble_covariance(st, ko)
+
+    nug0 = np.asarray(interp_input.surface_points.nugget_effect_scalar[sl_sp], dtype=float).copy()
+    A = matrix(nug0)
+    if fd:
+        g = np.zeros_like(nug0)
+        for k in range(nug0.size):
+            h = 1e-6 * max(nug0[k], 1e-4)
+            up, dn = nug0.copy(), nug0.copy()
+            up[k] += h
+            dn[k] -= h
+            g[k] = (np.linalg.cond(matrix(up)) - np.linalg.cond(matrix(dn))) / (2 * h)
+        return float(np.linalg.cond(A)), g
+    lam, Q = np.linalg.eigh(A)
+    iM, im = int(np.argmax(np.abs(lam))), int(np.argmin(np.abs(lam)))
+    n_ori = interp_input.orientations.dip_positions[sl_or].shape[0]
+    starts = np.concatenate([[0], np.cumsum(nps)[:-1]])
+    is_ref = np.zeros(nug0.size, bool)
+    is_ref[starts] = True
+    rest_idx = np.nonzero(~is_ref)[0]
+    ref_idx = np.repeat(starts, nps - 1)
+    rows = slice(3 * n_ori, 3 * n_ori + rest_idx.size)
+    g_diag = (np.sign(lam[iM]) * Q[rows, iM] ** 2 * abs(lam[im]) - abs(lam[iM]) * np.sign(lam[im]) * Q[rows, im] ** 2) / lam[im] ** 2
+    g = np.zeros_like(nug0)
+    np.add.at(g, rest_idx, 0.5 * ko.c_o * g_diag)
+    np.add.at(g, ref_idx, 0.5 * ko.c_o * g_diag)
+    return float(abs(lam[iM]) / abs(lam[im])), g
+
+
+# ----------------------------------------------------------------------------------------------
 # marching cubes on the dense grid (SURVEY.md 8f rank 4)
 # ----------------------------------------------------------------------------------------------
 # The reference's dense-grid mesher (gempy/modules/mesh_extranction/marching_cubes.py:13-101) hands each stack's

@@ -672,3 +672,27 @@ def test_marching_cubes_large_lattice_is_closed(eng):
     assert int(used.min()) >= 3                                             # every vertex is in a fan of >= 3 triangles
     # vertices lie on the level set of the trilinear field to first order: |F(v)| small vs. the cell increment
     assert torch.isfinite(v).all() and float(v.min()) >= 0 and float(v.max()) <= n - 1
+
+
+# ------------------------------------------------------------------------------------------------ nugget optimiser
+@pytest.mark.gpu
+def test_condition_number_gradient_and_optimiser_on_device(eng):
+    """Device condition number / gradient (gpb_assemble_cov + symmetric eigenpairs) against the oracle, then the whole
+    optimisation loop on the device against the oracle-driven loop."""
+    from gempy_b200.engine.nuggets import condition_number_and_gradient, optimize_nuggets
+    m = ex.synthetic_stress(n_sp_per_surface=60, n_surfaces=4, n_ori=40, resolution=(4, 4, 4))
+    ii, opt, desc = m.args()
+    st = gc.StackTables(ii, desc, 0, opt.kernel_options, eng.device)
+    c, g = condition_number_and_gradient(eng, st)
+    c_ref, g_ref = orc.condition_number_and_gradient(ii, opt, desc, 0)
+    assert abs(c - c_ref) < 1e-6 * c_ref
+    assert np.abs(g - g_ref).max() < 1e-5 * np.abs(g_ref).max()
+    hist = optimize_nuggets(ii, opt, desc, max_epochs=40, convergence_criteria=1e3, engine=eng)
+    m2 = ex.synthetic_stress(n_sp_per_surface=60, n_surfaces=4, n_ori=40, resolution=(4, 4, 4))
+    i2, o2, d2 = m2.args()
+    hist_ref = optimize_nuggets(i2, o2, d2, max_epochs=40, convergence_criteria=1e3,
+                                cond_and_grad=lambda i: orc.condition_number_and_gradient(i2, o2, d2, i))
+    assert len(hist[0]) == len(hist_ref[0])
+    np.testing.assert_allclose(hist[0], hist_ref[0], rtol=1e-4)
+    np.testing.assert_allclose(ii.surface_points.nugget_effect_scalar, i2.surface_points.nugget_effect_scalar, rtol=1e-6, atol=1e-12)
+    assert hist[0][-1] < 1e5 < hist[0][0]

@@ -193,3 +193,31 @@ def test_marching_cubes_table_is_watertight():
     tri = v[t]
     nrm = np.cross(tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 0])
     assert (np.einsum("ij,ij->i", nrm, tri.mean(1) - (n - 1) / 2) > 0).all()
+
+
+def test_condition_number_gradient_and_nugget_optimiser():
+    """gempy/modules/optimize_nuggets (_optimizer.py:9-68, _ops.py:6-94) restated: the analytic derivative of the
+    condition number with respect to the surface-point nuggets agrees with central finite differences, and the Adam
+    loop (lr 0.01, top-1 % gradient masking, clamp at 1e-7, the reference's convergence rule) lowers the condition
+    number of an ill-conditioned stack by orders of magnitude."""
+    from gempy_b200.engine.nuggets import gradient_masking, has_converged, optimize_nuggets
+    m = ex.anticline()
+    ii, opt, desc = m.args()
+    c, g = orc.condition_number_and_gradient(ii, opt, desc, 0)
+    c_fd, g_fd = orc.condition_number_and_gradient(ii, opt, desc, 0, fd=True)
+    assert abs(c - c_fd) < 1e-6 * c
+    assert np.abs(g - g_fd).max() < 1e-4 * np.abs(g).max()
+    # helpers follow the reference's rules
+    gm = gradient_masking(np.array([1.0, -5.0, 3.0, 0.5] * 50), focus=0.01)          # int(200 * 0.01) = 2 entries survive
+    assert np.count_nonzero(gm) == 2 and set(np.unique(gm)) == {-5.0, 0.0}
+    assert gradient_masking(np.ones(27), focus=0.01).sum() == 0                       # int(27 * 0.01) = 0, as torch.topk(k=0)
+    assert has_converged(9e4, 1e9) and not has_converged(2e5, 1e9, epoch=3)
+    assert has_converged(2e5, 2.001e5, epoch=11) and not has_converged(2e5, 3e5, epoch=11)
+    big = ex.synthetic_stress(n_sp_per_surface=60, n_surfaces=4, n_ori=40, resolution=(4, 4, 4))
+    ii, opt, desc = big.args()
+    hist = optimize_nuggets(ii, opt, desc, max_epochs=40, convergence_criteria=1e3,
+                            cond_and_grad=lambda i: orc.condition_number_and_gradient(ii, opt, desc, i))
+    assert hist[0][0] > 5e6 and hist[0][-1] < 1e5
+    nug = ii.surface_points.nugget_effect_scalar
+    assert (nug >= 1e-7).all() and 0 < (nug != 2e-5).sum() <= 40
+    assert opt.kernel_options.condition_number == hist[0][-1]
