@@ -696,3 +696,56 @@ def test_condition_number_gradient_and_optimiser_on_device(eng):
     np.testing.assert_allclose(hist[0], hist_ref[0], rtol=1e-4)
     np.testing.assert_allclose(ii.surface_points.nugget_effect_scalar, i2.surface_points.nugget_effect_scalar, rtol=1e-6, atol=1e-12)
     assert hist[0][-1] < 1e5 < hist[0][0]
+
+
+# ------------------------------------------------------------------------------------------------ edge cases
+def _ragged_model(custom_xyz=None, refinement=3):
+    """Surfaces with 1, 2 and 7 points (a one-point surface has no increment row: n_rest counts only the others), a
+    stack without orientations of its own element on one surface, octree + optional custom grid."""
+    from gempy_b200.engine.data import StackRelationType as R
+    rng = np.random.default_rng(5)
+    def plane(z, k):
+        xy = rng.uniform(100, 900, size=(k, 2))
+        return np.column_stack([xy, z + 20 * np.sin(xy[:, 0] / 200.0)])
+    sp = {"a": plane(800, 1), "b": plane(600, 2), "c": plane(350, 7)}
+    op = {"b": np.array([[500.0, 500.0, 600.0]]), "c": np.array([[300.0, 400.0, 350.0], [700.0, 600.0, 350.0]])}
+    og = {"b": np.array([[0.0, 0.0, 1.0]]), "c": np.array([[0.05, 0.0, 1.0], [0.0, -0.05, 1.0]])}
+    return ex.build_model("ragged", sp, op, og, [("s1", ["a", "b"], R.ERODE), ("s2", ["c"], R.ERODE)],
+                          [0, 1000, 0, 1000, 0, 1000], refinement=refinement, custom_xyz=custom_xyz)
+
+
+@pytest.mark.gpu
+def test_ragged_surfaces_and_empty_custom_grid(eng):
+    m_gpu = _ragged_model(custom_xyz=np.zeros((0, 3)))
+    m_cpu = _ragged_model(custom_xyz=np.zeros((0, 3)))
+    ii, opt, desc = m_gpu.args()
+    st = gc.StackTables(ii, desc, 0, opt.kernel_options, eng.device)
+    assert (st.n_surf, st.n_rest, st.n_ori) == (2, 1, 1)           # surfaces of 1 and 2 points -> one increment row
+    _compare_model(m_gpu, m_cpu)
+    sol = gc.compute_model(*_ragged_model(custom_xyz=np.zeros((0, 3))).args(), engine=eng)
+    assert sol.raw_arrays.custom is None or len(sol.raw_arrays.custom) == 0
+    # five custom points straddling the three surfaces
+    pts = np.array([[500, 500, z] for z in (950.0, 700.0, 500.0, 200.0, 10.0)])
+    sol = gc.compute_model(*_ragged_model(custom_xyz=pts).args(), engine=eng)
+    ref = orc.interpolate_all_fields(*_ragged_model(custom_xyz=pts).args(), _ragged_model(custom_xyz=pts).interpolation_input.grid.custom_grid.values)
+    np.testing.assert_array_equal(sol.raw_arrays.custom, ref.lith_ids)
+    assert sol.raw_arrays.custom[0] == 1 and sol.raw_arrays.custom[-1] == 4
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(1, 1, 1), (1, 1, 8), (3, 1, 5), (2, 7, 3)])
+def test_tiny_dense_grids(eng, shape):
+    """Dense grids down to a single cell (every z-run eligibility rule fails -> generic kernel), fields against the
+    oracle."""
+    m = ex.anticline(resolution=shape)
+    ii, opt, desc = m.args()
+    sol = gc.compute_model(ii, opt, desc, engine=eng)
+    g = ii.grid.dense_grid
+    ref = orc.interpolate_all_fields(ii, opt, desc, np.vstack([ii.grid.octree_grid.values, g.values]) + orc.GRID_SHIFT)
+    out = sol.octrees_output[0].outputs[0]
+    sl = out.grid.dense_grid_slice
+    zf = out.exported_fields.scalar_field
+    n_oct = ii.grid.octree_grid.n_points
+    assert sl.stop - sl.start == int(np.prod(shape))
+    assert _rel_err(zf[sl], ref.stacks[0].Z[n_oct:n_oct + g.n_points]) < RTOL
+    np.testing.assert_array_equal(sol.raw_arrays.lith_block, ref.lith_ids[n_oct:n_oct + g.n_points])
