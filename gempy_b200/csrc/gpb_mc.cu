@@ -1,8 +1,8 @@
 // Marching cubes on the dense regular grid: the device-side replacement for the
 // skimage.measure.marching_cubes call of gempy/modules/mesh_extranction/marching_cubes.py:82-89.
 //
-// HBM-bound byte/integer work.  Three passes over the lattice, one thread per lattice point, 1024 consecutive points
-// (z fastest) per CTA so that every load is coalesced and the +y/+x neighbours come out of L2:
+// HBM-bound byte/integer work.  Three passes over the lattice, 4096 consecutive points (z fastest) per CTA so that
+// every load is coalesced and the +y/+x neighbours come out of L2:
 //   (1) classify: which of the point's three +x/+y/+z edges carry a vertex, how many triangles its cube emits
 //       -> one flag byte per point + per-CTA totals;
 //   (2) a single-CTA scan of the per-CTA totals (vertices and triangles);
