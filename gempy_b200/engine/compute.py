@@ -287,9 +287,9 @@ class B200Engine:
                                segments: List[Segment], weights_cache: List[Optional[torch.Tensor]],
                                gradient: Optional[bool] = None, tables: Optional[List[StackTables]] = None,
                                comm: Optional[Comm] = None) -> FieldsOnDevice:
-        """`segments` are this rank's evaluation points.  With a multi-rank `comm`, rank 0 solves and broadcasts
-        the weights and the fault-block minima are all-reduced, so every rank sees the values a single-GPU run
-        would produce."""
+        """`segments` are this rank's evaluation points.  With a multi-rank `comm`, the systems are solved once (rank 0,
+        or the owner rank for fault-free stacks) and the weights broadcast, and the fault-block minima are all-reduced,
+        so every rank sees the values a single-GPU run would produce."""
         comm = comm or Comm()
         ko = options.kernel_options
         if gradient is None:
@@ -313,6 +313,28 @@ class B200Engine:
         iso_max = self.empty(n_st)
         isos, conds, srcs = [], [], []
         tmp_min = self.empty(1)
+        # Stacks whose system has no fault-drift column depend on nothing: with several ranks their assemble + solve are
+        # dealt out round-robin and every owner broadcasts its weights (sharding by independent stack / series,
+        # SURVEY.md 8e); fault-dependent stacks are solved on rank 0 in stack order below.
+        pre_cond = {}
+        free = [i for i in range(n_st) if weights_cache[i] is None and tables[i].active_faults_dev is None]
+        if comm.world > 1 and len(free) > 1:
+            want_cond = bool(getattr(ko, "compute_condition_number", False))
+            mine = {}
+            for k, i in enumerate(free):
+                if k % comm.world == comm.rank:
+                    tables[i].set_faults(None)
+                    A, b = self.assemble(tables[i])
+                    c = float(torch.linalg.cond(A).item()) if want_cond else float("nan")
+                    mine[i] = (self.solve(A, b), c)
+                    del A
+            for k, i in enumerate(free):
+                owner = k % comm.world
+                w_new, c = mine[i] if owner == comm.rank else (self.empty(tables[i].n), float("nan"))
+                weights_cache[i] = comm.broadcast(w_new, src=owner)
+                if want_cond:
+                    ct = comm.broadcast(torch.tensor([c], dtype=F64, device=self.device), src=owner)
+                    pre_cond[i] = float(ct.item())
         for i in range(n_st):
             st = tables[i]
             f_every = None
@@ -321,7 +343,7 @@ class B200Engine:
                 st.set_faults(f_every[:, gsz:][:, st.sp_slice])
             else:
                 st.set_faults(None)
-            cond = None
+            cond = pre_cond.get(i)
             if weights_cache[i] is None:
                 if comm.rank == 0:
                     A, b = self.assemble(st)

@@ -24,7 +24,8 @@ def main():
     comm = Comm()
     eng = gc.B200Engine(local)
     worst = 0.0
-    for build in (ex.combination, ex.one_fault, lambda: ex.combination(resolution=(21, 10, 9))):
+    # greenstone: three fault-free series -> the per-stack solves are dealt out over the ranks
+    for build in (ex.combination, ex.one_fault, lambda: ex.combination(resolution=(21, 10, 9)), lambda: ex.greenstone(refinement=4)):
         sol_d = gc.compute_model(*build().args(), engine=eng, comm=comm)
         sol_1 = gc.compute_model(*build().args(), engine=eng, comm=None if False else _Single())
         assert len(sol_d.octrees_output) == len(sol_1.octrees_output)
