@@ -221,3 +221,38 @@ def test_condition_number_gradient_and_nugget_optimiser():
     nug = ii.surface_points.nugget_effect_scalar
     assert (nug >= 1e-7).all() and 0 < (nug != 2e-5).sum() <= 40
     assert opt.kernel_options.condition_number == hist[0][-1]
+
+
+def test_oracle_invariances():
+    """Properties universal co-kriging must have whatever the conventions: the gradient field is invariant under a
+    common translation of data and evaluation points (degree-1 drift), the field moves by a constant only, and the
+    result does not depend on the order of the non-reference points of a surface or of the orientations."""
+    m = ex.anticline()
+    ii, opt, desc = m.args()
+    ko = opt.kernel_options
+    nps = np.asarray(desc.tensors_structure.number_of_points_per_surface, int)
+    sp, op, og = ii.surface_points.sp_coords, ii.orientations.dip_positions, ii.orientations.dip_gradients
+    nug_s, nug_o = ii.surface_points.nugget_effect_scalar, ii.orientations.nugget_effect_grad
+    rng = np.random.default_rng(3)
+    xyz = rng.uniform(-0.3, 0.3, size=(40, 3))
+
+    def fields(sp_, op_, og_, pts, nug_s_=nug_s, nug_o_=nug_o):
+        st = orc.prepare_stack(sp_, nug_s_, nps, op_, og_, nug_o_)
+        w = orc.solve(orc.assemble_covariance(st, ko), orc.rhs(st, ko))
+        return orc.evaluate(st, ko, w, pts, gradient=True)
+
+    Z0, G0 = fields(sp, op, og, xyz)
+    t = np.array([0.11, -0.07, 0.05])
+    Z1, G1 = fields(sp + t, op + t, og, xyz + t)
+    np.testing.assert_allclose(G1, G0, rtol=0, atol=1e-7 * np.abs(G0).max())
+    dz = Z1 - Z0
+    assert np.ptp(dz) < 1e-7 * np.ptp(Z0)                    # a constant shift at most
+    # permute the non-reference points inside every surface, and the orientations
+    starts = np.concatenate([[0], np.cumsum(nps)[:-1]])
+    perm = np.arange(sp.shape[0])
+    for s0, k in zip(starts, nps):
+        perm[s0 + 1:s0 + k] = s0 + 1 + rng.permutation(k - 1)
+    po = rng.permutation(op.shape[0])
+    Z2, G2 = fields(sp[perm], op[po], og[po], xyz, nug_s[perm], nug_o[po])
+    np.testing.assert_allclose(Z2, Z0, rtol=0, atol=1e-8 * np.abs(Z0).max())
+    np.testing.assert_allclose(G2, G0, rtol=0, atol=1e-8 * np.abs(G0).max())
