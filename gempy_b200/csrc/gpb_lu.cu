@@ -589,9 +589,17 @@ __device__ __forceinline__ void cp_async8(double* dst, const double* src, bool v
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(src), "r"(bytes) : "memory");
 }
 
+__device__ __forceinline__ void cp_async16(double* dst, const double* src, int bytes) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst);          // bytes in {0, 8, 16}: the rest is zero-filled
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(bytes) : "memory");
+}
+
+// kAligned16: every operand column starts on a 16-byte boundary (even leading dimension, 16-byte aligned base), so the
+// chunks move as 16-byte copies that bypass L1 -- half the copy instructions of the 8-byte path.
+template <bool kAligned16>
 __global__ void __launch_bounds__(kBThreads, 2) gemm_big_kernel(int M, int N, int K, const double* __restrict__ Ap,
                                                           const double* __restrict__ Bp, double* __restrict__ C, int lda, int tiles_per_cta) {
-    extern __shared__ double smem_big[];
+    extern __shared__ __align__(16) double smem_big[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nchunks = (K + kBK - 1) / kBK;
     // this CTA owns tiles_per_cta consecutive tiles (m fastest) and streams their K chunks through ONE continuous
@@ -610,21 +618,41 @@ __global__ void __launch_bounds__(kBThreads, 2) gemm_big_kernel(int M, int N, in
         double* As = smem_big + (size_t)slot * kBStageDoubles;
         double* Bs = As + kBK * kBLdA;
         const int kc = p_chunk * kBK;
-        // A chunk: 16 columns (k) x 128 rows (m), m contiguous in memory
+        if constexpr (kAligned16) {
+            // A chunk: kBK columns (k) x kBM rows (m), two rows per copy
 #pragma unroll
-        for (int t = 0; t < kBK * kBM / kBThreads; ++t) {
-            const int e = tid + kBThreads * t;
-            const int k = e / kBM, m = e % kBM;
-            const bool ok = (kc + k < K) && (p_m0 + m < M);
-            cp_async8(As + k * kBLdA + m, ok ? Ap + (long long)(kc + k) * lda + p_m0 + m : Ap, ok);
-        }
-        // B chunk: 128 columns (n) x 16 rows (k), k contiguous in memory
+            for (int t = 0; t < kBK * kBM / 2 / kBThreads; ++t) {
+                const int e = tid + kBThreads * t;
+                const int k = e / (kBM / 2), m = 2 * (e % (kBM / 2));
+                const int gm = p_m0 + m;
+                const int bytes = (kc + k < K) ? (gm + 1 < M ? 16 : (gm < M ? 8 : 0)) : 0;
+                cp_async16(As + k * kBLdA + m, bytes ? Ap + (long long)(kc + k) * lda + gm : Ap, bytes);
+            }
+            // B chunk: kBN columns (n) x kBK rows (k), two rows per copy
 #pragma unroll
-        for (int t = 0; t < kBN * kBK / kBThreads; ++t) {
-            const int e = tid + kBThreads * t;
-            const int nn = e / kBK, k = e % kBK;
-            const bool ok = (kc + k < K) && (p_n0 + nn < N);
-            cp_async8(Bs + nn * kBLdB + k, ok ? Bp + (long long)(p_n0 + nn) * lda + kc + k : Bp, ok);
+            for (int t = 0; t < kBN * kBK / 2 / kBThreads; ++t) {
+                const int e = tid + kBThreads * t;
+                const int nn = e / (kBK / 2), k = 2 * (e % (kBK / 2));
+                const int bytes = (p_n0 + nn < N) ? (kc + k + 1 < K ? 16 : (kc + k < K ? 8 : 0)) : 0;
+                cp_async16(Bs + nn * kBLdB + k, bytes ? Bp + (long long)(p_n0 + nn) * lda + kc + k : Bp, bytes);
+            }
+        } else {
+            // A chunk: kBK columns (k) x kBM rows (m), m contiguous in memory
+#pragma unroll
+            for (int t = 0; t < kBK * kBM / kBThreads; ++t) {
+                const int e = tid + kBThreads * t;
+                const int k = e / kBM, m = e % kBM;
+                const bool ok = (kc + k < K) && (p_m0 + m < M);
+                cp_async8(As + k * kBLdA + m, ok ? Ap + (long long)(kc + k) * lda + p_m0 + m : Ap, ok);
+            }
+            // B chunk: kBN columns (n) x kBK rows (k), k contiguous in memory
+#pragma unroll
+            for (int t = 0; t < kBN * kBK / kBThreads; ++t) {
+                const int e = tid + kBThreads * t;
+                const int nn = e / kBK, k = e % kBK;
+                const bool ok = (kc + k < K) && (p_n0 + nn < N);
+                cp_async8(Bs + nn * kBLdB + k, ok ? Bp + (long long)(p_n0 + nn) * lda + kc + k : Bp, ok);
+            }
         }
         if (++p_chunk == nchunks) {
             p_chunk = 0;
@@ -958,8 +986,10 @@ int outer_width(int n) {
 int launch_big_gemm(int n, int K0, int W, int col_begin, int col_end, double* A, int lda, cudaStream_t s) {
     static bool attr_set = false;
     if (!attr_set) {
-        GPB_CHECK_CUDA(cudaFuncSetAttribute(gemm_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBigGemmSmem));
-        GPB_CHECK_CUDA(cudaFuncSetAttribute(gemm_big_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        GPB_CHECK_CUDA(cudaFuncSetAttribute(gemm_big_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBigGemmSmem));
+        GPB_CHECK_CUDA(cudaFuncSetAttribute(gemm_big_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        GPB_CHECK_CUDA(cudaFuncSetAttribute(gemm_big_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBigGemmSmem));
+        GPB_CHECK_CUDA(cudaFuncSetAttribute(gemm_big_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         attr_set = true;
     }
     const int K1 = K0 + W;
@@ -967,9 +997,17 @@ int launch_big_gemm(int n, int K0, int W, int col_begin, int col_end, double* A,
     if (M <= 0 || N <= 0) return GPB_OK;
     const int ntiles = ((M + kBM - 1) / kBM) * ((N + kBN - 1) / kBN);
     static const int tiles_per_cta = [] { const char* e = getenv("GPB_LU_GEMM_TILES"); const int v = e ? atoi(e) : kBTilesPerCta; return v > 0 ? v : 1; }();
+    static const bool allow16 = getenv("GPB_LU_GEMM_NO16") == nullptr;
     const int grid = (ntiles + tiles_per_cta - 1) / tiles_per_cta;
-    gemm_big_kernel<<<grid, kBThreads, kBigGemmSmem, s>>>(M, N, W, A + (long long)K0 * lda + K1, A + (long long)col_begin * lda + K0,
-                                                    A + (long long)col_begin * lda + K1, lda, tiles_per_cta);
+    const double* Ap = A + (long long)K0 * lda + K1;
+    const double* Bp = A + (long long)col_begin * lda + K0;
+    double* Cp = A + (long long)col_begin * lda + K1;
+    const bool aligned = allow16 && (lda % 2 == 0) && (reinterpret_cast<uintptr_t>(Ap) % 16 == 0) &&
+                         (reinterpret_cast<uintptr_t>(Bp) % 16 == 0);
+    if (aligned)
+        gemm_big_kernel<true><<<grid, kBThreads, kBigGemmSmem, s>>>(M, N, W, Ap, Bp, Cp, lda, tiles_per_cta);
+    else
+        gemm_big_kernel<false><<<grid, kBThreads, kBigGemmSmem, s>>>(M, N, W, Ap, Bp, Cp, lda, tiles_per_cta);
     GPB_LAUNCH_CHECK();
     return GPB_OK;
 }
