@@ -9,8 +9,9 @@
 #define GPB_REG_EPS  1e-5     // h_u h_v / (r^2 + 1e-5)
 #define GPB_DIST_EPS 1e-10    // r = sqrt(|h|^2 + 1e-10)
 
+#include <atomic>
 extern thread_local char g_gpb_error[512];
-extern long long g_gpb_launches;
+extern std::atomic<long long> g_gpb_launches;
 
 int gpb_set_error(int code, const char* fmt, ...);
 
@@ -39,6 +40,25 @@ int gpb_set_error(int code, const char* fmt, ...);
 static inline long long gpb_round_up(long long v, long long m) { return (v + m - 1) / m * m; }
 
 int gpb_sm_count();
+// Index of the current CUDA device clamped to [0, GPB_MAX_DEVICES): per-device one-time state (function attributes,
+// side streams) is kept in arrays indexed by it, so one process may drive several devices.
+#define GPB_MAX_DEVICES 64
+int gpb_current_device();
+
+// High-priority side stream + two events of the current device (panel look-ahead of the LU / Cholesky
+// factorisations).  Created on first use, one per device, never destroyed; nullptr if the creation failed.
+struct GpbSideStream {
+    cudaStream_t stream;
+    cudaEvent_t ready, done;
+};
+GpbSideStream* gpb_side_stream();
+// The side stream and its events are shared by every caller on a device: the host-side ENQUEUE of a factorisation holds
+// this lock (event record / wait pairs are resolved at enqueue time, so serialising the enqueues is sufficient).
+struct GpbDeviceLock {
+    GpbDeviceLock();
+    ~GpbDeviceLock();
+    int dev;
+};
 
 // ---- fast FP64 primitives -------------------------------------------------------------------------
 // MUFU seeds (2^-22) + one third-order correction: error ~ e^3 ~ 1e-20 relative before rounding,

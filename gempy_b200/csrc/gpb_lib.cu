@@ -1,9 +1,11 @@
 // Library plumbing: error reporting, device query, launch counter.
 #include "gpb_common.cuh"
 #include <cstdarg>
+#include <cstdlib>
+#include <mutex>
 
 thread_local char g_gpb_error[512] = "";
-long long g_gpb_launches = 0;
+std::atomic<long long> g_gpb_launches{0};
 
 int gpb_set_error(int code, const char* fmt, ...) {
     va_list ap;
@@ -25,9 +27,41 @@ int gpb_sm_count() {
     return cached[dev];
 }
 
+int gpb_current_device() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) dev = 0;
+    return dev < GPB_MAX_DEVICES ? dev : GPB_MAX_DEVICES - 1;
+}
+
+namespace {
+std::mutex g_dev_mutex[GPB_MAX_DEVICES];
+std::mutex g_side_init_mutex;
+GpbSideStream g_side[GPB_MAX_DEVICES];
+int g_side_state[GPB_MAX_DEVICES] = {0};      // 0: not tried, 1: ok, -1: failed
+}  // namespace
+
+GpbSideStream* gpb_side_stream() {
+    const int dev = gpb_current_device();
+    std::lock_guard<std::mutex> g(g_side_init_mutex);
+    if (g_side_state[dev] == 0) {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        GpbSideStream& sd = g_side[dev];
+        const bool ok = cudaStreamCreateWithPriority(&sd.stream, cudaStreamNonBlocking, hi) == cudaSuccess &&
+                        cudaEventCreateWithFlags(&sd.ready, cudaEventDisableTiming) == cudaSuccess &&
+                        cudaEventCreateWithFlags(&sd.done, cudaEventDisableTiming) == cudaSuccess;
+        cudaGetLastError();
+        g_side_state[dev] = ok ? 1 : -1;
+    }
+    return g_side_state[dev] == 1 ? &g_side[dev] : nullptr;
+}
+
+GpbDeviceLock::GpbDeviceLock() : dev(gpb_current_device()) { g_dev_mutex[dev].lock(); }
+GpbDeviceLock::~GpbDeviceLock() { g_dev_mutex[dev].unlock(); }
+
 extern "C" const char* gpb_last_error(void) { return g_gpb_error; }
-extern "C" int gpb_version(void) { return 100; }
-extern "C" long long gpb_launch_count(void) { return g_gpb_launches; }
+extern "C" int gpb_version(void) { return 200; }
+extern "C" long long gpb_launch_count(void) { return g_gpb_launches.load(); }
 
 extern "C" int gpb_device_info(int device, int* sm_count, int* cc_major, int* cc_minor) {
     int n = 0;

@@ -800,10 +800,12 @@ struct PanelConfig {
 };
 
 const PanelConfig& panel_config() {
-    static PanelConfig cfg;
-    static bool done = false;
-    if (done) return cfg;
-    done = true;
+    static PanelConfig cfgs[GPB_MAX_DEVICES];
+    static bool dones[GPB_MAX_DEVICES] = {false};
+    const int dev = gpb_current_device();
+    PanelConfig& cfg = cfgs[dev];
+    if (dones[dev]) return cfg;
+    dones[dev] = true;
     const size_t want = 200 * 1024;
     if (cudaFuncSetAttribute(panel_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want) != cudaSuccess) {
         cudaGetLastError();
@@ -879,18 +881,16 @@ struct LookAhead {
     bool ok = false;
 };
 
-LookAhead& look_ahead() {
-    static LookAhead la;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
-        int lo = 0, hi = 0;
-        cudaDeviceGetStreamPriorityRange(&lo, &hi);
-        if (getenv("GPB_LU_NO_LOOKAHEAD") != nullptr) return la;      // diagnostic: everything on the caller's stream
-        la.ok = cudaStreamCreateWithPriority(&la.panel_stream, cudaStreamNonBlocking, hi) == cudaSuccess &&
-                cudaEventCreateWithFlags(&la.ready, cudaEventDisableTiming) == cudaSuccess &&
-                cudaEventCreateWithFlags(&la.panel_done, cudaEventDisableTiming) == cudaSuccess;
-        cudaGetLastError();
+// the side stream and its events are per device (gpb_side_stream); callers hold a GpbDeviceLock while enqueuing
+LookAhead look_ahead() {
+    LookAhead la;
+    static const bool disabled = getenv("GPB_LU_NO_LOOKAHEAD") != nullptr;      // diagnostic: everything on the caller's stream
+    if (disabled) return la;
+    if (GpbSideStream* sd = gpb_side_stream()) {
+        la.panel_stream = sd->stream;
+        la.ready = sd->ready;
+        la.panel_done = sd->done;
+        la.ok = true;
     }
     return la;
 }
@@ -917,7 +917,7 @@ int factor_blocked(int n, double* A, int lda, int* ipiv, int* info, double* B, i
     if (outer_width(n) > 0) return factor_outer(n, A, lda, ipiv, info, B, nrhs, ldb, s);
     zero_info_kernel<<<1, 1, 0, s>>>(info);
     GPB_LAUNCH_CHECK();
-    LookAhead& la = look_ahead();
+    const LookAhead la = look_ahead();
     const bool ahead = la.ok;
     cudaStream_t ps = ahead ? la.panel_stream : s;
     const int rhs_blocks = (B != nullptr) ? (nrhs + 63) / 64 : 0;
@@ -987,7 +987,8 @@ int outer_width(int n) {
 }
 
 int launch_big_gemm(int n, int K0, int W, int col_begin, int col_end, double* A, int lda, cudaStream_t s) {
-    static bool attr_set = false;
+    static bool attr_sets[GPB_MAX_DEVICES] = {false};
+    bool& attr_set = attr_sets[gpb_current_device()];
     if (!attr_set) {
         GPB_CHECK_CUDA(cudaFuncSetAttribute(gemm_big_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBigGemmSmem));
         GPB_CHECK_CUDA(cudaFuncSetAttribute(gemm_big_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
@@ -1040,7 +1041,7 @@ int factor_outer_panel(int n, int K0, int W, double* A, int lda, int* ipiv, int*
 int factor_outer(int n, double* A, int lda, int* ipiv, int* info, double* B, int nrhs, int ldb, cudaStream_t s) {
     zero_info_kernel<<<1, 1, 0, s>>>(info);
     GPB_LAUNCH_CHECK();
-    LookAhead& la = look_ahead();
+    const LookAhead la = look_ahead();
     const bool ahead = la.ok;
     cudaStream_t ps = ahead ? la.panel_stream : s;
     if (ahead) {
@@ -1117,7 +1118,8 @@ int backward_blocked(int n, const double* LU, int lda, double* B, int nrhs, int 
 
 int small_path(int n, double* A, int lda, double* b, int nrhs, int ldb, int* ipiv, int* info, int do_solve, cudaStream_t s) {
     const size_t smem = (size_t)n * (n + 1) * sizeof(double);
-    static bool attr_set = false;
+    static bool attr_sets[GPB_MAX_DEVICES] = {false};
+    bool& attr_set = attr_sets[gpb_current_device()];
     if (!attr_set) {
         GPB_CHECK_CUDA(cudaFuncSetAttribute(lu_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         attr_set = true;
@@ -1144,6 +1146,7 @@ extern "C" int gpb_lu_set_outer_width(int width) {
 extern "C" int gpb_lu_factor(int n, double* A, int lda, int* ipiv, int* info, void* stream) {
     GPB_REQUIRE(n > 0 && A && ipiv && lda >= n, "bad arguments");
     if (n <= kSmallN) return small_path(n, A, lda, nullptr, 0, 0, ipiv, info, 0, (cudaStream_t)stream);
+    GpbDeviceLock lock;
     return factor_blocked(n, A, lda, ipiv, info, nullptr, 0, 0, (cudaStream_t)stream);
 }
 
@@ -1158,6 +1161,7 @@ extern "C" int gpb_lu_solve(int n, double* A, int lda, double* b, int nrhs, int 
     GPB_REQUIRE(n > 0 && A && b && ipiv && lda >= n && ldb >= n && nrhs >= 1, "bad arguments");
     if (n <= kSmallN) return small_path(n, A, lda, b, nrhs, ldb, ipiv, info, 1, (cudaStream_t)stream);
     // forward substitution rides along with the factorisation (b is one more block of columns), then U x = y
+    GpbDeviceLock lock;
     int rc = factor_blocked(n, A, lda, ipiv, info, b, nrhs, ldb, (cudaStream_t)stream);
     if (rc) return rc;
     return backward_blocked(n, A, lda, b, nrhs, ldb, (cudaStream_t)stream);

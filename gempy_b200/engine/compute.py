@@ -19,6 +19,7 @@ from __future__ import annotations
 
 import contextlib
 import ctypes as C
+import os
 from dataclasses import dataclass
 from typing import List, Optional, Sequence, Tuple
 
@@ -242,28 +243,59 @@ class B200Engine:
         return torch.empty(*shape, dtype=dtype, device=self.device)
 
     # -- stages ----------------------------------------------------------------------------------------------
-    def assemble(self, st: StackTables) -> Tuple[torch.Tensor, torch.Tensor]:
+    def assemble(self, st: StackTables, extra_rows: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
+        """System matrix (column-major: tensor row j = matrix column j) and right-hand side.  With ``extra_rows`` the
+        leading dimension is n + extra_rows rounded up to an even number (16-byte aligned columns; the symmetric solve
+        carries its right-hand sides as extra rows) and the tensor has shape (n, lda)."""
         n = st.n
-        A = self.empty(n, n)                # column-major n x n (symmetric at this point)
+        lda = n if extra_rows == 0 else (n + extra_rows + 1) & ~1
+        A = self.empty(n, lda)              # symmetric at this point
         b = self.empty(n)
         s = st.struct()
-        _lib.check(self.lib.gpb_assemble_cov(C.byref(s), _ptr(A), n, _ptr(b), self.stream))
+        _lib.check(self.lib.gpb_assemble_cov(C.byref(s), _ptr(A), lda, _ptr(b), self.stream))
         return A, b
 
-    def solve(self, A: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
-        """b -> weights (returned); A is overwritten by its LU factors, except that a large system of odd order is
-        first copied into a buffer with an even leading dimension (every column then starts on a 16-byte boundary and the
-        K = 256 trailing update uses 16-byte operand copies: 1.18 s -> 1.09 s at n = 35 000 for a 3 ms copy)."""
+    def _check_info(self, info: torch.Tensor, what: str) -> int:
+        k = int(info.item())                # one 4-byte read per solve: a singular system must not pass silently
+        if k != 0:
+            raise _lib.GpbError(f"{what}: zero pivot at column {k} -- the co-kriging system is singular "
+                                "(duplicate surface points / orientations with zero nugget, or an all-zero drift column)")
+        return k
+
+    def solve(self, A: torch.Tensor, b: torch.Tensor, what: str = "LU solve") -> torch.Tensor:
+        """General path: b -> A^-1 b by the pivoted blocked LU (A is overwritten by its factors); raises on a zero
+        pivot.  A large system of odd order is first copied into a buffer with an even leading dimension (every column
+        then starts on a 16-byte boundary and the K = 256 trailing update uses 16-byte operand copies)."""
         n = A.shape[0]
-        lda = n
-        if n % 2 == 1 and n >= int(self.lib.gpb_lu_set_outer_min_n(-1)):
+        lda = A.shape[1]
+        if lda == n and n % 2 == 1 and n >= int(self.lib.gpb_lu_set_outer_min_n(-1)):
             W = self.empty(n, n + 1)
             W[:, :n].copy_(A)
             A, lda = W, n + 1
         ipiv = self.empty(n, dtype=torch.int32)
         info = torch.zeros(1, dtype=torch.int32, device=self.device)
         _lib.check(self.lib.gpb_lu_solve(n, _ptr(A), lda, _ptr(b), 1, n, _ptr(ipiv), _ptr(info), self.stream))
+        self._check_info(info, what)
         return b
+
+    SMALL_N = 160          # systems up to this order are solved by the one-CTA LU (every reference example model)
+
+    def solve_stack(self, st: StackTables, what: str = "stack") -> Tuple[torch.Tensor, str]:
+        """Assemble and solve one stack's saddle-point system; returns (weights, path).  Systems larger than SMALL_N
+        take the symmetric path (Cholesky of the covariance block + Schur complement of the drift rows,
+        gpb_sym_solve); if the covariance block is not numerically positive definite the system is re-assembled and
+        solved by the pivoted LU."""
+        n = st.n
+        nk = 3 * st.n_ori + st.n_rest
+        if n > self.SMALL_N and nk >= 1 and os.environ.get("GPB_SOLVER", "sym") != "lu":
+            A, b = self.assemble(st, extra_rows=1)
+            info = torch.zeros(1, dtype=torch.int32, device=self.device)
+            _lib.check(self.lib.gpb_sym_solve(n, nk, _ptr(A), A.shape[1], _ptr(b), 1, n, _ptr(info), self.stream))
+            if int(info.item()) == 0:
+                return b, "sym"
+            del A, b
+        A, b = self.assemble(st)
+        return self.solve(A, b, what), "lu"
 
     def pack(self, st: StackTables, w: torch.Tensor) -> torch.Tensor:
         s = st.struct()

@@ -4,7 +4,11 @@
  * below is a DEVICE pointer unless the parameter is documented as host; `stream` is a cudaStream_t
  * passed as void* (0 = legacy default stream).  Every entry returns 0 on success or a negative
  * GPB_E_* code, in which case gpb_last_error() holds a message.  Launches are asynchronous on
- * `stream` unless stated otherwise.
+ * `stream` unless stated otherwise.  Entries act on the CURRENT CUDA device (cudaSetDevice before calling; the host
+ * mirror does).  Process-wide state: the launch counter (atomic); the tuning setters gpb_lu_set_outer_*; per DEVICE:
+ * kernel attributes and one high-priority side stream + two events used by the factorisations' look-ahead -- the
+ * enqueue of a factorisation is serialised per device by a mutex inside the library, so calls are thread-safe, but a
+ * factor and the gpb_lu_apply calls that replay it must see the same gpb_lu_set_outer_* settings.
  *
  * Reference interface replaced (the engine package itself is not vendored in the reference tree; the
  * only reference-side binding is the Python call
@@ -113,6 +117,16 @@ int gpb_lu_set_outer_width(int width);
 /* Factor only / solve only (weight reuse across octree levels, timing against cusolverDnDgetrf/Dgetrs). */
 int gpb_lu_factor(int n, double* A, int lda, int* ipiv, int* info, void* stream);
 int gpb_lu_apply(int n, const double* LU, int lda, const int* ipiv, double* b, int nrhs, int ldb, void* stream);
+
+/* Symmetric path for the saddle-point system A = [K U; U^T 0] the covariance assembly produces: K = leading nk x nk
+ * block (symmetric positive definite: covariances + nuggets), U = the n - nk <= 64 universal-drift and fault-drift
+ * columns.  Blocked right-looking Cholesky of K on the LOWER triangle (no pivoting, DMMA trailing updates), Schur
+ * complement for the drift coefficients, triangular solves.  Only the lower triangle of A is read; A is overwritten.
+ * The right-hand sides ride through the factorisation as extra rows: lda >= n + nrhs (rows n .. n+nrhs-1 of every
+ * column are workspace).  b (n x nrhs, ldb) is overwritten with the solution.  `info` (device int, may be NULL): 0, or
+ * the 1-based column of a non-positive pivot -- K is then not numerically positive definite (or U is rank deficient)
+ * and the caller should re-assemble and use gpb_lu_solve. */
+int gpb_sym_solve(int n, int nk, double* A, int lda, double* b, int nrhs, int ldb, int* info, void* stream);
 
 /* ---- (3) fused field + gradient evaluation  [engine stage "evaluator"; the dominant kernel] -------- */
 /* Pack the weights of one solved stack into the evaluation source tables (range-normalised coordinates,

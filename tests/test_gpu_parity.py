@@ -154,6 +154,83 @@ def test_lu_outer_blocked_path(eng, n, width):
         eng.lib.gpb_lu_set_outer_width(prev_w)
 
 
+def _saddle(n, nu, seed, cond_boost=0.0):
+    """Random symmetric saddle-point system [K U; U^T 0] with K = G G^T / nk + shift (SPD)."""
+    rng = np.random.default_rng(seed)
+    nk = n - nu
+    G = rng.standard_normal((nk, nk))
+    Kb = G @ G.T / nk + (0.05 + cond_boost) * np.eye(nk)
+    U = rng.standard_normal((nk, nu))
+    A = np.zeros((n, n))
+    A[:nk, :nk] = Kb
+    A[:nk, nk:] = U
+    A[nk:, :nk] = U.T
+    return A, nk
+
+
+@pytest.mark.parametrize("n,nu", [(5, 0), (40, 3), (64, 0), (67, 3), (128, 9), (129, 1), (200, 12), (333, 3), (640, 0),
+                                  (1000, 3), (1539, 9), (2049, 4)])
+def test_sym_solve_random_saddle(eng, n, nu):
+    """gpb_sym_solve (Cholesky of the covariance block + Schur complement of the drift rows) against numpy on random
+    saddle-point systems: panel remainders, no drift rows, several drift rows, upper triangle never read."""
+    A, nk = _saddle(n, nu, seed=n)
+    rng = np.random.default_rng(n + 1)
+    B = rng.standard_normal((n, 2))
+    X_ref = np.linalg.solve(A, B)
+    nrhs = 2
+    lda = (n + nrhs + 1) & ~1
+    Ap = np.full((n, lda), np.nan)
+    Ap[:, :n] = np.tril(A).T + np.triu(np.full((n, n), np.nan), 1).T       # tensor row j = column j; only i >= j defined
+    Ad = torch.as_tensor(Ap, device=eng.device)
+    Bd = torch.as_tensor(B.T.copy(), device=eng.device)
+    info = torch.full((1,), -7, dtype=torch.int32, device=eng.device)
+    _lib.check(eng.lib.gpb_sym_solve(n, nk, Ad.data_ptr(), lda, Bd.data_ptr(), nrhs, n, info.data_ptr(), eng.stream))
+    X = Bd.cpu().numpy().T
+    assert int(info.item()) == 0
+    cond = np.linalg.cond(A)
+    assert np.isfinite(X).all()
+    assert np.abs(X - X_ref).max() <= 1e-13 * cond * np.abs(X_ref).max()
+    res = np.abs(A @ X - B).max() / (np.abs(A).max() * np.abs(X).max() * n * np.finfo(float).eps)
+    assert res < 50, f"scaled residual {res}"
+
+
+def test_sym_solve_reports_indefinite_block(eng):
+    n, nu = 300, 3
+    A, nk = _saddle(n, nu, seed=5)
+    A[170, 170] = -1.0                                   # K is no longer positive definite
+    lda = n + 2
+    Ap = np.zeros((n, lda))
+    Ap[:, :n] = A.T
+    Ad = torch.as_tensor(Ap, device=eng.device)
+    bd = torch.ones(n, dtype=torch.float64, device=eng.device)
+    info = torch.zeros(1, dtype=torch.int32, device=eng.device)
+    _lib.check(eng.lib.gpb_sym_solve(n, nk, Ad.data_ptr(), lda, bd.data_ptr(), 1, n, info.data_ptr(), eng.stream))
+    assert 1 <= int(info.item()) <= 171
+
+
+def test_solve_stack_paths_agree_and_singular_raises(eng):
+    """solve_stack: symmetric path on a model system = pivoted LU to rounding (times the condition number); a singular
+    system (two identical orientations, zero nugget) raises instead of returning garbage weights."""
+    m = ex.synthetic_stress(n_sp_per_surface=120, n_surfaces=4, n_ori=100, resolution=(4, 4, 4))
+    ii, opt, desc = m.args()
+    st = gc.StackTables(ii, desc, 0, opt.kernel_options, eng.device)
+    st.set_faults(None)
+    w_sym, path = eng.solve_stack(st)
+    assert path == "sym"
+    A, b = eng.assemble(st)
+    A_h = A.cpu().numpy()
+    w_lu = eng.solve(A.clone(), b.clone()).cpu().numpy()
+    w_sym = w_sym.cpu().numpy()
+    cond = np.linalg.cond(A_h)
+    assert np.abs(w_sym - w_lu).max() <= 1e-13 * cond * np.abs(w_lu).max()
+    bh = b.cpu().numpy()
+    assert np.abs(A_h @ w_sym - bh).max() <= 1e-10 * max(1.0, np.abs(bh).max())
+    # singular: a fault-drift column that is constant over the surface points is an all-zero column of the system
+    st.set_faults(torch.ones((1, int(desc.stack_structure.number_of_points_per_stack[0])), dtype=torch.float64, device=eng.device))
+    with pytest.raises(_lib.GpbError, match="singular"):
+        eng.solve_stack(st)
+
+
 def test_lu_reports_singular(eng):
     n = 40
     A = np.zeros((n, n))
