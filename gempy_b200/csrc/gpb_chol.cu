@@ -74,55 +74,200 @@ __global__ void save_diag_kernel(int n, const double* __restrict__ A, int lda, d
     if (i < n) diag0[i] = A[(long long)i * lda + i];
 }
 
-__global__ void __launch_bounds__(256) potrf_diag_kernel(int k0, int jb, double* __restrict__ A, int lda, int* __restrict__ info,
-                                                         const double* __restrict__ diag0) {
-    __shared__ double S[kCB * kPLd];
-    const int tid = threadIdx.x;
-    for (int e = tid; e < jb * jb; e += 256) {
-        const int c = e / jb, i = e - c * jb;
-        if (i >= c) S[c * kPLd + i] = A[(long long)(k0 + c) * lda + k0 + i];
+// 1/sqrt(u), u > 0 normal: MUFU seed (2^-22) + one third-order step (error ~1e-20 before rounding)
+__device__ __forceinline__ double rsqrt_fast(double u) {
+    const double y0 = gpb_rsqrt_seed(u);
+    const double g = u * y0;
+    const double e = fma(-g, y0, 1.0);
+    const double p = fma(0.375, e, 0.5);
+    return fma(y0 * e, p, y0);
+}
+
+// ---- diagonal block: L11 = chol(A11) and Wt = L11^-T, one CTA ------------------------------------------------------------
+// The 64 x 64 block lives in shared memory with 64 IDENTITY rows appended below it: the column eliminations that turn the
+// matrix rows into L11 turn the identity rows into L11^-T (rows riding along = forward substitution).  Blocked by 16
+// columns: (i) warp 0 factors the 16 x 16 diagonal block in registers, one matrix row per lane (lanes 0-15) and the
+// block's 16 identity rows in lanes 16-31, pivots and multipliers exchanged by shuffles -- no block barrier inside the
+// 16 sequential columns; (ii) every remaining row times the 16 x 16 inverse that (i) just produced; (iii) rank-16 update
+// of the block's remaining columns.  The panel below is then a GEMM with Wt (trsm_dmma_kernel).
+constexpr int kPB = 16;
+constexpr int kLdS = 129;                      // 64 matrix rows + 64 identity rows + 1
+constexpr size_t kPotrfSmem = (size_t)(kCB * kLdS + kCB) * sizeof(double);
+
+__global__ void __launch_bounds__(256) potrf64_kernel(int k0, int jb, double* __restrict__ A, int lda, int* __restrict__ info,
+                                                      const double* __restrict__ diag0, double* __restrict__ Wt) {
+    extern __shared__ double S[];              // S[c * kLdS + slot]
+    double* tol = S + kCB * kLdS;              // pivot thresholds of the block's columns
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int e = tid; e < kCB * kLdS; e += 256) S[e] = 0.0;
+    if (tid < kCB) tol[tid] = (tid < jb && diag0) ? kPivotTol * fabs(diag0[k0 + tid]) : 0.0;
+    __syncthreads();
+    {
+        double tmp[16];
+#pragma unroll
+        for (int t = 0; t < 16; ++t) {
+            const int e = tid + 256 * t, c = e >> 6, i = e & 63;
+            tmp[t] = (c < jb && i < jb && i >= c) ? A[(long long)(k0 + c) * lda + k0 + i] : 0.0;
+        }
+#pragma unroll
+        for (int t = 0; t < 16; ++t) {
+            const int e = tid + 256 * t, c = e >> 6, i = e & 63;
+            S[c * kLdS + i] = tmp[t];
+        }
+        if (tid < jb) S[tid * kLdS + 64 + tid] = 1.0;
     }
     __syncthreads();
-    chol_smem(S, kPLd, jb, info, k0, diag0 ? diag0 + k0 : nullptr);
-    for (int e = tid; e < jb * jb; e += 256) {
-        const int c = e / jb, i = e - c * jb;
-        if (i >= c) A[(long long)(k0 + c) * lda + k0 + i] = S[c * kPLd + i];
+    const int nbk = (jb + kPB - 1) / kPB;
+    for (int b = 0; b < nbk; ++b) {
+        const int o = b * kPB;
+        const int w = min(kPB, jb - o);
+        // (i) 16 x 16 diagonal block + its 16 identity rows, in registers of warp 0
+        if (warp == 0) {
+            const int ridx = (lane < 16) ? o + lane : 64 + o + (lane - 16);
+            double v[kPB];
+#pragma unroll
+            for (int c = 0; c < kPB; ++c) v[c] = S[(o + c) * kLdS + ridx];
+#pragma unroll
+            for (int j = 0; j < kPB; ++j) {
+                if (j < w) {
+                    const double d = __shfl_sync(0xffffffffu, v[j], j);
+                    const bool bad = !(d > tol[o + j]);
+                    if (bad && lane == 0 && info) atomicCAS(info, 0, k0 + o + j + 1);
+                    const double inv = rsqrt_fast(bad ? 1.0 : d);
+                    const double l = v[j] * inv;
+                    v[j] = l;
+#pragma unroll
+                    for (int c = j + 1; c < kPB; ++c) {
+                        const double lc = __shfl_sync(0xffffffffu, l, c);
+                        v[c] = fma(-l, lc, v[c]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < kPB; ++c)
+                if (lane >= 16 || c <= lane) S[(o + c) * kLdS + ridx] = v[c];
+        }
+        __syncthreads();
+        // (ii) rows below the diagonal block and the identity rows of the earlier blocks: X = rows * L_bb^-T
+        const int nm = max(0, jb - o - kPB);
+        if (tid < nm + o) {
+            const int i = (tid < nm) ? o + kPB + tid : 64 + (tid - nm);
+            double a[kPB], x[kPB];
+#pragma unroll
+            for (int k = 0; k < kPB; ++k) a[k] = S[(o + k) * kLdS + i];
+#pragma unroll
+            for (int n = 0; n < kPB; ++n) {
+                double acc = 0.0;
+#pragma unroll
+                for (int k = 0; k <= n; ++k) acc = fma(a[k], S[(o + n) * kLdS + 64 + o + k], acc);
+                x[n] = acc;
+            }
+#pragma unroll
+            for (int n = 0; n < kPB; ++n) S[(o + n) * kLdS + i] = x[n];
+        }
+        __syncthreads();
+        // (iii) rank-16 update of the block's remaining columns (two threads per row slot)
+        const int c_lo = o + kPB;
+        if (c_lo < jb) {
+            const int slot = tid >> 1, half = tid & 1;
+            const bool valid = (slot < 64) ? (slot >= c_lo && slot < jb) : (slot - 64 < c_lo);
+            if (valid) {
+                double xi[kPB];
+#pragma unroll
+                for (int k = 0; k < kPB; ++k) xi[k] = S[(o + k) * kLdS + slot];
+                const int c_hi = (slot < 64) ? min(jb, slot + 1) : jb;
+                for (int c = c_lo + half; c < c_hi; c += 2) {
+                    double acc = S[c * kLdS + slot];
+#pragma unroll
+                    for (int k = 0; k < kPB; ++k) acc = fma(-xi[k], S[(o + k) * kLdS + c], acc);
+                    S[c * kLdS + slot] = acc;
+                }
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int t = 0; t < 16; ++t) {
+        const int e = tid + 256 * t, c = e >> 6, i = e & 63;
+        if (c < jb && i < jb && i >= c) A[(long long)(k0 + c) * lda + k0 + i] = S[c * kLdS + i];
+    }
+    for (int e = tid; e < kCB * kCB; e += 256) {       // Wt[k][n] = (L11^-T)[k][n], zero below the diagonal / beyond jb
+        const int k = e >> 6, n = e & 63;
+        Wt[e] = (k <= n && n < jb) ? S[n * kLdS + 64 + k] : 0.0;
     }
 }
 
-// ---- L21 = A21 L11^-T: every thread owns one row of the panel (64 doubles in registers) ----------------------------------
-// Right-looking substitution: x_i = a_i / L_ii, then a_c -= x_i L_ci for c > i.  Column i of L11 below its diagonal is
-// contiguous in shared memory, every thread of the warp reads the same address (broadcast).
-__global__ void __launch_bounds__(128) trsm_panel_kernel(int M, int k0, int jb, double* __restrict__ A, int lda) {
-    __shared__ __align__(16) double Ls[kCB * kCB];      // Ls[i * 64 + c] = L[c][i], c >= i; identity beyond jb
-    __shared__ double invd[kCB];
-    const int tid = threadIdx.x;
-    for (int e = tid; e < kCB * kCB; e += 128) {
-        const int i = e >> 6, c = e & 63;
-        double v;
-        if (i < jb && c < jb) v = (c >= i) ? A[(long long)(k0 + i) * lda + k0 + c] : 0.0;
-        else v = (c == i) ? 1.0 : 0.0;
-        Ls[e] = v;
+// ---- panel below the diagonal block: L21 = A21 * Wt on the FP64 tensor cores, 64 rows per CTA, in place ------------------
+__device__ __forceinline__ void dmma_884(double& c0, double& c1, double a, double b);
+__device__ __forceinline__ void cpa8(double* dst, const double* src, bool valid);
+__device__ __forceinline__ void cpa16(double* dst, const double* src, int bytes);
+constexpr int kTLd = kCB + 4;
+constexpr size_t kTrsmSmem = (size_t)2 * kCB * kTLd * sizeof(double);
+
+template <bool kAligned16>
+__global__ void __launch_bounds__(128) trsm_dmma_kernel(int M, int k0, int jb, double* __restrict__ A, int lda,
+                                                        const double* __restrict__ Wt) {
+    extern __shared__ __align__(16) double smem_trsm[];
+    double* As = smem_trsm;                    // As[k * kTLd + m]
+    double* Bs = smem_trsm + kCB * kTLd;       // Bs[k * kTLd + n]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int row0 = k0 + jb + (int)blockIdx.x * kCB;
+    const double* Ap = A + (long long)k0 * lda;
+    if constexpr (kAligned16) {
+#pragma unroll
+        for (int t = 0; t < kCB * kCB / 2 / 128; ++t) {
+            const int e = tid + 128 * t;
+            const int k = e >> 5, m = 2 * (e & 31);
+            const int gm = row0 + m;
+            const int bytes = (k < jb) ? (gm + 1 < M ? 16 : (gm < M ? 8 : 0)) : 0;
+            cpa16(As + k * kTLd + m, bytes ? Ap + (long long)k * lda + gm : Ap, bytes);
+        }
+    } else {
+#pragma unroll
+        for (int t = 0; t < kCB * kCB / 128; ++t) {
+            const int e = tid + 128 * t;
+            const int k = e >> 6, m = e & 63;
+            const bool ok = (k < jb) && (row0 + m < M);
+            cpa8(As + k * kTLd + m, ok ? Ap + (long long)k * lda + row0 + m : Ap, ok);
+        }
     }
+#pragma unroll
+    for (int t = 0; t < kCB * kCB / 2 / 128; ++t) {
+        const int e = tid + 128 * t;
+        const int k = e >> 5, n = 2 * (e & 31);
+        cpa16(Bs + k * kTLd + n, Wt + k * kCB + n, 16);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
-    if (tid < kCB) invd[tid] = 1.0 / Ls[tid * kCB + tid];
-    __syncthreads();
-    const long long row = (long long)k0 + jb + (long long)blockIdx.x * 128 + tid;
-    if (row >= M) return;
-    double a[kCB];
-    double* const base = A + (long long)k0 * lda + row;
+    const int wm = (warp & 1) * 32, wn = (warp >> 1) * 32;
+    const int r = lane >> 2, q = lane & 3;
+    double acc[4][4][2];
 #pragma unroll
-    for (int c = 0; c < kCB; ++c) a[c] = (c < jb) ? base[(long long)c * lda] : 0.0;
+    for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int i = 0; i < kCB; ++i) {
-        const double x = a[i] * invd[i];
-        a[i] = x;
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    const int kend = wn + 32;                  // Wt is upper triangular: column n needs k <= n only
+    for (int ks = 0; ks < kend; ks += 4) {
+        double a[4], b[4];
 #pragma unroll
-        for (int c = i + 1; c < kCB; ++c) a[c] = fma(-x, Ls[i * kCB + c], a[c]);
+        for (int i = 0; i < 4; ++i) a[i] = As[(ks + q) * kTLd + wm + 8 * i + r];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) b[j] = Bs[(ks + q) * kTLd + wn + 8 * j + r];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dmma_884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
     }
 #pragma unroll
-    for (int c = 0; c < kCB; ++c)
-        if (c < jb) base[(long long)c * lda] = a[c];
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int gm = row0 + wm + 8 * i + r;
+            const int gn = wn + 8 * j + 2 * q;
+            if (gm < M && gn < jb) A[(long long)(k0 + gn) * lda + gm] = acc[i][j][0];
+            if (gm < M && gn + 1 < jb) A[(long long)(k0 + gn + 1) * lda + gm] = acc[i][j][1];
+        }
 }
 
 // ---- trailing update on the FP64 tensor cores: C[i, j] -= sum_k X[i, k] X[j, k], i >= j ----------------------------------
@@ -336,11 +481,11 @@ __global__ void __launch_bounds__(256) schur_kernel(int n, int nk, const double*
 // ---- backward substitution L^T x = z ---------------------------------------------------------------------------------------
 // CTA `blockIdx.x` owns block row I = nblk - 1 - blockIdx.x (64 unknowns), so CTAs are dispatched in dependency order.
 // x_I = L_II^-T (z_I - sum_{J > I} L[J, I]^T x_J): the columns of L[J, I] are contiguous (column-major), every warp owns 16
-// columns and keeps per-lane partial sums; solution blocks are consumed as their flags appear.
+// columns and keeps per-lane partial sums; solution blocks are consumed as their flags appear; the diagonal solve is a
+// 64 x 64 matrix-vector product with the block's L_II^-T the factorisation left in the workspace (Wt_all).
 __global__ void __launch_bounds__(128) trsv_lt_kernel(int nk, const double* __restrict__ L, int lda, double* __restrict__ x,
-                                                      int* __restrict__ flags) {
-    __shared__ double D[kCB * (kCB + 1)];
-    __shared__ double invD[kCB];
+                                                      const double* __restrict__ Wt_all, int* __restrict__ flags) {
+    __shared__ double Ws[kCB * (kCB + 1)];       // Ws[k * 65 + n] = (L_II^-T)[k][n]
     __shared__ double xs[kCB];
     __shared__ double part[kCB];
     const int nblk = (nk + kCB - 1) / kCB;
@@ -348,12 +493,18 @@ __global__ void __launch_bounds__(128) trsv_lt_kernel(int nk, const double* __re
     const int c0 = I * kCB;
     const int jb = min(kCB, nk - c0);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int e = tid; e < jb * jb; e += 128) {
-        const int c = e / jb, i = e - c * jb;
-        if (i >= c) D[c * (kCB + 1) + i] = L[(long long)(c0 + c) * lda + c0 + i];
+    {
+        const double* Wt = Wt_all + (long long)I * kCB * kCB;
+        double tmp[32];
+#pragma unroll
+        for (int t = 0; t < 32; ++t) tmp[t] = Wt[tid + 128 * t];
+#pragma unroll
+        for (int t = 0; t < 32; ++t) {
+            const int e = tid + 128 * t;
+            Ws[(e >> 6) * (kCB + 1) + (e & 63)] = tmp[t];
+        }
     }
-    __syncthreads();
-    if (tid < jb) invD[tid] = 1.0 / D[tid * (kCB + 1) + tid];
+    const double z_own = (tid < jb) ? x[c0 + tid] : 0.0;
     double acc[16];
 #pragma unroll
     for (int cc = 0; cc < 16; ++cc) acc[cc] = 0.0;
@@ -370,7 +521,7 @@ __global__ void __launch_bounds__(128) trsv_lt_kernel(int nk, const double* __re
             v1[cc] = (c < jb && lane + 32 < rb) ? col[lane + 32] : 0.0;
         }
         if (tid == 0) {
-            while (atomicAdd(&flags[J], 0) == 0) { __nanosleep(20); }
+            while (atomicAdd(&flags[J], 0) == 0) { }
             __threadfence();
         }
         __syncthreads();
@@ -388,27 +539,24 @@ __global__ void __launch_bounds__(128) trsv_lt_kernel(int nk, const double* __re
         if (lane == 0) part[warp * 16 + cc] = s;
     }
     __syncthreads();
-    if (warp == 0) {
-        double v0 = (lane < jb) ? x[c0 + lane] - part[lane] : 0.0;
-        double v1 = (lane + 32 < jb) ? x[c0 + lane + 32] - part[lane + 32] : 0.0;
-        for (int c = jb - 1; c >= 0; --c) {
-            const double vc = (c < 32) ? __shfl_sync(0xffffffffu, v0, c) : __shfl_sync(0xffffffffu, v1, c - 32);
-            const double xc = vc * invD[c];
-            if (lane < c) v0 = fma(-D[lane * (kCB + 1) + c], xc, v0);
-            if (lane + 32 < c) v1 = fma(-D[(lane + 32) * (kCB + 1) + c], xc, v1);
-            if (lane == (c & 31)) { if (c < 32) v0 = xc; else v1 = xc; }
-        }
-        if (lane < jb) x[c0 + lane] = v0;
-        if (lane + 32 < jb) x[c0 + lane + 32] = v1;
-        __threadfence();
-        __syncwarp();
-        if (lane == 0) atomicExch(&flags[I], 1);
+    if (tid < kCB) xs[tid] = (tid < jb) ? z_own - part[tid] : 0.0;       // v = z_I - sum
+    __syncthreads();
+    {   // x_I[k] = sum_{n >= k} Wt[k][n] v[n]: two threads per k, 32 columns each
+        const int k = tid >> 1, half = tid & 1;
+        double s = 0.0;
+#pragma unroll 8
+        for (int n = half * 32; n < half * 32 + 32; ++n) s = fma(Ws[k * (kCB + 1) + n], xs[n], s);
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        if (half == 0 && k < jb) x[c0 + k] = s;
     }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) atomicExch(&flags[I], 1);
 }
 
 // ---- host side ------------------------------------------------------------------------------------------------------------
-int syrk_mode() {       // 0: load / subtract / store epilogue, 1: L2 reductions (GPB_CHOL_RED=1)
-    static const int v = [] { const char* e = getenv("GPB_CHOL_RED"); return e ? atoi(e) : 0; }();
+int syrk_mode() {       // 1 (default): L2 reductions, 0: load / subtract / store epilogue (GPB_CHOL_RED=0)
+    static const int v = [] { const char* e = getenv("GPB_CHOL_RED"); return e ? atoi(e) : 1; }();
     return v;
 }
 
@@ -440,16 +588,38 @@ int launch_syrk(int M, int K, int src, int col_begin, int col_end, double* A, in
 }
 
 // columns [K0, K0 + W) of the factor, 64 at a time, updates confined to the block's own columns
-int factor_block(int M, int K0, int W, double* A, int lda, int* info, const double* diag0, cudaStream_t q) {
+int chol_panel_attrs() {
+    static bool attr_sets[GPB_MAX_DEVICES] = {false};
+    bool& attr_set = attr_sets[gpb_current_device()];
+    if (!attr_set) {
+        GPB_CHECK_CUDA(cudaFuncSetAttribute(trsm_dmma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTrsmSmem));
+        GPB_CHECK_CUDA(cudaFuncSetAttribute(trsm_dmma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTrsmSmem));
+        GPB_CHECK_CUDA(cudaFuncSetAttribute(potrf64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPotrfSmem));
+        attr_set = true;
+    }
+    return GPB_OK;
+}
+
+int launch_trsm(int M, int k0, int jb, double* A, int lda, const double* Wt, cudaStream_t q) {
+    const int rows = M - (k0 + jb);
+    if (rows <= 0) return GPB_OK;
+    const bool aligned = (lda % 2 == 0) && (reinterpret_cast<uintptr_t>(A) % 16 == 0) && ((k0 + jb) % 2 == 0);
+    const int grid = (rows + kCB - 1) / kCB;
+    if (aligned) trsm_dmma_kernel<true><<<grid, 128, kTrsmSmem, q>>>(M, k0, jb, A, lda, Wt);
+    else trsm_dmma_kernel<false><<<grid, 128, kTrsmSmem, q>>>(M, k0, jb, A, lda, Wt);
+    GPB_LAUNCH_CHECK();
+    return GPB_OK;
+}
+
+// wt_all: nblk blocks of 64 x 64 doubles (L_II^-T of every diagonal block; block index k0 / 64)
+int factor_block(int M, int K0, int W, double* A, int lda, int* info, const double* diag0, double* wt_all, cudaStream_t q) {
     for (int k0 = K0; k0 < K0 + W; k0 += kCB) {
         const int jb = min(kCB, K0 + W - k0);
-        potrf_diag_kernel<<<1, 256, 0, q>>>(k0, jb, A, lda, info, diag0);
+        double* Wt = wt_all + (long long)(k0 / kCB) * kCB * kCB;
+        int rc0;
+        potrf64_kernel<<<1, 256, kPotrfSmem, q>>>(k0, jb, A, lda, info, diag0, Wt);
         GPB_LAUNCH_CHECK();
-        const int rows = M - (k0 + jb);
-        if (rows > 0) {
-            trsm_panel_kernel<<<(rows + 127) / 128, 128, 0, q>>>(M, k0, jb, A, lda);
-            GPB_LAUNCH_CHECK();
-        }
+        if ((rc0 = launch_trsm(M, k0, jb, A, lda, Wt, q))) return rc0;
         if (k0 + jb < K0 + W) {
             int rc = launch_syrk(M, jb, k0, k0 + jb, K0 + W, A, lda, q);
             if (rc) return rc;
@@ -458,21 +628,24 @@ int factor_block(int M, int K0, int W, double* A, int lda, int* info, const doub
     return GPB_OK;
 }
 
-int outer_width_chol() {
-    static const int v = [] { const char* e = getenv("GPB_CHOL_OUTER"); const int w = e ? atoi(e) : kCOuter; return (w == 64 || w == 128 || w == 192 || w == 256) ? w : kCOuter; }();
-    return v;
+// outer block width: 128 below n = 12 000, 256 above (measured: n = 6 999 8.4 vs 8.7 ms, n = 17 499 70.7 vs 66.5 ms);
+// GPB_CHOL_OUTER = 64 / 128 / 192 / 256 forces one
+int outer_width_chol(int nk) {
+    static const int forced = [] { const char* e = getenv("GPB_CHOL_OUTER"); const int w = e ? atoi(e) : 0; return (w == 64 || w == 128 || w == 192 || w == 256) ? w : 0; }();
+    if (forced) return forced;
+    return nk >= 12000 ? 256 : kCOuter;
 }
 
-int chol_factor(int M, int n, int nk, double* A, int lda, int* info, const double* diag0, cudaStream_t s) {
+int chol_factor(int M, int n, int nk, double* A, int lda, int* info, const double* diag0, double* wt_all, cudaStream_t s) {
     GpbSideStream* side = gpb_side_stream();
     const bool ahead = side != nullptr && getenv("GPB_LU_NO_LOOKAHEAD") == nullptr;
     cudaStream_t ps = ahead ? side->stream : s;
-    const int ow = outer_width_chol();
+    const int ow = outer_width_chol(nk);
     if (ahead) {
         GPB_CHECK_CUDA(cudaEventRecord(side->ready, s));
         GPB_CHECK_CUDA(cudaStreamWaitEvent(ps, side->ready, 0));
     }
-    int rc = factor_block(M, 0, min(ow, nk), A, lda, info, diag0, ps);
+    int rc = factor_block(M, 0, min(ow, nk), A, lda, info, diag0, wt_all, ps);
     if (rc) return rc;
     for (int K0 = 0; K0 < nk;) {
         const int W = min(ow, nk - K0);
@@ -488,7 +661,7 @@ int chol_factor(int M, int n, int nk, double* A, int lda, int* info, const doubl
                 GPB_CHECK_CUDA(cudaEventRecord(side->ready, s));
                 GPB_CHECK_CUDA(cudaStreamWaitEvent(ps, side->ready, 0));
             }
-            if ((rc = factor_block(M, K1, W1, A, lda, info, diag0, ps))) return rc;
+            if ((rc = factor_block(M, K1, W1, A, lda, info, diag0, wt_all, ps))) return rc;
             if ((rc = launch_syrk(M, W, K0, K1 + W1, n, A, lda, s))) return rc;
         } else {
             if ((rc = launch_syrk(M, W, K0, K1, n, A, lda, s))) return rc;      // the Schur corner (columns nk .. n-1)
@@ -520,11 +693,18 @@ extern "C" int gpb_sym_solve(int n, int nk, double* A, int lda, double* b, int n
     // workspace: the original diagonal of K (pivot threshold) + the flags of the backward substitution
     const int nblk = (nk + kCB - 1) / kCB;
     double* ws = nullptr;
-    GPB_CHECK_CUDA(cudaMallocAsync((void**)&ws, sizeof(double) * nk + sizeof(int) * nblk, s));
-    int* flags = reinterpret_cast<int*>(ws + nk);
+    const long long wt_doubles = (long long)nblk * kCB * kCB;
+    const long long nk_pad = (nk + 1) & ~1LL;            // keeps wt_all 16-byte aligned (cudaMallocAsync aligns to >= 256 B)
+    {
+        int rca = chol_panel_attrs();
+        if (rca) return rca;
+    }
+    GPB_CHECK_CUDA(cudaMallocAsync((void**)&ws, sizeof(double) * (nk_pad + wt_doubles) + sizeof(int) * nblk, s));
+    double* wt_all = ws + nk_pad;
+    int* flags = reinterpret_cast<int*>(ws + nk_pad + wt_doubles);
     save_diag_kernel<<<(nk + 255) / 256, 256, 0, s>>>(nk, A, lda, ws);
     GPB_LAUNCH_CHECK();
-    int rc = chol_factor(M, n, nk, A, lda, info, ws, s);
+    int rc = chol_factor(M, n, nk, A, lda, info, ws, wt_all, s);
     if (rc) { cudaFreeAsync(ws, s); return rc; }
     int grid = (nk + 255) / 256;
     if (grid > 64) grid = 64;
@@ -532,7 +712,7 @@ extern "C" int gpb_sym_solve(int n, int nk, double* A, int lda, double* b, int n
     GPB_LAUNCH_CHECK();
     for (int r = 0; r < nrhs; ++r) {
         GPB_CHECK_CUDA(cudaMemsetAsync(flags, 0, sizeof(int) * nblk, s));
-        trsv_lt_kernel<<<nblk, 128, 0, s>>>(nk, A, lda, b + (long long)r * ldb, flags);
+        trsv_lt_kernel<<<nblk, 128, 0, s>>>(nk, A, lda, b + (long long)r * ldb, wt_all, flags);
         GPB_LAUNCH_CHECK();
     }
     GPB_CHECK_CUDA(cudaFreeAsync(ws, s));
