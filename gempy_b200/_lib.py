@@ -37,6 +37,40 @@ class GpbRegularGrid(C.Structure):
     ]
 
 
+class GpbModelStack(C.Structure):
+    _fields_ = [
+        ("st", GpbStack), ("relation", C.c_int), ("fault_stacks_host", C.POINTER(C.c_int)), ("fault_stacks_dev", C.c_void_p),
+        ("sp_begin", C.c_int), ("n_sp", C.c_int), ("unit_ids", C.c_void_p), ("weights", C.c_void_p),
+        ("eval_table", C.c_void_p), ("isovalues", C.c_void_p),
+    ]
+
+
+class GpbModelDesc(C.Structure):
+    _fields_ = [
+        ("n_stacks", C.c_int), ("stacks", C.POINTER(GpbModelStack)), ("sp_all", C.c_void_p), ("n_sp_all", C.c_longlong),
+        ("sigmoid_slope", C.c_double), ("iso_min", C.c_void_p), ("iso_max", C.c_void_p), ("fault_min", C.c_void_p),
+        ("solver", C.c_int),
+    ]
+
+
+GPB_SEG_POINTS, GPB_SEG_REGULAR = 0, 1
+
+
+class GpbSegment(C.Structure):
+    _fields_ = [
+        ("kind", C.c_int), ("count", C.c_longlong), ("out_offset", C.c_longlong), ("xyz", C.c_void_p),
+        ("ld_xyz", C.c_longlong), ("grid", GpbRegularGrid), ("i0", C.c_longlong),
+    ]
+
+
+class GpbLevel(C.Structure):
+    _fields_ = [
+        ("ld", C.c_longlong), ("n_segments", C.c_int), ("segments", C.POINTER(GpbSegment)), ("sp_offset", C.c_longlong),
+        ("Z", C.c_void_p), ("G", C.c_void_p), ("block", C.c_void_p), ("final_block", C.c_void_p),
+        ("faults_block", C.c_void_p), ("squeezed", C.c_void_p), ("mask", C.c_void_p),
+    ]
+
+
 # name -> (restype, argtypes); every symbol include/gempy_b200.h declares
 _LL = C.c_longlong
 _P = C.c_void_p
@@ -61,6 +95,22 @@ SIGNATURES = {
     "gpb_eval_regular": (C.c_int, [C.POINTER(GpbStack), _P, C.POINTER(GpbRegularGrid), _LL, _LL, _P, _LL,
                                    _P, _P, _P, _P, _P]),
     "gpb_eval_points": (C.c_int, [C.POINTER(GpbStack), _P, _P, _LL, _LL, _P, _LL, _P, _P, _P, _P, _P]),
+    "gpb_model_create": (C.c_int, [C.POINTER(GpbModelDesc), C.POINTER(C.c_void_p)]),
+    "gpb_model_destroy": (None, [C.c_void_p]),
+    "gpb_model_solve_stack": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(GpbLevel), C.POINTER(C.c_int), _P]),
+    "gpb_model_eval_stack": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(GpbLevel), _P]),
+    "gpb_model_combine": (C.c_int, [C.c_void_p, C.POINTER(GpbLevel), _P]),
+    "gpb_model_run_level": (C.c_int, [C.c_void_p, C.POINTER(GpbLevel), C.c_int, _P]),
+    "gpb_model_solver_path": (C.c_int, [C.c_void_p, C.c_int]),
+    "gpb_copy_2d": (C.c_int, [_P, _LL, _P, _LL, _LL, _LL, _P]),
+    "gpb_scan_elems": (_LL, [_LL]),
+    "gpb_count_marked": (C.c_int, [_P, _LL, _P, C.POINTER(_LL), _P]),
+    "gpb_emit_marked": (C.c_int, [_P, _LL, _LL, _P, _P, C.c_double, C.c_double, C.c_double, _P, _LL, _P]),
+    "gpb_upsample2": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "gpb_scatter_lattice": (C.c_int, [_P, _LL, _LL, C.POINTER(GpbRegularGrid), _P, C.c_int, _P, _P]),
+    "gpb_dc_scratch_bytes": (_LL, [_LL]),
+    "gpb_dual_contour": (C.c_int, [C.POINTER(GpbStack), _P, _P, _LL, _P, _P, _P, _LL, _LL, _P, C.POINTER(GpbRegularGrid),
+                                   C.c_double, _P, _LL, _P, _P, _P, _P, _P, _P, _P]),
     "gpb_activate": (C.c_int, [_P, _LL, _P, _P, C.c_int, C.c_double, _P, _P]),
     "gpb_min": (C.c_int, [_P, _LL, _P, _P]),
     "gpb_shift": (C.c_int, [_P, _LL, _P, _P, _P]),

@@ -5,7 +5,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
-SOURCES = ["gpb_lib.cu", "gpb_eval.cu", "gpb_cov.cu", "gpb_lu.cu", "gpb_chol.cu", "gpb_post.cu", "gpb_mc.cu"]
+SOURCES = ["gpb_lib.cu", "gpb_eval.cu", "gpb_cov.cu", "gpb_lu.cu", "gpb_chol.cu", "gpb_model.cu", "gpb_dc.cu", "gpb_post.cu", "gpb_mc.cu"]
 OUT = os.path.join(PKG, "libgempy_b200.so")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "-cudart", "static"]

@@ -60,6 +60,34 @@ struct GpbDeviceLock {
     int dev;
 };
 
+// ---- internal evaluation entry (gpb_eval.cu), used by the C ABI wrappers and by the level executor (gpb_model.cu) ----
+struct GpbEvalCall {
+    const gpb_stack* st = nullptr;
+    const double* src = nullptr;          // packed evaluation table
+    int regular = 0;                      // 1: points i0 .. i0 + m of `grid`; 0: explicit points xyz [3][ld_xyz]
+    gpb_regular_grid grid{};
+    long long i0 = 0;
+    const double* xyz = nullptr;
+    long long ld_xyz = 0;
+    long long m = 0;
+    const long long* m_dev = nullptr;     // explicit points only: actual count on the device (m is then the upper bound)
+    const double* fault_vals = nullptr;   // row f: fault_vals + (fault_ids ? fault_ids[f] : f) * ld_fault, minus fault_min[row]
+    long long ld_fault = 0;
+    const int* fault_ids = nullptr;
+    const double* fault_min = nullptr;
+    double* Z = nullptr;
+    double* gx = nullptr;
+    double* gy = nullptr;
+    double* gz = nullptr;
+    double* block = nullptr;              // fused activator output (optional)
+    const double* act_iso = nullptr;
+    const double* act_ids = nullptr;
+    int act_n = 0;
+    double act_slope = 0.0;
+    double* block_min = nullptr;          // running minimum of block (optional)
+};
+int gpb_eval_call(const GpbEvalCall& c, cudaStream_t stream);
+
 // ---- fast FP64 primitives -------------------------------------------------------------------------
 // MUFU seeds (2^-22) + one third-order correction: error ~ e^3 ~ 1e-20 relative before rounding,
 // with no divergent slow path (arguments are strictly positive, normal numbers on this path).

@@ -38,9 +38,19 @@ struct EvalParams {
     const double* xyz;       // !REGULAR: [3][ld_xyz]
     long long ld_xyz;
     long long i0;            // first global index (REGULAR)
-    long long m;             // number of points
-    const double* fault_vals;
+    long long m;             // number of points (upper bound when m_dev is set)
+    const long long* m_dev;  // optional (device): the actual number of points, read by the kernel (compacted lists)
+    const double* fault_vals;   // row f of the fault values: fault_vals + (fault_ids ? fault_ids[f] : f) * ld_fault
     long long ld_fault;
+    const int* fault_ids;       // optional (device): rows of the active faults inside a [n_stacks][ld] block matrix
+    const double* fault_min;    // optional (device): per-row minimum subtracted from the fault values
+    // fused activator (optional): block[k] = ids[n] + sum_j (ids[j] - ids[j+1]) sigma(slope (Z - iso[j]))
+    double* block;
+    const double* act_iso;
+    const double* act_ids;
+    int act_n;
+    double act_slope;
+    double* block_min;          // optional: running minimum of `block` over the launch (fault stacks)
     double* Z;
     double* gx;
     double* gy;
@@ -98,13 +108,72 @@ __device__ __forceinline__ void cov_ori(double u, double t, double& kp, double& 
     }
 }
 
+// ---- fused activator + fault terms (epilogue helpers shared by both kernels) ----------------------------------------
+constexpr int kActMax = 64;
+struct ActShared {
+    double iso[kActMax];
+    double dif[kActMax];
+    double base;
+};
+
+// 1 / (1 + exp(-x)); saturates exactly in FP64 beyond |x| ~ 40 / 745 (same expression as activate_kernel, gpb_post.cu)
+__device__ __forceinline__ double act_sigmoid(double x) {
+    if (x > 40.0) return 1.0;
+    if (x < -745.0) return 0.0;
+    return 1.0 / (1.0 + exp(-x));
+}
+
+__device__ __forceinline__ void act_load(const EvalParams& prm, ActShared& as) {
+    if (prm.block != nullptr) {
+        const int t = threadIdx.x;
+        if (t < prm.act_n) {
+            as.iso[t] = prm.act_iso[t];
+            as.dif[t] = prm.act_ids[t] - prm.act_ids[t + 1];
+        }
+        if (t == 0) as.base = prm.act_ids[prm.act_n];
+    }
+}
+
+__device__ __forceinline__ double act_value(const EvalParams& prm, const ActShared& as, double z) {
+    double v = as.base;
+    for (int j = 0; j < prm.act_n; ++j) v = fma(as.dif[j], act_sigmoid(prm.act_slope * (z - as.iso[j])), v);
+    return v;
+}
+
+__device__ __forceinline__ double fault_term(const EvalParams& prm, const double* tail_faults, long long idx, double z) {
+    for (int f = 0; f < prm.n_faults; ++f) {
+        const long long row = prm.fault_ids ? prm.fault_ids[f] : f;
+        double fv = prm.fault_vals[row * prm.ld_fault + idx];
+        if (prm.fault_min) fv -= prm.fault_min[row];
+        z = fma(tail_faults[f], fv, z);
+    }
+    return z;
+}
+
+__device__ __forceinline__ void act_min_commit(const EvalParams& prm, double vmin) {
+    if (prm.block == nullptr || prm.block_min == nullptr) return;
+    for (int o = 16; o > 0; o >>= 1) vmin = fmin(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
+    if ((threadIdx.x & 31) == 0) {
+        unsigned long long* a = reinterpret_cast<unsigned long long*>(prm.block_min);
+        unsigned long long old = *a;
+        while (vmin < __longlong_as_double((long long)old)) {
+            const unsigned long long assumed = old;
+            old = atomicCAS(a, assumed, (unsigned long long)__double_as_longlong(vmin));
+            if (old == assumed) break;
+        }
+    }
+}
+
 template <int KERNEL, bool GRAD, bool REGULAR, int P, int kThreads, int kMinBlocks>
 __global__ void __launch_bounds__(kThreads, kMinBlocks)
 eval_kernel(const EvalParams prm) {
     __shared__ __align__(128) double stage[2][kTileBytes / 8];
     __shared__ __align__(8) uint64_t full[2];
+    __shared__ ActShared act;
+    double vmin = __longlong_as_double(0x7ff0000000000000LL);
 
     const int tid = threadIdx.x;
+    act_load(prm, act);
     if (tid == 0) {
         gpb_mbar_init(&full[0], 1);
         gpb_mbar_init(&full[1], 1);
@@ -119,7 +188,8 @@ eval_kernel(const EvalParams prm) {
     const double* tail = src_ori + 6 * prm.n_ori_pad;
 
     const long long chunk = (long long)kThreads * P;
-    const long long n_chunks = (prm.m + chunk - 1) / chunk;
+    const long long m_pts = (prm.m_dev != nullptr) ? min(prm.m, *prm.m_dev) : prm.m;
+    const long long n_chunks = (m_pts + chunk - 1) / chunk;
     unsigned long long gt = 0;   // global tile counter of this CTA (buffer = gt & 1, parity = (gt >> 1) & 1)
 
     auto issue = [&](long long j, unsigned long long g) {
@@ -154,7 +224,7 @@ eval_kernel(const EvalParams prm) {
 #pragma unroll
         for (int k = 0; k < P; ++k) {
             idx[k] = c * chunk + (long long)k * kThreads + tid;
-            const long long i = idx[k] < prm.m ? idx[k] : prm.m - 1;     // clamp: tail threads recompute the last point
+            const long long i = idx[k] < m_pts ? idx[k] : m_pts - 1;     // clamp: tail threads recompute the last point
             double x, y, z;
             if constexpr (REGULAR) {
                 const long long gi = prm.i0 + i;
@@ -266,7 +336,7 @@ eval_kernel(const EvalParams prm) {
         const double inv_agi = tail[19];        // 1 / (a * gi)
 #pragma unroll
         for (int k = 0; k < P; ++k) {
-            if (idx[k] >= prm.m) continue;
+            if (idx[k] >= m_pts) continue;
             double z = accZ[k];
             double g0 = hx[k] * inv_agi, g1 = hy[k] * inv_agi, g2 = hz[k] * inv_agi;
             if (prm.n_drift >= 3) {
@@ -282,16 +352,21 @@ eval_kernel(const EvalParams prm) {
                     g2 += 2.0 * tail[14] * Zc[k] + tail[16] * X[k] + tail[17] * Y[k];
                 }
             }
-            for (int f = 0; f < prm.n_faults; ++f)
-                z = fma(tail[kTailDoubles + f], prm.fault_vals[(long long)f * prm.ld_fault + idx[k]], z);
+            z = fault_term(prm, tail + kTailDoubles, idx[k], z);
             prm.Z[idx[k]] = z;
             if constexpr (GRAD) {
                 prm.gx[idx[k]] = g0;
                 prm.gy[idx[k]] = g1;
                 prm.gz[idx[k]] = g2;
             }
+            if (prm.block != nullptr) {
+                const double v = act_value(prm, act, z);
+                prm.block[idx[k]] = v;
+                vmin = fmin(vmin, v);
+            }
         }
     }
+    act_min_commit(prm, vmin);
 }
 
 // ---- packing ----------------------------------------------------------------------------------------------
@@ -387,8 +462,11 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks)
 eval_zrun_kernel(const EvalParams prm) {
     __shared__ __align__(128) double stage[2][kTileBytes / 8];
     __shared__ __align__(8) uint64_t full[2];
+    __shared__ ActShared act;
+    double vmin = __longlong_as_double(0x7ff0000000000000LL);
 
     const int tid = threadIdx.x;
+    act_load(prm, act);
     if (tid == 0) {
         gpb_mbar_init(&full[0], 1);
         gpb_mbar_init(&full[1], 1);
@@ -553,9 +631,7 @@ eval_zrun_kernel(const EvalParams prm) {
                     g2v += 2.0 * tail[14] * Zc[k] + tail[16] * X + tail[17] * Y;
                 }
             }
-            if (live)
-                for (int f = 0; f < prm.n_faults; ++f)
-                    z = fma(tail[kTailDoubles + f], prm.fault_vals[(long long)f * prm.ld_fault + run * P + k], z);
+            if (live) z = fault_term(prm, tail + kTailDoubles, run * P + k, z);
             zo[k] = z; g0o[k] = g0v; g1o[k] = g1v; g2o[k] = g2v;
         }
         if (live) {
@@ -570,8 +646,17 @@ eval_zrun_kernel(const EvalParams prm) {
                     *reinterpret_cast<double2*>(prm.gz + o + k) = make_double2(g2o[k], g2o[k + 1]);
                 }
             }
+            if (prm.block != nullptr) {
+#pragma unroll
+                for (int k = 0; k < P; k += 2) {
+                    const double v0 = act_value(prm, act, zo[k]), v1 = act_value(prm, act, zo[k + 1]);
+                    *reinterpret_cast<double2*>(prm.block + o + k) = make_double2(v0, v1);
+                    vmin = fmin(vmin, fmin(v0, v1));
+                }
+            }
         }
     }
+    act_min_commit(prm, vmin);
 }
 
 template <int KERNEL, bool GRAD, int P, int T, int MINB>
@@ -594,7 +679,7 @@ template <int P>
 bool zrun_ok(const EvalParams& prm) {
     auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
     return prm.grid.nz % P == 0 && prm.i0 % P == 0 && prm.m % P == 0 && prm.m >= P && al(prm.Z) &&
-           (prm.gx == nullptr || (al(prm.gx) && al(prm.gy) && al(prm.gz)));
+           (prm.gx == nullptr || (al(prm.gx) && al(prm.gy) && al(prm.gz))) && (prm.block == nullptr || al(prm.block));
 }
 
 template <int KERNEL, bool GRAD, bool REGULAR, int P, int T, int MINB>
@@ -697,41 +782,67 @@ extern "C" int gpb_pack_eval_table(const gpb_stack* st, const double* w, double*
     return GPB_OK;
 }
 
+// Internal entry shared with the level executor (gpb_model.cu): one evaluation launch described by a GpbEvalCall.
+int gpb_eval_call(const GpbEvalCall& c, cudaStream_t stream) {
+    EvalParams prm{};
+    int rc = fill_common(c.st, c.src, prm);
+    if (rc) return rc;
+    GPB_REQUIRE(c.m >= 0, "bad point count");
+    if (c.m == 0) return GPB_OK;
+    GPB_REQUIRE(c.Z != nullptr, "null output");
+    GPB_REQUIRE((c.gx == nullptr) == (c.gy == nullptr) && (c.gx == nullptr) == (c.gz == nullptr), "gradient outputs: all or none");
+    GPB_REQUIRE(c.st->n_faults == 0 || c.fault_vals != nullptr, "fault values missing");
+    GPB_REQUIRE(c.block == nullptr || (c.act_ids != nullptr && c.act_n >= 0 && c.act_n <= kActMax && (c.act_n == 0 || c.act_iso != nullptr)),
+                "fused activator: ids / isovalues missing or more than 64 surfaces");
+    if (c.regular) {
+        GPB_REQUIRE(c.i0 >= 0 && c.i0 + c.m <= (long long)c.grid.nx * c.grid.ny * c.grid.nz, "bad point range");
+        prm.grid = c.grid;
+        prm.i0 = c.i0;
+    } else {
+        GPB_REQUIRE(c.xyz != nullptr && c.ld_xyz >= c.m, "null points / bad leading dimension");
+        prm.xyz = c.xyz;
+        prm.ld_xyz = c.ld_xyz;
+    }
+    prm.m = c.m;
+    prm.fault_vals = c.fault_vals;
+    prm.ld_fault = c.ld_fault;
+    prm.fault_ids = c.fault_ids;
+    prm.fault_min = c.fault_min;
+    prm.block = c.block;
+    prm.act_iso = c.act_iso;
+    prm.act_ids = c.act_ids;
+    prm.act_n = c.act_n;
+    prm.act_slope = c.act_slope;
+    prm.block_min = c.block_min;
+    prm.m_dev = c.regular ? nullptr : c.m_dev;
+    prm.Z = c.Z; prm.gx = c.gx; prm.gy = c.gy; prm.gz = c.gz;
+    return c.regular ? dispatch_eval<true>(c.st->kernel, c.gx != nullptr, prm, stream)
+                     : dispatch_eval<false>(c.st->kernel, c.gx != nullptr, prm, stream);
+}
+
 extern "C" int gpb_eval_regular(const gpb_stack* st, const double* src, const gpb_regular_grid* grid, long long i0,
                                 long long i1, const double* fault_vals, long long ld_fault, double* Z, double* gx,
                                 double* gy, double* gz, void* stream) {
-    EvalParams prm{};
-    int rc = fill_common(st, src, prm);
-    if (rc) return rc;
     GPB_REQUIRE(grid && Z, "null grid or output");
     GPB_REQUIRE(i0 >= 0 && i1 >= i0 && i1 <= (long long)grid->nx * grid->ny * grid->nz, "bad point range");
-    GPB_REQUIRE((gx == nullptr) == (gy == nullptr) && (gx == nullptr) == (gz == nullptr), "gradient outputs: all or none");
-    GPB_REQUIRE(st->n_faults == 0 || fault_vals != nullptr, "fault values missing");
-    prm.grid = *grid;
-    prm.i0 = i0;
-    prm.m = i1 - i0;
-    prm.fault_vals = fault_vals;
-    prm.ld_fault = ld_fault;
-    prm.Z = Z; prm.gx = gx; prm.gy = gy; prm.gz = gz;
-    return dispatch_eval<true>(st->kernel, gx != nullptr, prm, (cudaStream_t)stream);
+    GpbEvalCall c;
+    c.st = st; c.src = src;
+    c.regular = 1; c.grid = *grid; c.i0 = i0; c.m = i1 - i0;
+    c.fault_vals = fault_vals; c.ld_fault = ld_fault;
+    c.Z = Z; c.gx = gx; c.gy = gy; c.gz = gz;
+    return gpb_eval_call(c, (cudaStream_t)stream);
 }
 
 extern "C" int gpb_eval_points(const gpb_stack* st, const double* src, const double* xyz, long long ld_xyz, long long m,
                                const double* fault_vals, long long ld_fault, double* Z, double* gx, double* gy,
                                double* gz, void* stream) {
-    EvalParams prm{};
-    int rc = fill_common(st, src, prm);
-    if (rc) return rc;
     GPB_REQUIRE(m >= 0 && ld_xyz >= m, "bad point count");
     if (m == 0) return GPB_OK;
     GPB_REQUIRE(xyz && Z, "null points or output");
-    GPB_REQUIRE((gx == nullptr) == (gy == nullptr) && (gx == nullptr) == (gz == nullptr), "gradient outputs: all or none");
-    GPB_REQUIRE(st->n_faults == 0 || fault_vals != nullptr, "fault values missing");
-    prm.xyz = xyz;
-    prm.ld_xyz = ld_xyz;
-    prm.m = m;
-    prm.fault_vals = fault_vals;
-    prm.ld_fault = ld_fault;
-    prm.Z = Z; prm.gx = gx; prm.gy = gy; prm.gz = gz;
-    return dispatch_eval<false>(st->kernel, gx != nullptr, prm, (cudaStream_t)stream);
+    GpbEvalCall c;
+    c.st = st; c.src = src;
+    c.xyz = xyz; c.ld_xyz = ld_xyz; c.m = m;
+    c.fault_vals = fault_vals; c.ld_fault = ld_fault;
+    c.Z = Z; c.gx = gx; c.gy = gy; c.gz = gz;
+    return gpb_eval_call(c, (cudaStream_t)stream);
 }

@@ -439,6 +439,83 @@ extern "C" int gpb_emit_children(const double* centers, long long ld_c, long lon
     return GPB_OK;
 }
 
+// ---- octree -> regular fill: dense array at a level's resolution from the level above + the level's own voxels ----------
+__global__ void upsample2_kernel(const double* __restrict__ src, int nx, int ny, int nz, double* __restrict__ dst) {
+    const long long total = 8LL * nx * ny * nz;
+    const int fy = 2 * ny, fz = 2 * nz;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long i = e / ((long long)fy * fz);
+        const long long rem = e - i * fy * fz;
+        const int j = (int)(rem / fz), k = (int)(rem - (long long)j * fz);
+        dst[e] = src[((i >> 1) * ny + (j >> 1)) * nz + (k >> 1)];
+    }
+}
+
+__global__ void scatter_lattice_kernel(const double* __restrict__ cen, long long ld_c, long long nvox, gpb_regular_grid g,
+                                       const double* __restrict__ vals, int round_ids, double* __restrict__ dst) {
+    for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < nvox; v += (long long)gridDim.x * blockDim.x) {
+        const long long i = llrint((cen[v] - g.x0) / g.dx), j = llrint((cen[ld_c + v] - g.y0) / g.dy),
+                        k = llrint((cen[2 * ld_c + v] - g.z0) / g.dz);
+        if (i < 0 || j < 0 || k < 0 || i >= g.nx || j >= g.ny || k >= g.nz) continue;
+        const double x = vals[v];
+        dst[(i * g.ny + j) * g.nz + k] = round_ids ? rint(x) : x;
+    }
+}
+
+extern "C" int gpb_upsample2(const double* src, int nx, int ny, int nz, double* dst, void* stream) {
+    GPB_REQUIRE(src && dst && nx > 0 && ny > 0 && nz > 0, "bad arguments");
+    upsample2_kernel<<<blocks_for(8LL * nx * ny * nz), kT, 0, (cudaStream_t)stream>>>(src, nx, ny, nz, dst);
+    GPB_LAUNCH_CHECK();
+    return GPB_OK;
+}
+
+extern "C" int gpb_scatter_lattice(const double* centers, long long ld_c, long long nvox, const gpb_regular_grid* lattice,
+                                   const double* vals, int round_ids, double* dst, void* stream) {
+    GPB_REQUIRE(centers && lattice && vals && dst && nvox >= 0 && ld_c >= nvox, "bad arguments");
+    if (nvox == 0) return GPB_OK;
+    scatter_lattice_kernel<<<blocks_for(nvox), kT, 0, (cudaStream_t)stream>>>(centers, ld_c, nvox, *lattice, vals, round_ids, dst);
+    GPB_LAUNCH_CHECK();
+    return GPB_OK;
+}
+
+extern "C" long long gpb_scan_elems(long long nvox) { return (nvox + kScanBlock - 1) / kScanBlock + 1; }
+
+extern "C" int gpb_count_marked(const unsigned char* mark, long long nvox, long long* offsets, long long* n_marked_host,
+                                void* stream) {
+    GPB_REQUIRE(mark && offsets && n_marked_host && nvox >= 0, "bad arguments");
+    *n_marked_host = 0;
+    if (nvox == 0) return GPB_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    const long long nblocks = (nvox + kScanBlock - 1) / kScanBlock;
+    count_kernel<<<(unsigned)nblocks, kScanBlock, 0, s>>>(mark, nvox, offsets);
+    GPB_LAUNCH_CHECK();
+    scan_counts_kernel<<<1, 1024, 0, s>>>(offsets, nblocks, offsets + nblocks);
+    GPB_LAUNCH_CHECK();
+    GPB_CHECK_CUDA(cudaMemcpyAsync(n_marked_host, offsets + nblocks, sizeof(long long), cudaMemcpyDeviceToHost, s));
+    GPB_CHECK_CUDA(cudaStreamSynchronize(s));
+    return GPB_OK;
+}
+
+extern "C" int gpb_emit_marked(const double* centers, long long ld_c, long long nvox, const unsigned char* mark,
+                               const long long* offsets, double hx, double hy, double hz, double* children, long long ld_ch,
+                               void* stream) {
+    GPB_REQUIRE(centers && mark && offsets && children && nvox >= 0 && ld_c >= nvox, "bad arguments");
+    if (nvox == 0) return GPB_OK;
+    const long long nblocks = (nvox + kScanBlock - 1) / kScanBlock;
+    emit_kernel<<<(unsigned)nblocks, kScanBlock, 0, (cudaStream_t)stream>>>(centers, ld_c, nvox, mark, offsets, hx, hy, hz, children, ld_ch);
+    GPB_LAUNCH_CHECK();
+    return GPB_OK;
+}
+
+extern "C" int gpb_copy_2d(double* dst, long long ld_dst, const double* src, long long ld_src, long long rows, long long cols,
+                           void* stream) {
+    GPB_REQUIRE(dst && src && rows >= 0 && cols >= 0 && ld_dst >= cols && ld_src >= cols, "bad arguments");
+    if (rows == 0 || cols == 0) return GPB_OK;
+    GPB_CHECK_CUDA(cudaMemcpy2DAsync(dst, sizeof(double) * ld_dst, src, sizeof(double) * ld_src, sizeof(double) * cols, rows,
+                                     cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return GPB_OK;
+}
+
 extern "C" int gpb_any8(const unsigned char* in, long long nvox, unsigned char* out, void* stream) {
     GPB_REQUIRE(in && out && nvox >= 0, "bad arguments");
     if (nvox == 0) return GPB_OK;

@@ -20,6 +20,7 @@ from __future__ import annotations
 import contextlib
 import ctypes as C
 import os
+import warnings
 from dataclasses import dataclass
 from typing import List, Optional, Sequence, Tuple
 
@@ -30,8 +31,8 @@ from .. import _lib
 from .comm import Comm
 from .data import (BlockSolutionType, CombinedScalarFieldsOutput, Deferred, DualContouringData, DualContouringMesh, EngineGrid,
                    ExportedFields, GenericGrid, InputDataDescriptor, InterpolationInput, InterpolationOptions,
-                   InterpOutput, OctreeLevel, RawArraysSolution, RegularGrid, ScalarFieldOutput, Solutions,
-                   StackRelationType)
+                   InterpOutput, MeshExtractionMaskingOptions, OctreeLevel, RawArraysSolution, RegularGrid, ScalarFieldOutput,
+                   Solutions, StackRelationType)
 
 GRID_SHIFT = 1e-6          # regular-grid / octree points sit at centre + 1e-6 (pinned by the approved vectors)
 F64 = torch.float64
@@ -170,15 +171,86 @@ class StackTables:
 
 
 class ModelTables(list):
-    """Per-stack device tables plus the model-wide constants (all surface points, unit ids), uploaded once per
-    ``compute_model`` call: no host-to-device copy is issued inside the per-level loop, so the host runs ahead of the
-    GPU instead of synchronising on every small pageable copy."""
+    """Per-stack device tables plus everything the level executor needs, allocated once per ``compute_model`` call:
+    model-wide constants (all surface points, unit ids), per-stack outputs of the solve (weights, packed evaluation table,
+    isovalues), the fault-drift tables the executor fills, and the native model handle (gpb_model_create).  No
+    host-to-device copy is issued inside the per-level loop."""
 
-    def __init__(self, ii: InterpolationInput, desc: InputDataDescriptor, ko, device):
-        super().__init__(StackTables(ii, desc, i, ko, device) for i in range(desc.stack_structure.n_stacks))
+    def __init__(self, eng: "B200Engine", ii: InterpolationInput, desc: InputDataDescriptor, options: InterpolationOptions):
+        ko = options.kernel_options
+        ss = desc.stack_structure
+        n_st = ss.n_stacks
+        device = eng.device
+        super().__init__(StackTables(ii, desc, i, ko, device) for i in range(n_st))
+        self.eng = eng
         self.sp_all = torch.as_tensor(np.ascontiguousarray(ii.surface_points.sp_coords.T), dtype=F64, device=device)
         self.unit_values = torch.as_tensor(np.asarray(ii.unit_values, dtype=np.float64), device=device)
-        self.src_cache = {}            # stack -> packed evaluation table (the weights do not change between levels)
+        self.rel = [_rel_code(r) for r in ss.masking_descriptor]
+        self.iso_min = eng.empty(n_st)
+        self.iso_max = eng.empty(n_st)
+        self.fault_min = eng.empty(n_st)
+        self.iso_all = eng.empty(int(ss.number_of_surfaces_per_stack.sum()))
+        self._iso_host = None
+        self.weights: List[torch.Tensor] = []
+        self.eval_tables: List[torch.Tensor] = []
+        self.isovalues: List[torch.Tensor] = []
+        arr = (_lib.GpbModelStack * n_st)()
+        self._keep = []
+        for i, st in enumerate(self):
+            n_f = int(st.active_faults.size)
+            st.n_faults = n_f
+            if n_f:
+                st.fault_rest = eng.empty(n_f, max(st.n_rest, 1))
+                st.fault_ref = eng.empty(n_f, max(st.n_rest, 1))
+                host_ids = (C.c_int * n_f)(*[int(g) for g in st.active_faults])
+                dev_ids = torch.as_tensor(np.asarray(st.active_faults, dtype=np.int32), device=device)
+                self._keep += [host_ids, dev_ids]
+            st._struct = None
+            sct = st.struct()
+            ids = self.unit_values[st.surf_slice.start:st.surf_slice.stop + 1]
+            if ids.shape[0] != st.n_surf + 1:
+                raise ValueError("unit_values must hold one id per surface plus the basement")
+            if st.n_surf > 64:
+                raise ValueError(f"stack {i}: more than 64 surfaces in one stack")
+            w = eng.empty(st.n)
+            tab = eng.empty(int(eng.lib.gpb_eval_table_doubles(C.byref(sct))))
+            iso = self.iso_all[st.surf_slice.start:st.surf_slice.stop]
+            self.weights.append(w)
+            self.eval_tables.append(tab)
+            self.isovalues.append(iso)
+            ms = arr[i]
+            ms.st = sct
+            ms.relation = self.rel[i]
+            ms.fault_stacks_host = host_ids if n_f else None
+            ms.fault_stacks_dev = _ptr(dev_ids) if n_f else None
+            ms.sp_begin = st.sp_slice.start
+            ms.n_sp = st.sp_slice.stop - st.sp_slice.start
+            ms.unit_ids = _ptr(ids)
+            ms.weights = _ptr(w)
+            ms.eval_table = _ptr(tab)
+            ms.isovalues = _ptr(iso)
+        solver = 1 if os.environ.get("GPB_SOLVER", "sym") == "lu" else 0
+        d = _lib.GpbModelDesc(n_st, arr, _ptr(self.sp_all), int(self.sp_all.shape[1]), float(options.sigmoid_slope),
+                              _ptr(self.iso_min), _ptr(self.iso_max), _ptr(self.fault_min), solver)
+        self.handle = C.c_void_p()
+        _lib.check(eng.lib.gpb_model_create(C.byref(d), C.byref(self.handle)))
+        self._destroy = eng.lib.gpb_model_destroy
+
+    def iso_host(self, i: int) -> np.ndarray:
+        """Isovalues of stack i on the host (one device-to-host copy for the whole model, on first use)."""
+        if self._iso_host is None:
+            self._iso_host = self.iso_all.cpu().numpy()
+        return self._iso_host[self[i].surf_slice.start:self[i].surf_slice.stop]
+
+    def solver_paths(self) -> List[str]:
+        names = {0: "none", 1: "sym", 2: "lu"}
+        return [names.get(int(self.eng.lib.gpb_model_solver_path(self.handle, i)), "?") for i in range(len(self))]
+
+    def __del__(self):
+        h = getattr(self, "handle", None)
+        if h is not None and h.value:
+            self._destroy(h)
+            self.handle = None
 
 
 # ------------------------------------------------------------------------------------------------ engine
@@ -198,6 +270,14 @@ class FieldsOnDevice:
     weights: List[torch.Tensor]
     cond: List[Optional[float]]
     srcs: List[torch.Tensor] = None    # packed evaluation tables per stack
+
+    def seg_offset(self, name: str) -> int:
+        off = 0
+        for s in self.segments:
+            if s.name == name:
+                return off
+            off += s.m
+        return off
 
     def seg_slice(self, name: str) -> slice:
         off = 0
@@ -223,21 +303,23 @@ class B200Engine:
     # -- helpers --------------------------------------------------------------------------------------------
     @property
     def stream(self) -> int:
-        """The caller's current CUDA stream.  Inside ``hold_stream()`` the lookup is done once (786 lookups cost 6 ms of
-        the 100 ms a 15-stack octree-8 ``compute_model`` takes on the host)."""
+        """The caller's current CUDA stream on this engine's device.  Inside ``hold_stream()`` the lookup is done once."""
         if self._held_stream is not None:
             return self._held_stream
         return torch.cuda.current_stream(self.device).cuda_stream
 
     @contextlib.contextmanager
     def hold_stream(self):
+        """Makes this engine's device the current CUDA device (the library launches on the current device) and caches the
+        stream handle for the duration of a call."""
         outer = self._held_stream
-        if outer is None:
-            self._held_stream = torch.cuda.current_stream(self.device).cuda_stream
-        try:
-            yield
-        finally:
-            self._held_stream = outer
+        with torch.cuda.device(self.device):
+            if outer is None:
+                self._held_stream = torch.cuda.current_stream(self.device).cuda_stream
+            try:
+                yield
+            finally:
+                self._held_stream = outer
 
     def empty(self, *shape, dtype=F64) -> torch.Tensor:
         return torch.empty(*shape, dtype=dtype, device=self.device)
@@ -252,7 +334,8 @@ class B200Engine:
         A = self.empty(n, lda)              # symmetric at this point
         b = self.empty(n)
         s = st.struct()
-        _lib.check(self.lib.gpb_assemble_cov(C.byref(s), _ptr(A), lda, _ptr(b), self.stream))
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.gpb_assemble_cov(C.byref(s), _ptr(A), lda, _ptr(b), self.stream))
         return A, b
 
     def _check_info(self, info: torch.Tensor, what: str) -> int:
@@ -274,7 +357,8 @@ class B200Engine:
             A, lda = W, n + 1
         ipiv = self.empty(n, dtype=torch.int32)
         info = torch.zeros(1, dtype=torch.int32, device=self.device)
-        _lib.check(self.lib.gpb_lu_solve(n, _ptr(A), lda, _ptr(b), 1, n, _ptr(ipiv), _ptr(info), self.stream))
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.gpb_lu_solve(n, _ptr(A), lda, _ptr(b), 1, n, _ptr(ipiv), _ptr(info), self.stream))
         self._check_info(info, what)
         return b
 
@@ -284,13 +368,14 @@ class B200Engine:
         """Assemble and solve one stack's saddle-point system; returns (weights, path).  Systems larger than SMALL_N
         take the symmetric path (Cholesky of the covariance block + Schur complement of the drift rows,
         gpb_sym_solve); if the covariance block is not numerically positive definite the system is re-assembled and
-        solved by the pivoted LU."""
+        solved by the pivoted LU.  (The level executor does the same natively, gpb_model_solve_stack.)"""
         n = st.n
         nk = 3 * st.n_ori + st.n_rest
         if n > self.SMALL_N and nk >= 1 and os.environ.get("GPB_SOLVER", "sym") != "lu":
             A, b = self.assemble(st, extra_rows=1)
             info = torch.zeros(1, dtype=torch.int32, device=self.device)
-            _lib.check(self.lib.gpb_sym_solve(n, nk, _ptr(A), A.shape[1], _ptr(b), 1, n, _ptr(info), self.stream))
+            with torch.cuda.device(self.device):
+                _lib.check(self.lib.gpb_sym_solve(n, nk, _ptr(A), A.shape[1], _ptr(b), 1, n, _ptr(info), self.stream))
             if int(info.item()) == 0:
                 return b, "sym"
             del A, b
@@ -301,7 +386,8 @@ class B200Engine:
         s = st.struct()
         nd = int(self.lib.gpb_eval_table_doubles(C.byref(s)))
         src = self.empty(nd)
-        _lib.check(self.lib.gpb_pack_eval_table(C.byref(s), _ptr(w), _ptr(src), self.stream))
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.gpb_pack_eval_table(C.byref(s), _ptr(w), _ptr(src), self.stream))
         return src
 
     def evaluate_segment(self, st: StackTables, src: torch.Tensor, seg: Segment, off: int, Z: torch.Tensor,
@@ -314,126 +400,70 @@ class B200Engine:
         o8 = off * 8
         gp = [None, None, None] if G is None else [_ptr(G[a], o8) for a in range(3)]
         fv = _ptr(fault_vals, o8) if fault_vals is not None else None
-        if seg.grid is not None:
-            _lib.check(self.lib.gpb_eval_regular(C.byref(s), _ptr(src), C.byref(seg.grid), seg.i0, seg.i0 + seg.m,
-                                                 fv, L, _ptr(Z, o8), gp[0], gp[1], gp[2], self.stream))
-        else:
-            _lib.check(self.lib.gpb_eval_points(C.byref(s), _ptr(src), _ptr(seg.xyz), seg.xyz.shape[1], seg.m,
-                                                fv, L, _ptr(Z, o8), gp[0], gp[1], gp[2], self.stream))
+        with torch.cuda.device(self.device):
+            if seg.grid is not None:
+                _lib.check(self.lib.gpb_eval_regular(C.byref(s), _ptr(src), C.byref(seg.grid), seg.i0, seg.i0 + seg.m,
+                                                     fv, L, _ptr(Z, o8), gp[0], gp[1], gp[2], self.stream))
+            else:
+                _lib.check(self.lib.gpb_eval_points(C.byref(s), _ptr(src), _ptr(seg.xyz), seg.xyz.stride(0), seg.m,
+                                                    fv, L, _ptr(Z, o8), gp[0], gp[1], gp[2], self.stream))
 
-    # -- all stacks on one domain ----------------------------------------------------------------------------
-    def interpolate_all_fields(self, ii: InterpolationInput, options: InterpolationOptions, desc: InputDataDescriptor,
-                               segments: List[Segment], weights_cache: List[Optional[torch.Tensor]],
-                               gradient: Optional[bool] = None, tables: Optional[List[StackTables]] = None,
-                               comm: Optional[Comm] = None) -> FieldsOnDevice:
-        """`segments` are this rank's evaluation points.  With a multi-rank `comm`, the systems are solved once (rank 0,
-        or the owner rank for fault-free stacks) and the weights broadcast, and the fault-block minima are all-reduced,
-        so every rank sees the values a single-GPU run would produce."""
+    # -- all stacks on one domain: the level executor ------------------------------------------------------------
+    def run_level(self, tables: ModelTables, xyz: Optional[torch.Tensor], parts: List[Tuple[str, int]],
+                  dense: Optional[Tuple[_lib.GpbRegularGrid, int, int]], solve: bool, gradient: bool,
+                  comm: Optional[Comm] = None) -> FieldsOnDevice:
+        """Evaluate every stack on one level.  ``xyz`` [3, Lx]: the explicit points in the order of ``parts``
+        (name, count) without the dense grid; ``dense`` = (grid descriptor, first index, count) is evaluated from the
+        linear index and sits right after the first part (the octree centres) in the outputs.  The last part must be
+        the model's surface points.  With a multi-rank ``comm`` the stacks are walked one by one and every fault
+        block's minimum is all-reduced before the next stack needs it; otherwise one native call does the level."""
         comm = comm or Comm()
-        ko = options.kernel_options
-        if gradient is None:
-            gradient = bool(options.evaluation_options.compute_scalar_gradient)
-        ss = desc.stack_structure
-        n_st = ss.n_stacks
-        rel = [_rel_code(r) for r in ss.masking_descriptor]
-        if tables is None or not isinstance(tables, ModelTables):
-            tables = ModelTables(ii, desc, ko, self.device)
-        sp_all = tables.sp_all
-        n_sp = sp_all.shape[1]
-        gsz = sum(s.m for s in segments)
-        L = gsz + n_sp
-        sp_seg = Segment("surface_points", n_sp, xyz=sp_all)
+        n_st = len(tables)
+        n_dense = dense[2] if dense is not None else 0
+        Lx = sum(c for _, c in parts)
+        L = Lx + n_dense
+        n_sp = int(tables.sp_all.shape[1])
+        assert parts[-1] == ("surface_points", n_sp)
         Z = self.empty(n_st, L)
         G = self.empty(n_st, 3, L) if gradient else None
         block = self.empty(n_st, L)
-        values_everywhere = self.empty(n_st, L)
-        unit_values = tables.unit_values
-        iso_min = self.empty(n_st)
-        iso_max = self.empty(n_st)
-        isos, conds, srcs = [], [], []
-        tmp_min = self.empty(1)
-        # Stacks whose system has no fault-drift column depend on nothing: with several ranks their assemble + solve are
-        # dealt out round-robin and every owner broadcasts its weights (sharding by independent stack / series,
-        # SURVEY.md 8e); fault-dependent stacks are solved on rank 0 in stack order below.
-        pre_cond = {}
-        free = [i for i in range(n_st) if weights_cache[i] is None and tables[i].active_faults_dev is None]
-        if comm.world > 1 and len(free) > 1:
-            want_cond = bool(getattr(ko, "compute_condition_number", False))
-            mine = {}
-            for k, i in enumerate(free):
-                if k % comm.world == comm.rank:
-                    tables[i].set_faults(None)
-                    A, b = self.assemble(tables[i])
-                    c = float(torch.linalg.cond(A).item()) if want_cond else float("nan")
-                    mine[i] = (self.solve(A, b), c)
-                    del A
-            for k, i in enumerate(free):
-                owner = k % comm.world
-                w_new, c = mine[i] if owner == comm.rank else (self.empty(tables[i].n), float("nan"))
-                weights_cache[i] = comm.broadcast(w_new, src=owner)
-                if want_cond:
-                    ct = comm.broadcast(torch.tensor([c], dtype=F64, device=self.device), src=owner)
-                    pre_cond[i] = float(ct.item())
-        for i in range(n_st):
-            st = tables[i]
-            f_every = None
-            if st.active_faults_dev is not None:
-                f_every = values_everywhere.index_select(0, st.active_faults_dev).contiguous()
-                st.set_faults(f_every[:, gsz:][:, st.sp_slice])
-            else:
-                st.set_faults(None)
-            cond = pre_cond.get(i)
-            if weights_cache[i] is None:
-                if comm.rank == 0:
-                    A, b = self.assemble(st)
-                    if getattr(ko, "compute_condition_number", False):
-                        cond = float(torch.linalg.cond(A).item())
-                    w_new = self.solve(A, b)
-                    del A
-                else:
-                    w_new = self.empty(st.n)
-                weights_cache[i] = comm.broadcast(w_new, src=0)
-            w = weights_cache[i]
-            if w.shape[0] != st.n:
-                raise ValueError(f"stack {i}: cached weights have length {w.shape[0]}, system size is {st.n}")
-            src = tables.src_cache.get(i)
-            if src is None:
-                src = tables.src_cache[i] = self.pack(st, w)
-            srcs.append(src)
-            Gi = G[i] if gradient else None
-            # surface points first (the isovalues feed the activator), then every grid segment
-            self.evaluate_segment(st, src, sp_seg, gsz, Z[i], Gi, f_every)
-            off = 0
-            for seg in segments:
-                self.evaluate_segment(st, src, seg, off, Z[i], Gi, f_every)
-                off += seg.m
-            iso = Z[i, gsz + st.sp_slice.start:gsz + st.sp_slice.stop].index_select(0, st.ref_local_dev).contiguous()
-            isos.append(iso)
-            iso_min[i] = iso.min()
-            iso_max[i] = iso.max()
-            ids = unit_values[st.surf_slice.start:st.surf_slice.stop + 1].contiguous()
-            if ids.shape[0] != st.n_surf + 1:
-                raise ValueError("unit_values must hold one id per surface plus the basement")
-            _lib.check(self.lib.gpb_activate(_ptr(Z[i]), L, _ptr(iso), _ptr(ids), st.n_surf, float(options.sigmoid_slope),
-                                             _ptr(block[i]), self.stream))
-            if rel[i] == StackRelationType.FAULT.value:
-                _lib.check(self.lib.gpb_min(_ptr(block[i]), L, _ptr(tmp_min), self.stream))
-                comm.all_reduce_min(tmp_min)
-                _lib.check(self.lib.gpb_shift(_ptr(block[i]), L, _ptr(tmp_min), _ptr(values_everywhere[i]), self.stream))
-            else:
-                values_everywhere[i].copy_(block[i])
-            conds.append(cond)
-            if cond is not None:
-                ko.condition_number = cond
         final_block = self.empty(L)
         faults_block = self.empty(L)
         squeezed = self.empty(n_st, L, dtype=torch.uint8)
         mask = self.empty(n_st, L, dtype=torch.uint8)
-        rel_arr = (C.c_int * n_st)(*rel)
-        _lib.check(self.lib.gpb_combine(_ptr(Z), _ptr(block), L, L, n_st, rel_arr, _ptr(iso_min), _ptr(iso_max),
-                                        _ptr(final_block), _ptr(faults_block), _ptr(squeezed), _ptr(mask), self.stream))
-        return FieldsOnDevice(segments, gsz, Z, G, block, final_block, faults_block, squeezed, mask, isos,
-                              [weights_cache[i] for i in range(n_st)], conds, srcs)
+        ld_xyz = int(xyz.stride(0)) if xyz is not None else 0
+        segs = []
+        if dense is None:
+            segs.append((_lib.GPB_SEG_POINTS, Lx, 0, _ptr(xyz), ld_xyz, None, 0))
+        else:
+            n0 = parts[0][1]
+            segs.append((_lib.GPB_SEG_POINTS, n0, 0, _ptr(xyz), ld_xyz, None, 0))
+            segs.append((_lib.GPB_SEG_REGULAR, n_dense, n0, None, 0, dense[0], dense[1]))
+            segs.append((_lib.GPB_SEG_POINTS, Lx - n0, n0 + n_dense, _ptr(xyz, 8 * n0), ld_xyz, None, 0))
+        arr = (_lib.GpbSegment * len(segs))()
+        for k, (kind, cnt, off, xp, ldx, gd, i0) in enumerate(segs):
+            arr[k].kind, arr[k].count, arr[k].out_offset, arr[k].xyz, arr[k].ld_xyz, arr[k].i0 = kind, cnt, off, xp, ldx, i0
+            if gd is not None:
+                arr[k].grid = gd
+        lvl = _lib.GpbLevel(L, len(segs), arr, L - n_sp, _ptr(Z), _ptr(G), _ptr(block), _ptr(final_block), _ptr(faults_block),
+                            _ptr(squeezed), _ptr(mask))
+        lib, h, stream = self.lib, tables.handle, self.stream
+        if comm.world == 1:
+            _lib.check(lib.gpb_model_run_level(h, C.byref(lvl), int(solve), stream))
+        else:
+            for i in range(n_st):
+                if solve:
+                    _lib.check(lib.gpb_model_solve_stack(h, i, C.byref(lvl), None, stream))
+                _lib.check(lib.gpb_model_eval_stack(h, i, C.byref(lvl), stream))
+                if tables.rel[i] == StackRelationType.FAULT.value:
+                    comm.all_reduce_min(tables.fault_min[i:i + 1])
+            _lib.check(lib.gpb_model_combine(h, C.byref(lvl), stream))
+        out_segments = [Segment(parts[0][0], parts[0][1])]
+        if dense is not None:
+            out_segments.append(Segment("dense_grid", n_dense))
+        out_segments += [Segment(nm, c) for nm, c in parts[1:-1]]
+        return FieldsOnDevice(out_segments, L - n_sp, Z, G, block, final_block, faults_block, squeezed, mask,
+                              tables.isovalues, tables.weights, [None] * n_st, tables.eval_tables)
 
     def gradient_at(self, st: StackTables, src: torch.Tensor, xyz: torch.Tensor) -> torch.Tensor:
         """Engine-convention gradient [3, m] of one stack's field at explicit points.  The fault drift has no
@@ -441,18 +471,24 @@ class B200Engine:
         m = xyz.shape[1]
         Z = self.empty(m)
         G = self.empty(3, m)
-        s = st.struct()
+        s = _lib.GpbStack.from_buffer_copy(st.struct())
         s.n_faults = 0
-        _lib.check(self.lib.gpb_eval_points(C.byref(s), _ptr(src), _ptr(xyz), m, m, None, 0, _ptr(Z), _ptr(G[0]), _ptr(G[1]),
-                                            _ptr(G[2]), self.stream))
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.gpb_eval_points(C.byref(s), _ptr(src), _ptr(xyz), xyz.stride(0), m, None, 0, _ptr(Z), _ptr(G[0]),
+                                                _ptr(G[1]), _ptr(G[2]), self.stream))
         return G
 
     # -- octree ----------------------------------------------------------------------------------------------
+    def corners_into(self, centers: torch.Tensor, nv: int, d: np.ndarray, out: torch.Tensor):
+        """8 corners per voxel of centers[:, :nv] (row stride respected) written to out[:, :8 nv]."""
+        if nv:
+            _lib.check(self.lib.gpb_voxel_corners(_ptr(centers), centers.stride(0), nv, d[0] / 2, d[1] / 2, d[2] / 2, _ptr(out),
+                                                  out.stride(0), self.stream))
+
     def corners_of(self, centers: torch.Tensor, d: np.ndarray) -> torch.Tensor:
         nv = centers.shape[1]
         out = self.empty(3, 8 * nv)
-        _lib.check(self.lib.gpb_voxel_corners(_ptr(centers), nv, nv, d[0] / 2, d[1] / 2, d[2] / 2, _ptr(out), 8 * nv,
-                                              self.stream))
+        self.corners_into(centers, nv, d, out)
         return out
 
     def mark(self, nv: int, lith_corners: torch.Tensor, fault_corners: torch.Tensor, force_all: bool) -> torch.Tensor:
@@ -463,18 +499,26 @@ class B200Engine:
                                                 self.stream))
         return mark
 
-    def emit(self, centers: torch.Tensor, d: np.ndarray, mark: torch.Tensor) -> torch.Tensor:
-        """Children (8 per marked voxel, parent order preserved) of the marked voxels."""
-        nv = centers.shape[1]
-        n_children = C.c_longlong(0)
-        _lib.check(self.lib.gpb_emit_children(_ptr(centers), nv, nv, _ptr(mark), d[0] / 4, d[1] / 4, d[2] / 4, None, 0,
-                                              C.byref(n_children), self.stream))
-        nc = int(n_children.value)
-        children = self.empty(3, nc)
-        if nc:
-            _lib.check(self.lib.gpb_emit_children(_ptr(centers), nv, nv, _ptr(mark), d[0] / 4, d[1] / 4, d[2] / 4,
-                                                  _ptr(children), nc, C.byref(n_children), self.stream))
-        return children
+    def count_marked(self, mark: torch.Tensor) -> Tuple[int, torch.Tensor]:
+        """Number of marked voxels (the one host synchronisation of a level: the next level must be sized) and the scan
+        offsets the emission re-uses."""
+        nv = mark.shape[0]
+        offsets = self.empty(int(self.lib.gpb_scan_elems(nv)), dtype=torch.int64)
+        n = C.c_longlong(0)
+        _lib.check(self.lib.gpb_count_marked(_ptr(mark), nv, _ptr(offsets), C.byref(n), self.stream))
+        return int(n.value), offsets
+
+    def emit_into(self, centers: torch.Tensor, nv: int, d: np.ndarray, mark: torch.Tensor, offsets: torch.Tensor,
+                  out: torch.Tensor):
+        """Children (8 per marked voxel, parent order preserved) of centers[:, :nv] written to the first columns of out."""
+        if nv:
+            _lib.check(self.lib.gpb_emit_marked(_ptr(centers), centers.stride(0), nv, _ptr(mark), _ptr(offsets), d[0] / 4, d[1] / 4,
+                                                d[2] / 4, _ptr(out), out.stride(0), self.stream))
+
+    def copy_rows(self, dst: torch.Tensor, src: torch.Tensor):
+        """dst[r, :] = src[r, :] for 2-D float64 device tensors with unit column stride (copy engine, no kernel)."""
+        rows, cols = src.shape
+        _lib.check(self.lib.gpb_copy_2d(_ptr(dst), dst.stride(0), _ptr(src), src.stride(0), rows, cols, self.stream))
 
     def gather_fields(self, f: FieldsOnDevice, totals: Sequence[int], comm: Comm) -> FieldsOnDevice:
         """All-gather a range-sharded level into whole arrays (segment by segment; the surface-point tail is
@@ -517,54 +561,64 @@ def compute_dense_fields(interpolation_input: InterpolationInput, options: Inter
         raise ValueError("compute_dense_fields needs a dense grid")
     i0, i1 = point_range if point_range is not None else (0, g.n_points)
     m = i1 - i0
-    st = StackTables(ii, desc, stack, ko, eng.device)
     fr = desc.stack_structure.faults_relations
     if fr is not None and np.asarray(fr)[:, stack].any():
         raise ValueError("compute_dense_fields handles fault-free stacks; use compute_model for faulted ones")
-    A, b = eng.assemble(st)
-    w = eng.solve(A, b)
-    del A
-    src = eng.pack(st, w)
-    if out is None:
-        out = torch.empty((4, m), dtype=F64, pin_memory=True)
-    gd = regular_descriptor(g)
-    nyz = int(g.regular_grid_shape[1] * g.regular_grid_shape[2])
-    # slabs aligned to whole x planes when possible (keeps every slab on the z-run kernel)
-    per = max(1, -(-m // max(1, n_slabs)))
-    if per > nyz:
-        per = -(-per // nyz) * nyz
-    compute = torch.cuda.current_stream(eng.device)
-    copier = torch.cuda.Stream(eng.device)
-    bufs = [eng.empty(4, per) for _ in range(2)]
-    free_ev = [None, None]
-    k = 0
-    for s0 in range(0, m, per):
-        s1 = min(m, s0 + per)
-        buf = bufs[k & 1]
-        if free_ev[k & 1] is not None:
-            compute.wait_event(free_ev[k & 1])          # the copy that used this buffer has finished
-        seg = Segment("dense_grid", s1 - s0, grid=gd, i0=i0 + s0)
-        eng.evaluate_segment(st, src, seg, 0, buf[0], buf[1:], None)
-        done = torch.cuda.Event()
-        done.record(compute)
-        with torch.cuda.stream(copier):
-            copier.wait_event(done)
-            for a in range(4):                          # row by row: contiguous 1-D copies stay on the DMA path
-                out[a, s0:s1].copy_(buf[a, :s1 - s0], non_blocking=True)
-            ev = torch.cuda.Event()
-            ev.record(copier)
-            free_ev[k & 1] = ev
-        k += 1
-    copier.synchronize()
+    with eng.hold_stream():
+        st = StackTables(ii, desc, stack, ko, eng.device)
+        w, _ = eng.solve_stack(st, f"stack {stack}")
+        src = eng.pack(st, w)
+        if out is None:
+            out = torch.empty((4, m), dtype=F64, pin_memory=True)
+        gd = regular_descriptor(g)
+        nyz = int(g.regular_grid_shape[1] * g.regular_grid_shape[2])
+        # slabs aligned to whole x planes when possible (keeps every slab on the z-run kernel)
+        per = max(1, -(-m // max(1, n_slabs)))
+        if per > nyz:
+            per = -(-per // nyz) * nyz
+        compute = torch.cuda.current_stream(eng.device)
+        copier = torch.cuda.Stream(eng.device)
+        bufs = [eng.empty(4, per) for _ in range(2)]
+        free_ev = [None, None]
+        k = 0
+        for s0 in range(0, m, per):
+            s1 = min(m, s0 + per)
+            buf = bufs[k & 1]
+            if free_ev[k & 1] is not None:
+                compute.wait_event(free_ev[k & 1])          # the copy that used this buffer has finished
+            seg = Segment("dense_grid", s1 - s0, grid=gd, i0=i0 + s0)
+            eng.evaluate_segment(st, src, seg, 0, buf[0], buf[1:], None)
+            done = torch.cuda.Event()
+            done.record(compute)
+            with torch.cuda.stream(copier):
+                copier.wait_event(done)
+                for a in range(4):                          # row by row: contiguous 1-D copies stay on the DMA path
+                    out[a, s0:s1].copy_(buf[a, :s1 - s0], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copier)
+                free_ev[k & 1] = ev
+            k += 1
+        copier.synchronize()
     return out
 
 
 # ------------------------------------------------------------------------------------------------ materialisation
 def _np(t: Optional[torch.Tensor]) -> Optional[np.ndarray]:
-    return None if t is None else t.detach().cpu().numpy()
+    """Device tensor -> numpy.  Row-strided 2-D float64 views (slices of a level's buffers) are packed with a 2-D copy on
+    the copy engine first, so that no elementwise kernel is launched for a read-back."""
+    if t is None:
+        return None
+    t = t.detach()
+    if t.is_cuda and not t.is_contiguous() and t.dim() == 2 and t.stride(1) == 1 and t.dtype == F64 and t.shape[1] > 0:
+        tmp = torch.empty(t.shape, dtype=F64, device=t.device)
+        with torch.cuda.device(t.device):
+            _lib.check(_lib.lib().gpb_copy_2d(_ptr(tmp), tmp.stride(0), _ptr(t), t.stride(0), t.shape[0], t.shape[1],
+                                              torch.cuda.current_stream(t.device).cuda_stream))
+        t = tmp
+    return t.cpu().numpy()
 
 
-def _level_outputs(f: FieldsOnDevice, grid: EngineGrid, rel_enum: Sequence) -> List[InterpOutput]:
+def _level_outputs(f: FieldsOnDevice, grid: EngineGrid, rel_enum: Sequence, iso_host=None) -> List[InterpOutput]:
     """Host containers over the device results; every array is copied on first access only."""
     D = Deferred
     fb = D(lambda: _np(f.final_block))
@@ -572,7 +626,8 @@ def _level_outputs(f: FieldsOnDevice, grid: EngineGrid, rel_enum: Sequence) -> L
     outs = []
     for i in range(f.Z.shape[0]):
         g = (None, None, None) if f.G is None else tuple(D(lambda i=i, a=a: _np(f.G[i, a])) for a in range(3))
-        ef = ExportedFields(D(lambda i=i: _np(f.Z[i])), g[0], g[1], g[2], f.grid_size, D(lambda i=i: _np(f.isovalues[i])))
+        iso = D(lambda i=i: iso_host(i).copy()) if iso_host is not None else D(lambda i=i: _np(f.isovalues[i]))
+        ef = ExportedFields(D(lambda i=i: _np(f.Z[i])), g[0], g[1], g[2], f.grid_size, iso)
         sfo = ScalarFieldOutput(D(lambda i=i: _np(f.weights[i])), grid, ef, D(lambda i=i: _np(f.block[i])[None, :]),
                                 rel_enum[i], D(lambda i=i: _np(f.mask[i]).astype(bool)))
         comb = CombinedScalarFieldsOutput(D(lambda i=i: _np(f.squeezed[i]).astype(bool)), fb, fa)
@@ -580,67 +635,55 @@ def _level_outputs(f: FieldsOnDevice, grid: EngineGrid, rel_enum: Sequence) -> L
     return outs
 
 
-def _fill_regular_from_octree(levels_host, base_shape: np.ndarray, key) -> np.ndarray:
-    """Dense array at the finest octree resolution: level-0 values upsampled, refined voxels overwritten by their
-    children (the engine's octree -> regular fill used by RawArraysSolution)."""
-    shape = np.asarray(base_shape, dtype=int)
-    vals = np.asarray(key(levels_host[0])).reshape(shape)
-    # index arrays of the voxels of each level inside the level's full lattice
-    ijk = np.stack(np.meshgrid(*[np.arange(s) for s in shape], indexing="ij"), axis=-1).reshape(-1, 3)
-    dense = vals
-    for lvl in range(1, len(levels_host)):
-        sel = levels_host[lvl - 1]["selected"]
-        sel = sel.get() if isinstance(sel, Deferred) else sel
-        dense = dense.repeat(2, axis=0).repeat(2, axis=1).repeat(2, axis=2)
-        parents = ijk[sel]
-        off = np.array([[i, j, k] for i in (0, 1) for j in (0, 1) for k in (0, 1)])
-        ijk = (parents[:, None, :] * 2 + off[None, :, :]).reshape(-1, 3)
-        v = key(levels_host[lvl])
-        dense[ijk[:, 0], ijk[:, 1], ijk[:, 2]] = v
-    return dense.ravel()
+def _lattice(root: RegularGrid, level: int) -> _lib.GpbRegularGrid:
+    """Voxel lattice of octree level `level` (0 = root): centre of cell (0, 0, 0) with the grid shift, cell size, cells."""
+    e, s = root.orthogonal_extent, root.regular_grid_shape * (2 ** level)
+    d = np.array([(e[1] - e[0]) / s[0], (e[3] - e[2]) / s[1], (e[5] - e[4]) / s[2]])
+    return _lib.GpbRegularGrid(e[0] + d[0] / 2 + GRID_SHIFT, e[2] + d[1] / 2 + GRID_SHIFT, e[4] + d[2] / 2 + GRID_SHIFT,
+                               d[0], d[1], d[2], int(s[0]), int(s[1]), int(s[2]))
 
 
-# ------------------------------------------------------------------------------------------------ triangulation
-def triangulate(valid: np.ndarray, ijk: np.ndarray) -> np.ndarray:
-    """Quads (as two triangles) around every crossed edge shared by four existing surface voxels; vertex index =
-    rank among voxels with at least one crossing (same rule as oracle.dual_contour_triangles, vectorised)."""
-    vv = valid.any(axis=1)
-    k = ijk[vv].astype(np.int64)
-    val = valid[vv]
-    if k.shape[0] == 0:
-        return np.zeros((0, 3), dtype=np.int64)
-    lo = k.min(axis=0) - 1
-    span = k.max(axis=0) - lo + 2
-    code = lambda a: ((a[:, 0] - lo[0]) * span[1] + (a[:, 1] - lo[1])) * span[2] + (a[:, 2] - lo[2])
-    codes = code(k)
-    order = np.argsort(codes, kind="stable")
-    sorted_codes = codes[order]
+def _fill_regular_from_octree(eng: B200Engine, levels_dev, root: RegularGrid, which: str) -> np.ndarray:
+    """Dense array at the finest octree resolution, on the device: every level's lattice is the level above repeated
+    twice per axis with the level's own voxels written over it (the engine's octree -> regular fill used by
+    RawArraysSolution).  levels_dev: [(centers [3, nv] view, nv, FieldsOnDevice)]."""
+    with eng.hold_stream():
+        dense = None
+        for lvl, (centers, nv, f) in enumerate(levels_dev):
+            lat = _lattice(root, lvl)
+            cur = eng.empty(lat.nx * lat.ny * lat.nz)
+            if dense is not None:
+                _lib.check(eng.lib.gpb_upsample2(_ptr(dense), lat.nx // 2, lat.ny // 2, lat.nz // 2, _ptr(cur), eng.stream))
+            vals = f.final_block if which == "lith" else f.faults_block
+            _lib.check(eng.lib.gpb_scatter_lattice(_ptr(centers), centers.stride(0), nv, C.byref(lat), _ptr(vals), 1, _ptr(cur),
+                                                   eng.stream))
+            dense = cur
+        return _np(dense)
 
-    def find(a):
-        c = code(a)
-        pos = np.searchsorted(sorted_codes, c)
-        pos = np.clip(pos, 0, len(sorted_codes) - 1)
-        ok = sorted_codes[pos] == c
-        return np.where(ok, order[pos], -1)
 
-    tris = []
-    hh_edge = {0: 3, 1: 7, 2: 11}
-    others = {0: (1, 2), 1: (0, 2), 2: (0, 1)}
-    for ax in range(3):
-        e = hh_edge[ax]
-        u, v = others[ax]
-        n = np.nonzero(val[:, e])[0]
-        if n.size == 0:
-            continue
-        ku = k[n].copy(); ku[:, u] += 1
-        kv = k[n].copy(); kv[:, v] += 1
-        kuv = ku.copy(); kuv[:, v] += 1
-        a, b, c = find(ku), find(kv), find(kuv)
-        ok = (a >= 0) & (b >= 0) & (c >= 0)
-        n, a, b, c = n[ok], a[ok], b[ok], c[ok]
-        t = np.stack([np.stack([n, a, c], axis=1), np.stack([n, c, b], axis=1)], axis=1).reshape(-1, 3)
-        tris.append(t)
-    return np.concatenate(tris).astype(np.int64) if tris else np.zeros((0, 3), dtype=np.int64)
+_UNSUPPORTED_WARNED = set()
+
+
+def _warn_unsupported(options: InterpolationOptions, ii: InterpolationInput) -> None:
+    """Engine options this backend accepts but does not act on: say so once instead of silently ignoring them."""
+    eo = options.evaluation_options
+    notes = []
+    if float(getattr(eo, "octree_curvature_threshold", -1.0)) != -1.0:
+        notes.append("evaluation_options.octree_curvature_threshold (refinement is by corner ids only)")
+    if float(getattr(eo, "octree_error_threshold", 1.0)) != 1.0:
+        notes.append("evaluation_options.octree_error_threshold (refinement is by corner ids only)")
+    mo = getattr(eo, "mesh_extraction_masking_options", MeshExtractionMaskingOptions.INTERSECT)
+    if getattr(mo, "name", mo) not in ("INTERSECT", 3):
+        notes.append("evaluation_options.mesh_extraction_masking_options (meshes are masked by the squeezed stack mask = INTERSECT)")
+    if int(getattr(eo, "evaluation_chunk_size", 500_000)) != 500_000:
+        notes.append("evaluation_options.evaluation_chunk_size (the kernel matrix is never materialised: nothing to chunk)")
+    if ii.weights:
+        notes.append("interpolation_input.weights (the direct solver needs no warm start: every call assembles and solves again, "
+                     "so edited inputs can never meet stale weights; cache_mode has nothing to select)")
+    for n in notes:
+        if n not in _UNSUPPORTED_WARNED:
+            _UNSUPPORTED_WARNED.add(n)
+            warnings.warn("gempy_b200: option without effect in this backend: " + n, stacklevel=3)
 
 
 # ------------------------------------------------------------------------------------------------ entry point
@@ -649,7 +692,8 @@ def compute_model(interpolation_input: InterpolationInput, options: Interpolatio
                   engine: Optional[B200Engine] = None, comm: Optional[Comm] = None) -> Solutions:
     """Drop-in for ``gempy_engine.compute_model`` (same positional/keyword signature; the keyword-only extras
     select the CUDA device and, for one-process-per-GPU runs, the torch.distributed group).  Every rank returns
-    the same, complete ``Solutions``.  Raises ``NotImplementedError`` for geophysics input."""
+    the same, complete ``Solutions``.  Raises ``NotImplementedError`` for magnetics input and ``GpbError`` for a
+    singular system."""
     comm = comm or Comm()
     if geophysics_input is not None and interpolation_input.grid.geophysics_grid is None:
         raise ValueError("geophysics_input needs a centered (geophysics) grid")
@@ -670,68 +714,115 @@ def _compute_model(eng: B200Engine, interpolation_input, options, data_descripto
     ko = options.kernel_options
     if grid.octree_grid is None:
         raise ValueError("the engine grid always carries an octree grid (_engine_factory.py:88-96)")
+    _warn_unsupported(options, ii)
 
-    cache: List[Optional[torch.Tensor]] = [None] * n_st
-    if ii.weights:
-        for i, w in enumerate(ii.weights):
-            if w is not None and len(w):
-                cache[i] = torch.as_tensor(np.asarray(w, dtype=np.float64), device=eng.device)
-    tables = ModelTables(ii, desc, ko, eng.device)
-
+    tables = ModelTables(eng, ii, desc, options)
+    n_sp = int(tables.sp_all.shape[1])
+    gradient = bool(eo.compute_scalar_gradient)
     n_levels = int(eo.number_octree_levels)
     dc_level = min(int(eo.number_octree_levels_surface), n_levels) - 1 if eo.mesh_extraction else -1
-    centers, d = regular_centers_device(grid.octree_grid, eng.device)
-    extra_full: List[Segment] = []
-    if grid.dense_grid is not None:
-        extra_full.append(Segment("dense_grid", grid.dense_grid.n_points, grid=regular_descriptor(grid.dense_grid)))
+    root = grid.octree_grid
+    d = root.dxdydz.copy()
+
+    # explicit point sets of level 0 besides the octree centres (host tables; uploaded straight into the level's buffer)
+    extras_host: List[Tuple[str, np.ndarray]] = []
     for name in ("custom_grid", "topography", "sections", "geophysics_grid"):
         g = getattr(grid, name)
         if g is not None:
-            extra_full.append(Segment(name, g.n_points,
-                                      xyz=torch.as_tensor(np.ascontiguousarray(g.values.T), dtype=F64, device=eng.device)))
-
-    def local_part(seg: Segment) -> Segment:
-        """This rank's contiguous share of a segment."""
-        i0, i1 = comm.shard(seg.m)
-        if seg.grid is not None:
-            return Segment(seg.name, i1 - i0, grid=seg.grid, i0=seg.i0 + i0)
-        return Segment(seg.name, i1 - i0, xyz=seg.xyz[:, i0:i1].contiguous())
+            extras_host.append((name, np.ascontiguousarray(np.asarray(g.values, dtype=np.float64).T)))
+    dense_desc = regular_descriptor(grid.dense_grid) if grid.dense_grid is not None else None
 
     octree_levels: List[OctreeLevel] = []
-    levels_host = []
-    prev_regular = grid.octree_grid
+    levels_dev = []
+    prev_regular = root
     dc_payload = None
     gravity = None
+    centers_full: Optional[torch.Tensor] = None        # [3, nv] (possibly a strided view) of the current level
+    pending = None                                      # (parent centres, nv_parent, d_parent, mark, offsets) of the next emission
+    nv = int(np.prod(root.regular_grid_shape))
     for lvl in range(n_levels):
         need_corners = (lvl < n_levels - 1) or (lvl == dc_level)
-        nv = centers.shape[1]
         v0, v1 = comm.shard(nv)
-        centers_loc = centers[:, v0:v1].contiguous()
-        segs = [Segment("octree_grid", v1 - v0, xyz=centers_loc)]
+        nvl = v1 - v0
+        parts: List[Tuple[str, int]] = [("octree_grid", nvl)]
         totals = [nv]
+        dense = None
+        ex_loc = []
         if lvl == 0:
-            for sg in extra_full:
-                segs.append(local_part(sg))
-                totals.append(sg.m)
-        corners = None
+            if dense_desc is not None:
+                i0, i1 = comm.shard(grid.dense_grid.n_points)
+                dense = (dense_desc, i0, i1 - i0)
+                totals.append(grid.dense_grid.n_points)
+            for name, vals in extras_host:
+                i0, i1 = comm.shard(vals.shape[1])
+                ex_loc.append((name, vals[:, i0:i1]))
+                parts.append((name, i1 - i0))
+                totals.append(vals.shape[1])
         if need_corners:
-            corners_loc = eng.corners_of(centers_loc, d)
-            segs.append(Segment("corners", corners_loc.shape[1], xyz=corners_loc))
+            parts.append(("corners", 8 * nvl))
             totals.append(8 * nv)
-            corners = corners_loc if comm.world == 1 else eng.corners_of(centers, d)
-        f_loc = eng.interpolate_all_fields(ii, options, desc, segs, cache, tables=tables, comm=comm)
+        parts.append(("surface_points", n_sp))
+        Lx = sum(c for _, c in parts)
+        xyz = eng.empty(3, Lx)
+        # ---- this level's voxel centres
+        if lvl == 0:
+            ax = root.axis_coords()
+            gx, gy, gz = np.meshgrid(*ax, indexing="ij")
+            c_host = np.stack([gx.ravel(), gy.ravel(), gz.ravel()]) + GRID_SHIFT
+            c_dev = torch.as_tensor(c_host, dtype=F64, device=eng.device)
+            if comm.world == 1:
+                eng.copy_rows(xyz[:, :nv], c_dev)
+                centers_full = xyz[:, :nv]
+            else:
+                centers_full = c_dev
+        else:
+            p_cen, p_nv, p_d, p_mark, p_off = pending
+            if comm.world == 1:
+                eng.emit_into(p_cen, p_nv, p_d, p_mark, p_off, xyz)          # children land in the level's buffer directly
+                centers_full = xyz[:, :nv]
+            else:
+                centers_full = eng.empty(3, nv)
+                eng.emit_into(p_cen, p_nv, p_d, p_mark, p_off, centers_full)
+        if comm.world > 1 and nvl:
+            eng.copy_rows(xyz[:, :nvl], centers_full[:, v0:v1])
+        off = nvl
+        for name, vals in ex_loc:
+            k = vals.shape[1]
+            if k:
+                eng.copy_rows(xyz[:, off:off + k], torch.as_tensor(np.ascontiguousarray(vals), dtype=F64, device=eng.device))
+            off += k
+        corners_loc = None
+        if need_corners:
+            corners_loc = xyz[:, off:off + 8 * nvl]
+            eng.corners_into(xyz, nvl, d, corners_loc)
+            off += 8 * nvl
+        eng.copy_rows(xyz[:, off:off + n_sp], tables.sp_all)
+        # ---- all stacks (one native call on a single rank)
+        f_loc = eng.run_level(tables, xyz, parts, dense, solve=(lvl == 0), gradient=gradient, comm=comm)
+        f_loc._xyz = xyz                                  # keeps the centres / corners views alive with the fields
+        if lvl == 0 and getattr(ko, "compute_condition_number", False):
+            conds = []
+            for i, st in enumerate(tables):
+                A, _ = eng.assemble(st)
+                conds.append(float(torch.linalg.cond(A).item()))
+                del A
+            f_loc.cond = conds
+            ko.condition_number = conds[-1]
         # ---- refinement marks: local test, all-gathered so that every rank emits the identical child list
         mark_full = None
         if lvl < n_levels - 1:
-            csl = f_loc.seg_slice("corners")
-            mark_loc = eng.mark(v1 - v0, f_loc.final_block[csl].contiguous(), f_loc.faults_block[csl].contiguous(),
+            c_off = f_loc.seg_offset("corners")
+            mark_loc = eng.mark(nvl, f_loc.final_block[c_off:c_off + 8 * nvl], f_loc.faults_block[c_off:c_off + 8 * nvl],
                                 force_all=lvl < int(eo.octree_min_level))
             mark_full = comm.all_gather_cat(mark_loc, nv)
         f = eng.gather_fields(f_loc, totals, comm)
+        corners = corners_loc
+        if comm.world > 1 and need_corners:
+            corners = eng.corners_of(centers_full, d)
         # ---- host containers of this level
-        centers_host = Deferred(lambda c=centers: _np(c).T.copy())     # explicit centres (shift included), as evaluated
+        centers_host = Deferred(lambda c=centers_full: _np(c).T.copy())     # explicit centres (shift included), as evaluated
         if lvl == 0:
-            og0 = RegularGrid(grid.octree_grid.orthogonal_extent, grid.octree_grid.regular_grid_shape)
+            og0 = RegularGrid(root.orthogonal_extent, root.regular_grid_shape)
             og0._values, og0._n_points = centers_host, nv
             lvl_grid = EngineGrid(octree_grid=og0, dense_grid=grid.dense_grid, topography=grid.topography,
                                   sections=grid.sections, custom_grid=grid.custom_grid,
@@ -741,33 +832,32 @@ def _compute_model(eng: B200Engine, interpolation_input, options, data_descripto
             og._dxdydz, og._n_points = d.copy(), nv
             prev_regular = og
             lvl_grid = EngineGrid(octree_grid=og)
-        outs = _level_outputs(f, lvl_grid, rel_enum)
+        outs = _level_outputs(f, lvl_grid, rel_enum, tables.iso_host)
         level = OctreeLevel(grid_centers=lvl_grid, outputs_centers=outs,
                             _grid_corners=None if corners is None else
                             Deferred(lambda c=corners: EngineGrid.from_xyz_coords(_np(c).T)))
         level._device_fields = f
         octree_levels.append(level)
-        host = {"lith": Deferred(lambda o=outs[-1], nv=nv: np.rint(o.combined_scalar_field.final_block[:nv])),
-                "faults": Deferred(lambda o=outs[-1], nv=nv: np.rint(o.combined_scalar_field.faults_block[:nv])),
-                "selected": None}
-        levels_host.append(host)
+        levels_dev.append((centers_full, nv, f))
         if lvl == 0 and geophysics_input is not None:
             gravity = _forward_gravity(eng, geophysics_input, grid.geophysics_grid, f)
         if lvl == dc_level:
-            dc_payload = (centers, d.copy(), corners, f)
+            dc_payload = (lvl, centers_full, d.copy(), corners, f)
         if lvl == n_levels - 1:
             break
         level._marked_voxels = Deferred(lambda mk=mark_full: _np(mk).astype(bool))
-        host["selected"] = level._marked_voxels
-        centers = eng.emit(centers, d, mark_full)
+        n_marked, offsets = eng.count_marked(mark_full)
+        pending = (centers_full, nv, d.copy(), mark_full, offsets)
+        nv = 8 * n_marked
         d = d / 2
 
     meshes = None
     if eo.mesh_extraction and dc_payload is not None:
-        meshes = _dual_contouring(eng, ii, options, desc, tables, cache, dc_payload, grid.octree_grid)
+        meshes = _dual_contouring(eng, tables, dc_payload, root)
 
     sol = Solutions(octree_levels, meshes, gravity, options.block_solutions_type)
-    sol.raw_arrays = _raw_arrays(sol, levels_host, grid, options, meshes)
+    sol.raw_arrays = _raw_arrays(eng, sol, levels_dev, grid, options, meshes)
+    sol._tables = tables            # device tables + the native model handle live as long as the lazy outputs
     return sol
 
 
@@ -785,63 +875,72 @@ def _forward_gravity(eng: B200Engine, geophysics_input, centered_grid, f: Fields
     if tz_d.shape[0] != n_k:
         raise ValueError(f"tz has {tz_d.shape[0]} entries, the centered grid kernel has {n_k} voxels")
     sl = f.seg_slice("geophysics_grid")
-    block = f.final_block[sl].contiguous()
+    block = f.final_block[sl]
     out = eng.empty(n_centers)
     _lib.check(eng.lib.gpb_gravity(_ptr(block), _ptr(dens_d), int(dens_d.shape[0]), _ptr(tz_d), n_centers, n_k, _ptr(out),
                                    eng.stream))
     return _np(out)
 
 
-def _dual_contouring(eng: B200Engine, ii, options, desc, tables, cache, payload, root_grid) -> List[DualContouringMesh]:
-    centers, d, corners, f = payload
-    nv = centers.shape[1]
-    csl = f.seg_slice("corners")
-    e = root_grid.orthogonal_extent
-    ijk = np.rint((_np(centers).T - GRID_SHIFT - e[[0, 2, 4]]) / d - 0.5).astype(np.int64)
-    ss = desc.stack_structure
-    rel = [_rel_code(r) for r in ss.masking_descriptor]
+class _DeviceMesh:
+    """Device buffers of one dual-contoured surface (worst-case sized) and its three counts; trimmed and copied to the
+    host when the mesh is first read."""
+
+    def __init__(self, nv, counts, verts, tris, valid, xyz_c, grad_c):
+        self.nv, self.counts, self.verts, self.tris, self.valid, self.xyz_c, self.grad_c = nv, counts, verts, tris, valid, xyz_c, grad_c
+        self._n = None
+
+    def n(self):
+        if self._n is None:
+            self._n = [int(v) for v in self.counts.cpu().numpy()]
+        return self._n
+
+    def vertices(self) -> np.ndarray:
+        V = self.n()[1]
+        return _np(self.verts[:, :V]).T.copy()
+
+    def triangles(self) -> np.ndarray:
+        T = self.n()[2]
+        return _np(self.tris[:T]).astype(np.int64)
+
+    def dc_data(self) -> DualContouringData:
+        E = self.n()[0]
+        valid = _np(self.valid).astype(bool).reshape(self.nv, 12)
+        return DualContouringData(_np(self.xyz_c[:, :E]).T.copy(), valid, _np(self.grad_c[:, :E]).T.copy())
+
+
+def _dual_contouring(eng: B200Engine, tables: ModelTables, payload, root: RegularGrid) -> List[DualContouringMesh]:
+    """Every surface of every stack on the surface level, queued without a host round trip (gpb_dual_contour); the meshes
+    are read back lazily."""
+    lvl, centers, d, corners, f = payload
+    nv = int(centers.shape[1])
+    c_off = f.seg_offset("corners")
+    lat = _lattice(root, lvl)
     lib = eng.lib
-    # pass 1: every surface's device work is queued without a host round trip; the results start their way to the host
-    # on the same stream (non-blocking copies).  pass 2 triangulates on the host while later surfaces still run.
-    pending = []
-    for i in range(ss.n_stacks):
-        Zc = f.Z[i, csl].contiguous()
-        if rel[i] == StackRelationType.FAULT.value:
-            own = None
-        else:
-            own = eng.empty(nv, dtype=torch.uint8)
-            sq = f.squeezed[i, csl].contiguous()
-            _lib.check(lib.gpb_any8(_ptr(sq), nv, _ptr(own), eng.stream))
-        iso_host = _np(f.isovalues[i])
-        for s_idx, iso in enumerate(iso_host):
-            valid = eng.empty(12 * nv, dtype=torch.uint8)
-            xyz_e = eng.empty(3, 12 * nv)
-            _lib.check(lib.gpb_dc_edges(_ptr(corners), 8 * nv, _ptr(Zc), nv, float(iso), _ptr(own), _ptr(valid),
-                                        _ptr(xyz_e), eng.stream))
-            # gradient of stack i's field at the crossings: one more fused evaluation on the edge points
-            grad = eng.gradient_at(tables[i], f.srcs[i], xyz_e)
-            verts = eng.empty(3, nv)
-            _lib.check(lib.gpb_dc_vertices(_ptr(valid), _ptr(xyz_e), _ptr(grad), nv, 1.0, _ptr(verts), eng.stream))
-            host = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in (valid, verts, xyz_e, grad)]
-            for h, t in zip(host, (valid, verts, xyz_e, grad)):
-                h.copy_(t, non_blocking=True)
-            done = torch.cuda.Event()
-            done.record(torch.cuda.current_stream(eng.device))
-            pending.append((host, done, (valid, verts, xyz_e, grad)))       # device tensors stay alive until copied
+    n_bytes = int(lib.gpb_dc_scratch_bytes(nv))
+    scratch = eng.empty((n_bytes + 7) // 8)              # shared by all surfaces: the calls are ordered on one stream
     meshes: List[DualContouringMesh] = []
-    for host, done, _keep in pending:
-        done.synchronize()
-        valid_h = host[0].numpy().astype(bool).reshape(nv, 12)
-        verts_h = host[1].numpy().T
-        keep = valid_h.any(axis=1)
-        tris = triangulate(valid_h, ijk)
-        flat = valid_h.ravel()
-        data = DualContouringData(host[2].numpy().T[flat], valid_h, host[3].numpy().T[flat])
-        meshes.append(DualContouringMesh(verts_h[keep], tris, data))
+    for i, st in enumerate(tables):
+        sct = st.struct()
+        Zc = _ptr(f.Z[i], 8 * c_off)
+        sq = None if tables.rel[i] == StackRelationType.FAULT.value else _ptr(f.squeezed[i], c_off)
+        for s_idx in range(st.n_surf):
+            counts = eng.empty(3, dtype=torch.int64)
+            verts = eng.empty(3, max(nv, 1))
+            tris = eng.empty(max(6 * nv, 1), 3, dtype=torch.int32)
+            valid = eng.empty(max(12 * nv, 1), dtype=torch.uint8)
+            xyz_c = eng.empty(3, max(12 * nv, 1))
+            grad_c = eng.empty(3, max(12 * nv, 1))
+            _lib.check(lib.gpb_dual_contour(C.byref(sct), _ptr(tables.eval_tables[i]), _ptr(corners), corners.stride(0), Zc, sq,
+                                            _ptr(centers), centers.stride(0), nv, _ptr(tables.isovalues[i], 8 * s_idx),
+                                            C.byref(lat), 1.0, _ptr(scratch), n_bytes, _ptr(valid), _ptr(xyz_c), _ptr(grad_c),
+                                            _ptr(verts), _ptr(tris), _ptr(counts), eng.stream))
+            dm = _DeviceMesh(nv, counts, verts, tris, valid, xyz_c, grad_c)
+            meshes.append(DualContouringMesh(Deferred(dm.vertices), Deferred(dm.triangles), Deferred(dm.dc_data)))
     return meshes
 
 
-def _raw_arrays(sol: Solutions, levels_host, grid: EngineGrid, options, meshes) -> RawArraysSolution:
+def _raw_arrays(eng: B200Engine, sol: Solutions, levels_dev, grid: EngineGrid, options, meshes) -> RawArraysSolution:
     """RawArraysSolution over the level-0 outputs (dense grid) or the octree -> regular fill; lazy."""
     ra = RawArraysSolution()
     first = sol.octrees_output[0]
@@ -850,18 +949,16 @@ def _raw_arrays(sol: Solutions, levels_host, grid: EngineGrid, options, meshes) 
     g0 = first.grid_centers
     fb = lambda: last.combined_scalar_field.final_block
     fa = lambda: last.combined_scalar_field.faults_block
-    lith = lambda h: h["lith"].get()
-    faul = lambda h: h["faults"].get()
     sl = None
     if options.block_solutions_type == BlockSolutionType.DENSE_GRID and grid.dense_grid is not None:
         sl = g0.dense_grid_slice
         ra.set_lazy("lith_block", lambda: np.rint(fb()[sl]))
         ra.set_lazy("fault_block", lambda: np.rint(fa()[sl]))
     elif options.block_solutions_type == BlockSolutionType.OCTREE:
-        base = grid.octree_grid.regular_grid_shape
-        sl = slice(0, int(np.prod(base)))
-        ra.set_lazy("lith_block", lambda: _fill_regular_from_octree(levels_host, base, lith))
-        ra.set_lazy("fault_block", lambda: _fill_regular_from_octree(levels_host, base, faul))
+        root = grid.octree_grid
+        sl = slice(0, int(np.prod(root.regular_grid_shape)))
+        ra.set_lazy("lith_block", lambda: _fill_regular_from_octree(eng, levels_dev, root, "lith"))
+        ra.set_lazy("fault_block", lambda: _fill_regular_from_octree(eng, levels_dev, root, "faults"))
     if sl is not None:
         ra.set_lazy("scalar_field_matrix", lambda: np.stack([o.exported_fields.scalar_field_everywhere[sl] for o in outs]))
         ra.set_lazy("block_matrix", lambda: np.stack([o.scalar_fields.values_block[0, sl] for o in outs]))
@@ -877,6 +974,6 @@ def _raw_arrays(sol: Solutions, levels_host, grid: EngineGrid, options, meshes) 
         if s_.stop > s_.start:
             ra.set_lazy(name, lambda s_=s_: np.rint(fb()[s_]))
     if meshes is not None:
-        ra.vertices = [m.vertices for m in meshes]
-        ra.edges = [m.edges for m in meshes]
+        ra.set_lazy("vertices", lambda: [m.vertices for m in meshes])
+        ra.set_lazy("edges", lambda: [m.edges for m in meshes])
     return ra

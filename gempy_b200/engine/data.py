@@ -714,11 +714,38 @@ class DualContouringData:
     gradients: Optional[np.ndarray] = None
 
 
-@dataclass
 class DualContouringMesh:
-    vertices: np.ndarray
-    edges: np.ndarray
-    dc_data: Optional[DualContouringData] = None
+    """``dc_meshes[e]`` of the engine's Solutions: ``vertices`` (V, 3) float64, ``edges`` (T, 3) int64 triangles, ``dc_data``
+    (gempy/core/data/geo_model.py:110-121 reads the first two).  The B200 path hands in ``Deferred`` values: the mesh stays
+    on the device until an attribute is read."""
+
+    def __init__(self, vertices, edges, dc_data=None):
+        self._vertices = vertices
+        self._edges = edges
+        self._dc_data = dc_data
+
+    @property
+    def vertices(self) -> np.ndarray:
+        self._vertices = _res(self._vertices)
+        return self._vertices
+
+    @vertices.setter
+    def vertices(self, v):
+        self._vertices = v
+
+    @property
+    def edges(self) -> np.ndarray:
+        self._edges = _res(self._edges)
+        return self._edges
+
+    @edges.setter
+    def edges(self, v):
+        self._edges = v
+
+    @property
+    def dc_data(self) -> Optional[DualContouringData]:
+        self._dc_data = _res(self._dc_data)
+        return self._dc_data
 
     @property
     def vertices_tensor(self):
@@ -735,12 +762,11 @@ class RawArraysSolution:
         "scalar_field_matrix": lambda: np.empty((0, 0)), "block_matrix": lambda: np.empty((0, 0)),
         "mask_matrix": lambda: np.empty((0, 0)), "mask_matrix_squeezed": lambda: np.empty((0, 0)),
         "custom": lambda: None, "topography": lambda: None, "sections": lambda: None, "dense_ids": lambda: None,
+        "vertices": list, "edges": list,
     }
 
     def __init__(self):
         self._lazy = {}
-        self.vertices: list = []
-        self.edges: list = []
 
     def set_lazy(self, name: str, fn) -> None:
         self._lazy[name] = fn

@@ -160,6 +160,82 @@ int gpb_combine(const double* Z, const double* block, long long ld, long long m,
                 double* final_block, double* faults_block, unsigned char* squeezed_mask, unsigned char* mask,
                 void* stream);
 
+/* ---- level executor: every stack of a model on one evaluation domain  [engine stage interpolate_all_fields] ------
+ * One C call per octree level replaces the per-stack Python loop of the reference (and of round 1 of this backend):
+ * solve (level 0), fused evaluation + fault drift + activator per stack, combination.  All device buffers belong to the
+ * caller; the handle stores the description.  Stacks are processed in order; a stack's fault drift comes from EARLIER
+ * fault stacks (reference: structural_frame.py:243-273 fault_relations, upper triangular). */
+typedef struct gpb_model_stack {
+    gpb_stack st;                  /* tables of the stack; st.fault_rest / st.fault_ref: caller-allocated
+                                      [n_faults][n_rest] buffers FILLED by gpb_model_solve_stack */
+    int relation;                  /* GPB_REL_* */
+    const int* fault_stacks_host;  /* host [st.n_faults]: indices of the fault stacks drifting this one (read at create) */
+    const int* fault_stacks_dev;   /* the same list on the device */
+    int sp_begin;                  /* first surface point of the stack in the model-wide table */
+    int n_sp;                      /* its surface points (n_rest + n_surf) */
+    const double* unit_ids;        /* device [n_surf + 1] unit values of the surfaces + the unit below */
+    double* weights;               /* device [n] out */
+    double* eval_table;            /* device [gpb_eval_table_doubles()] out */
+    double* isovalues;             /* device [n_surf] out: scalar field at each surface's reference point */
+} gpb_model_stack;
+
+typedef struct gpb_model_desc {
+    int n_stacks;                  /* <= 64 */
+    const gpb_model_stack* stacks; /* host [n_stacks] */
+    const double* sp_all;          /* device [3][n_sp_all]: every surface point of the model, stack after stack */
+    long long n_sp_all;
+    double sigmoid_slope;
+    double* iso_min;               /* device [n_stacks] out */
+    double* iso_max;               /* device [n_stacks] out */
+    double* fault_min;             /* device [n_stacks] out: minimum of each fault stack's block on the current level */
+    int solver;                    /* 0: symmetric path, pivoted LU for n <= 160 or when not positive definite; 1: LU only */
+} gpb_model_desc;
+
+#define GPB_SEG_POINTS  0
+#define GPB_SEG_REGULAR 1
+typedef struct gpb_segment {
+    int kind;
+    long long count;               /* points of the segment */
+    long long out_offset;          /* their position in the level's outputs */
+    const double* xyz;             /* POINTS: device [3][ld_xyz] */
+    long long ld_xyz;
+    gpb_regular_grid grid;         /* REGULAR */
+    long long i0;                  /* REGULAR: first grid index */
+} gpb_segment;
+
+typedef struct gpb_level {
+    long long ld;                  /* leading dimension of the outputs (>= out_offset + count of every segment) */
+    int n_segments;
+    const gpb_segment* segments;   /* host [n_segments] */
+    long long sp_offset;           /* output position of the surface-point tail (sp_all, n_sp_all points, evaluated by one
+                                      of the segments), or -1; level 0 needs it */
+    double* Z;                     /* [n_stacks][ld] */
+    double* G;                     /* [n_stacks][3][ld] or NULL */
+    double* block;                 /* [n_stacks][ld] activator output */
+    double* final_block;           /* [ld] */
+    double* faults_block;          /* [ld] */
+    unsigned char* squeezed;       /* [n_stacks][ld] */
+    unsigned char* mask;           /* [n_stacks][ld] or NULL */
+} gpb_level;
+
+typedef struct gpb_model gpb_model;
+int  gpb_model_create(const gpb_model_desc* desc, gpb_model** out);
+void gpb_model_destroy(gpb_model* m);
+/* Assemble + solve stack i (weights, evaluation table, isovalues).  The earlier fault stacks must have been evaluated on
+ * `level0` (their block rows and minima feed the fault-drift columns).  Synchronises the stream (reads the solver's
+ * info); GPB_E_SINGULAR on a zero pivot.  path_host (may be NULL): 1 = symmetric path, 2 = pivoted LU. */
+int  gpb_model_solve_stack(gpb_model* m, int i, const gpb_level* level0, int* path_host, void* stream);
+/* Fused evaluation of stack i on every segment of the level: Z (+G), block, and for a fault stack the minimum of its
+ * block in fault_min[i] (multi-GPU callers all-reduce it before the next dependent stack). */
+int  gpb_model_eval_stack(gpb_model* m, int i, const gpb_level* lvl, void* stream);
+int  gpb_model_combine(gpb_model* m, const gpb_level* lvl, void* stream);
+/* solve (if `solve`) + evaluate every stack in order, then combine: the single-GPU path, one call per level. */
+int  gpb_model_run_level(gpb_model* m, const gpb_level* lvl, int solve, void* stream);
+int  gpb_model_solver_path(const gpb_model* m, int i);
+
+/* dst[r][0..cols) = src[r][0..cols) for r < rows (device to device, on the copy engine). */
+int gpb_copy_2d(double* dst, long long ld_dst, const double* src, long long ld_src, long long rows, long long cols, void* stream);
+
 /* ---- (4b) octree refinement  [engine stage "octrees_topology"] ----------------------------------- */
 /* Corners of voxels (8 per voxel, sign pattern x:----++++ y:--++--++ z:-+-+-+-+), voxel-major:
  * corner = centre +- (hx, hy, hz); pass the half cell size. */
@@ -174,6 +250,22 @@ int gpb_mark_voxels(const double* lith_corners, const double* fault_corners, lon
 int gpb_emit_children(const double* centers, long long ld_c, long long nvox, const unsigned char* mark,
                       double hx, double hy, double hz, double* children, long long ld_ch,
                       long long* n_children_host, void* stream);
+
+/* The same in two steps without the second synchronisation: gpb_count_marked scans the marks into `offsets`
+ * (gpb_scan_elems(nvox) long longs of device scratch) and returns the number of marked voxels (host; synchronises);
+ * gpb_emit_marked then writes the 8 children of every marked voxel (asynchronous). */
+long long gpb_scan_elems(long long nvox);
+int gpb_count_marked(const unsigned char* mark, long long nvox, long long* offsets, long long* n_marked_host, void* stream);
+int gpb_emit_marked(const double* centers, long long ld_c, long long nvox, const unsigned char* mark,
+                    const long long* offsets, double hx, double hy, double hz, double* children, long long ld_ch,
+                    void* stream);
+
+/* Octree -> regular fill (RawArraysSolution.lith_block of an octree model): dst (2nx x 2ny x 2nz) = src (nx x ny x nz) with
+ * every cell repeated twice per axis; then the level's own voxels overwrite their cells: dst[cell of centre v] = vals[v]
+ * (rint'ed if round_ids), `lattice` = the level's voxel lattice (centre of cell (0,0,0) incl. shift, cell size, cells). */
+int gpb_upsample2(const double* src, int nx, int ny, int nz, double* dst, void* stream);
+int gpb_scatter_lattice(const double* centers, long long ld_c, long long nvox, const gpb_regular_grid* lattice,
+                        const double* vals, int round_ids, double* dst, void* stream);
 
 /* out[v] = 1 if any of in[8v .. 8v+7] is non-zero (voxel ownership from the squeezed mask at its corners). */
 int gpb_any8(const unsigned char* in, long long nvox, unsigned char* out, void* stream);
@@ -192,6 +284,21 @@ int gpb_dc_edges(const double* corners, long long ld_k, const double* Z_corners,
  * grad_edge/xyz_edge: [3][12*nvox]; vertices: [3][nvox] (NaN for voxels without a crossing). */
 int gpb_dc_vertices(const unsigned char* valid, const double* xyz_edge, const double* grad_edge, long long nvox,
                     double bias, double* vertices, void* stream);
+
+/* One surface, entirely on the device and without a host synchronisation: crossings, stable compaction, gradient of the
+ * stack's field at the compacted crossings (fused evaluation kernel), QEF vertices in voxel order, triangulation through a
+ * hash table of the voxel lattice (two triangles per crossed edge shared by four surface voxels; (axis, voxel) order).
+ * corners [3][ld_k] (8 per voxel), Z_corners [8 nvox], sq_corners [8 nvox] squeezed mask of the stack at the corners (NULL:
+ * every voxel), centers [3][ld_c], iso_dev: the isovalue on the device, lattice: the level's voxel lattice (centre of cell
+ * (0,0,0) with the shift, cell size, cells per axis).  Caller-allocated outputs sized for the worst case: valid [12 nvox],
+ * xyz_c and grad_c [3][12 nvox] (compacted crossings / gradients; grad_c may be NULL), vertices [3][nvox] (compacted),
+ * triangles [6 nvox][3], counts [3] = crossings, vertices, triangles (device).  scratch: gpb_dc_scratch_bytes(nvox). */
+long long gpb_dc_scratch_bytes(long long nvox);
+int gpb_dual_contour(const gpb_stack* st, const double* eval_table, const double* corners, long long ld_k,
+                     const double* Z_corners, const unsigned char* sq_corners, const double* centers, long long ld_c,
+                     long long nvox, const double* iso_dev, const gpb_regular_grid* lattice, double bias,
+                     void* scratch, long long scratch_bytes, unsigned char* valid, double* xyz_c, double* grad_c,
+                     double* vertices, int* triangles, long long* counts, void* stream);
 
 /* ---- marching cubes on the dense grid (replaces the skimage.measure.marching_cubes call of
  * gempy/modules/mesh_extranction/marching_cubes.py:82-89) -------------------------------------------------

@@ -901,6 +901,24 @@ def marching_cubes_meshes(fields: "FieldsResult", descriptor, dense_shape, dense
 # ----------------------------------------------------------------------------------------------
 # entry
 # ----------------------------------------------------------------------------------------------
+def fill_regular_from_octree(levels_host, base_shape, key) -> np.ndarray:
+    """Dense array at the finest octree resolution: level-0 values upsampled, refined voxels overwritten by their
+    children (the engine's octree -> regular fill behind RawArraysSolution.lith_block of an octree model; consumers
+    gempy/API/gp2_gp3_compatibility/gp3_to_gp2_output.py:55-88).  levels_host: per level a dict with the values (read
+    through `key`) and "selected" = the refine mask of the level (None on the last)."""
+    shape = np.asarray(base_shape, dtype=int)
+    dense = np.asarray(key(levels_host[0])).reshape(shape)
+    ijk = np.stack(np.meshgrid(*[np.arange(s) for s in shape], indexing="ij"), axis=-1).reshape(-1, 3)
+    for lvl in range(1, len(levels_host)):
+        sel = np.asarray(levels_host[lvl - 1]["selected"], dtype=bool)
+        dense = dense.repeat(2, axis=0).repeat(2, axis=1).repeat(2, axis=2)
+        parents = ijk[sel]
+        off = np.array([[i, j, k] for i in (0, 1) for j in (0, 1) for k in (0, 1)])
+        ijk = (parents[:, None, :] * 2 + off[None, :, :]).reshape(-1, 3)
+        dense[ijk[:, 0], ijk[:, 1], ijk[:, 2]] = key(levels_host[lvl])
+    return dense.ravel()
+
+
 @dataclasses.dataclass
 class OracleSolutions:
     levels: List[OracleLevel]

@@ -1,5 +1,5 @@
 """CPU-only checks: the C-ABI library loads and exports every symbol include/gempy_b200.h declares, the ctypes
-signatures cover the header, host-side logic (data model, example builders, triangulation, octree fill) behaves,
+signatures cover the header, host-side logic (data model, example builders) behaves,
 and nothing in the product package routes through the oracle."""
 import ctypes
 import os
@@ -30,7 +30,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     # the ctypes table binds exactly the header's entry points
     assert sorted(_lib.SIGNATURES) == syms
     lib = _lib.lib()
-    assert lib.gpb_version() == 100
+    assert lib.gpb_version() == 200
     assert lib.gpb_launch_count() == 0          # no compute without a GPU
 
 
@@ -94,26 +94,14 @@ def test_regular_grid_ordering_and_slices():
     assert eg.dense_grid_slice == slice(8, 32) and eg.custom_grid_slice == slice(32, 37)
 
 
-def test_triangulation_matches_oracle_rule():
-    from gempy_b200.engine.compute import triangulate
+def test_octree_to_regular_fill_rule():
+    """The octree -> regular fill rule the device kernels (gpb_upsample2 + gpb_scatter_lattice) are checked against on the
+    GPU (tests/test_gpu_parity.py): refined voxels are overwritten by their children, the others keep the parent value."""
     from oracle import gempy_oracle as orc
-    rng = np.random.default_rng(0)
-    ijk = np.stack(np.meshgrid(np.arange(6), np.arange(5), np.arange(4), indexing="ij"), -1).reshape(-1, 3)
-    valid = rng.random((ijk.shape[0], 12)) < 0.4
-    valid[rng.random(ijk.shape[0]) < 0.3] = False
-    a = triangulate(valid, ijk)
-    b = orc.dual_contour_triangles(valid, ijk)
-    assert a.shape == b.shape and a.shape[0] > 10
-    assert set(map(tuple, a.tolist())) == set(map(tuple, b.tolist()))
-    assert triangulate(np.zeros((4, 12), bool), ijk[:4]).shape == (0, 3)
-
-
-def test_octree_to_regular_fill():
-    from gempy_b200.engine.compute import _fill_regular_from_octree
     base = np.array([2, 2, 2])
     lvl0 = {"lith": np.arange(8, dtype=float), "selected": np.array([1, 0, 0, 0, 0, 0, 0, 1], bool)}
     lvl1 = {"lith": 100 + np.arange(16, dtype=float), "selected": None}
-    dense = _fill_regular_from_octree([lvl0, lvl1], base, lambda h: h["lith"]).reshape(4, 4, 4)
+    dense = orc.fill_regular_from_octree([lvl0, lvl1], base, lambda h: h["lith"]).reshape(4, 4, 4)
     # voxel 0 (i=j=k=0) was refined: its 8 children carry 100..107 in (x slow, z fast) order
     np.testing.assert_array_equal(dense[:2, :2, :2].ravel(), 100 + np.arange(8))
     np.testing.assert_array_equal(dense[2:, 2:, 2:].ravel(), 108 + np.arange(8))

@@ -455,27 +455,49 @@ def test_dense_grid_solution_shape_and_ids():
     np.testing.assert_array_equal(sol.raw_arrays.lith_block, f.lith_ids)
 
 
-def test_dual_contouring_vertices_match_oracle():
-    m = ex.anticline(refinement=4)
+@pytest.mark.parametrize("build,n_meshes", [(lambda: ex.anticline(refinement=4), 2), (lambda: ex.combination(refinement=4), 4),
+                                            (lambda: ex.one_fault(refinement=5), 3)])
+def test_dual_contouring_meshes_match_oracle(build, n_meshes):
+    """Device dual contouring (crossings, compaction, gradients at the crossings, QEF vertices, hash-table triangulation)
+    against the oracle: same vertex set in the same (voxel) order, same triangles."""
+    m = build()
     sol = gc.compute_model(*m.args())
-    ref = orc.compute_model(*ex.anticline(refinement=4).args())
-    assert len(sol.dc_meshes) == len(ref.meshes) == 2
+    ref = orc.compute_model(*build().args())
+    assert len(sol.dc_meshes) == len(ref.meshes) == n_meshes
+    dc_level = min(m.options.number_octree_levels_surface, m.options.number_octree_levels) - 1
+    nv_dc = sol.octrees_output[dc_level].grid_centers.octree_grid.values.shape[0]
     extent_t = 0.5
     for a, b in zip(sol.dc_meshes, ref.meshes):
-        assert a.vertices.shape == b.vertices.shape
+        assert a.vertices.shape == b.vertices.shape and a.vertices.shape[0] > 0
         assert np.abs(a.vertices - b.vertices).max() < 1e-6 * extent_t
+        assert a.edges.shape == b.edges.shape and a.edges.dtype == np.int64
         assert set(map(tuple, a.edges.tolist())) == set(map(tuple, b.edges.tolist()))
+        assert a.dc_data.valid_edges.shape == (nv_dc, 12)
+        assert a.dc_data.xyz_on_edge.shape == a.dc_data.gradients.shape == (int(a.dc_data.valid_edges.sum()), 3)
+    assert [v.shape for v in sol.raw_arrays.vertices] == [m.vertices.shape for m in sol.dc_meshes]
 
 
-def test_weights_reused_when_provided():
+def test_recompute_with_stale_weights_attached_sees_the_edit():
+    """The reference bridge hands the previous solution's weights back on every compute_model after the first
+    (_engine_factory.py:45-48).  They are a solver warm start upstream; the direct solver here needs none, so an edited
+    model must never be answered from them: move one surface point, recompute with the old weights attached, and the
+    field changes exactly as a fresh computation does."""
     m = ex.anticline(refinement=2)
     sol = gc.compute_model(*m.args())
     w = [o.weights for o in sol.root_output.outputs]
-    m2 = ex.anticline(refinement=2)
+    z0 = sol.octrees_output[-1].outputs[0].exported_fields.scalar_field
+    m2, m3 = ex.anticline(refinement=2), ex.anticline(refinement=2)
+    for mm in (m2, m3):
+        mm.interpolation_input.surface_points.sp_coords[5, 2] += 0.01
     m2.interpolation_input.weights = w
-    sol2 = gc.compute_model(*m2.args())
-    np.testing.assert_array_equal(sol2.octrees_output[-1].outputs[0].exported_fields.scalar_field,
-                                  sol.octrees_output[-1].outputs[0].exported_fields.scalar_field)
+    with pytest.warns(UserWarning, match="weights"):
+        gc._UNSUPPORTED_WARNED.clear()
+        sol2 = gc.compute_model(*m2.args())
+    sol3 = gc.compute_model(*m3.args())
+    z2 = sol2.octrees_output[-1].outputs[0].exported_fields.scalar_field
+    z3 = sol3.octrees_output[-1].outputs[0].exported_fields.scalar_field
+    np.testing.assert_array_equal(z2, z3)
+    assert z2.shape != z0.shape or np.abs(z2 - z0).max() > 1e-6
 
 
 # ------------------------------------------------------------------------------------------- more model shapes
@@ -591,6 +613,11 @@ def test_octree_raw_arrays_fill_matches_dense_evaluation():
     lin = (ijk[:, 0] * 16 + ijk[:, 1]) * 16 + ijk[:, 2]
     np.testing.assert_array_equal(lb[lin], f.lith_ids[lin])
     assert set(np.unique(lb)) <= {1.0, 2.0, 3.0}
+    # the device fill (gpb_upsample2 + gpb_scatter_lattice per level) against the oracle's fill rule on the same levels
+    levels_host = [{"lith": np.rint(l.outputs_centers[-1].block[:l.grid_centers.octree_grid.values.shape[0]]),
+                    "selected": l.marked_voxels} for l in sol.octrees_output]
+    np.testing.assert_array_equal(lb, orc.fill_regular_from_octree(levels_host, [2, 2, 2], lambda h: h["lith"]))
+    assert sol.raw_arrays.fault_block.shape == lb.shape
 
 
 # ------------------------------------------------------------------------------------------- size-independent properties
