@@ -351,8 +351,11 @@ class InputDataDescriptor:
     @classmethod
     def from_structural_frame(cls, structural_frame, making_descriptor, faults_relations,
                               faults_input_data=None) -> "InputDataDescriptor":
-        # reads what gempy/core/data/structural_frame.py:333-350 exposes
-        ts = TensorsStructure(np.asarray(structural_frame.number_of_points_per_element))
+        # reads what gempy/core/data/structural_frame.py:333-350 exposes.  structural_elements ends with the basement
+        # element (no surface points: number_of_points_per_element = [..., 0]) while number_of_elements_per_group does not
+        # count it: only the elements that belong to a group describe surfaces.
+        n_surfaces = int(np.sum(structural_frame.number_of_elements_per_group))
+        ts = TensorsStructure(np.asarray(structural_frame.number_of_points_per_element)[:n_surfaces])
         ss = StacksStructure(
             number_of_points_per_stack=structural_frame.number_of_points_per_group,
             number_of_orientations_per_stack=structural_frame.number_of_orientations_per_group,
@@ -485,30 +488,87 @@ class InterpolationOptions:
 
 
 # --------------------------------------------------------------------------- transform
+class GlobalAnisotropy(enum.Enum):
+    """Anisotropy policy of the input transform (gempy/core/data/geo_model.py:274-279,
+    gempy/API/examples_generator.py:60,551)."""
+    CUBE = enum.auto()       # rescale every axis to the unit cube
+    NONE = enum.auto()       # one isotropic scale (the reference examples used here all end up with this)
+    MANUAL = enum.auto()
+
+
 @dataclass
 class Transform:
-    """Minimal input transform: ``x' = (x + position) * scale`` (rotation unsupported, always 0 in
-    the reference's models; gempy/core/data/geo_model.py:135-141,158-168,244-247).
-    The golden JSON pins HORIZONTAL_STRAT to position [-500]*3, scale 6.25e-4."""
+    """Input transform ``x' = (x + position) * scale`` (gempy/core/data/geo_model.py:135-141,158-168,244-247; rotations are
+    always 0 in the reference's models and unsupported here).  The golden JSON pins HORIZONTAL_STRAT to position [-500]*3,
+    scale 6.25e-4; ``from_input_points`` reproduces the transform stored in the reference's Greenstone.gempy bit for bit."""
     position: np.ndarray
     rotation: np.ndarray
     scale: np.ndarray
+    _is_default_transform: bool = False
+    _cached_pivot: Optional[np.ndarray] = None
+
+    def __post_init__(self):
+        self.position = np.asarray(self.position, dtype=np.float64).reshape(3)
+        self.rotation = np.asarray(self.rotation, dtype=np.float64).reshape(3)
+        self.scale = np.broadcast_to(np.asarray(self.scale, dtype=np.float64).ravel(), (3,)).copy()
 
     @classmethod
-    def from_input_points(cls, surface_points_xyz: np.ndarray, orientations_xyz: np.ndarray) -> "Transform":
-        pts = np.concatenate([np.asarray(surface_points_xyz).reshape(-1, 3),
-                              np.asarray(orientations_xyz).reshape(-1, 3)], axis=0)
+    def init_neutral(cls) -> "Transform":
+        return cls(position=np.zeros(3), rotation=np.zeros(3), scale=np.ones(3), _is_default_transform=True)
+
+    @classmethod
+    def from_input_points(cls, surface_points, orientations) -> "Transform":
+        """Accepts coordinate arrays or the reference's SurfacePointsTable / OrientationsTable (``.xyz``)."""
+        sp = np.asarray(getattr(surface_points, "xyz", surface_points), dtype=np.float64).reshape(-1, 3)
+        op = np.asarray(getattr(orientations, "xyz", orientations), dtype=np.float64).reshape(-1, 3)
+        pts = np.concatenate([sp, op], axis=0)
         mx, mn = pts.max(axis=0), pts.min(axis=0)
         scaling = 2.0 * np.max(mx - mn)
         center = (mx + mn) / 2.0
         f = 1.0 / scaling
         return cls(position=-center, rotation=np.zeros(3), scale=np.array([f, f, f]))
 
+    @classmethod
+    def from_matrix(cls, matrix: np.ndarray) -> "Transform":
+        m = np.asarray(matrix, dtype=np.float64)
+        if not np.allclose(m[:3, :3], np.diag(np.diag(m[:3, :3]))):
+            raise NotImplementedError("rotated grids are outside the B200 backend's scope")
+        return cls(position=m[:3, 3].copy(), rotation=np.zeros(3), scale=np.diag(m[:3, :3]).copy())
+
+    def _no_rotation(self):
+        if np.any(self.rotation != 0):
+            raise NotImplementedError("rotated transforms are outside the B200 backend's scope")
+
     def apply(self, points: np.ndarray) -> np.ndarray:
+        self._no_rotation()
         return (np.asarray(points, dtype=np.float64) + self.position) * self.scale
 
     def apply_inverse(self, points: np.ndarray) -> np.ndarray:
+        self._no_rotation()
         return np.asarray(points, dtype=np.float64) / self.scale - self.position
+
+    # pivot variants: a rotation-free transform does not depend on the pivot
+    def apply_with_pivot(self, points: np.ndarray, pivot=None) -> np.ndarray:
+        return self.apply(points)
+
+    def apply_inverse_with_pivot(self, points: np.ndarray, pivot=None) -> np.ndarray:
+        return self.apply_inverse(points)
+
+    def apply_with_cached_pivot(self, points: np.ndarray) -> np.ndarray:
+        return self.apply(points)
+
+    def apply_inverse_with_cached_pivot(self, points: np.ndarray) -> np.ndarray:
+        return self.apply_inverse(points)
+
+    def apply_anisotropy(self, anisotropy_type: "GlobalAnisotropy" = GlobalAnisotropy.NONE, anisotropy_limit=None) -> None:
+        if anisotropy_type in (GlobalAnisotropy.NONE, None):
+            self.scale = np.full(3, float(np.min(self.scale)) if np.ptp(self.scale) else float(self.scale[0]))
+            return
+        raise NotImplementedError("only GlobalAnisotropy.NONE is supported by the B200 backend's transform")
+
+    def __add__(self, other: "Transform") -> "Transform":
+        return Transform(position=self.position + other.position, rotation=self.rotation + other.rotation,
+                         scale=self.scale * other.scale)
 
     def transform_gradient(self, gradients: np.ndarray) -> np.ndarray:
         g = np.asarray(gradients, dtype=np.float64)
@@ -520,6 +580,12 @@ class Transform:
 
     def scale_points(self, points: np.ndarray) -> np.ndarray:
         return np.asarray(points, dtype=np.float64) * self.scale
+
+    def get_matrix_4x4(self) -> np.ndarray:
+        m = np.eye(4)
+        m[:3, :3] = np.diag(self.scale)
+        m[:3, 3] = self.position * self.scale
+        return m
 
 
 # --------------------------------------------------------------------------- outputs

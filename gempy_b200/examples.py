@@ -157,8 +157,12 @@ E, F = StackRelationType.ERODE, StackRelationType.FAULT
 
 
 def horizontal_strat(resolution=(50, 5, 50), **kw) -> ExampleModel:
-    """BASELINE config 1 (examples_generator.py:132-162): model1, dense 50x5x50."""
+    """BASELINE config 1 (examples_generator.py:132-162): model1, dense 50x5x50 AND refinement=3 -- create_geomodel
+    (initialization_API.py:67-85) builds the dense grid but keeps the default octree options, so the engine runs three
+    octree levels on the [2,2,2] root next to the dense grid and extracts meshes; the block solution type is inferred
+    DENSE_GRID (geo_model.py:324-339).  Checked against the reference's own bridge in tests/test_compat_reference.py."""
     sp, op, og = _from_tables("model1")
+    kw.setdefault("options", InterpolationOptions.init_octree_options(refinement=3))
     m = build_model("horizontal", sp, op, og, [("Strat_Series", ["rock2", "rock1"], E)],
                     [0, 1000, 0, 1000, 0, 1000], resolution=resolution, **kw)
     return m

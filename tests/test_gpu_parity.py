@@ -386,6 +386,44 @@ def test_compute_model_reproduces_approved_vectors(key, build):
     np.testing.assert_allclose(got, want, rtol=0, atol=5e-8)
 
 
+@pytest.mark.parametrize("key,fixture", [("anticline", "bridge_anticline.npz"), ("fault", "bridge_one_fault.npz"),
+                                         ("combination", "bridge_combination.npz")])
+def test_reference_bridge_inputs_reproduce_approved_vectors(key, fixture):
+    """Same golden check, but on the engine inputs the REFERENCE's own layer built: gp.generate_example_model(...,
+    compute_model=False) + interpolation_input_from_structural_frame (_engine_factory.py:14-58) + GeoModel.interpolation_options
+    + StructuralFrame.input_data_descriptor, exported by tests/compat/make_bridge_fixtures.py where /root/reference exists."""
+    from gempy_b200.engine.io import engine_inputs_from_npz
+    ii, opt, desc = engine_inputs_from_npz(os.path.join(os.path.dirname(__file__), "golden", fixture))
+    sol = gc.compute_model(ii, opt, desc)
+    got = _verify_scalar_field(sol)
+    assert got.shape == (51,)
+    np.testing.assert_allclose(got, np.array(GOLD[key]), rtol=0, atol=5e-8)
+
+
+def test_reference_bridge_graben_two_faults_matches_oracle():
+    """GRABEN (two fault stacks + one series, examples_generator.py) as the reference's bridge hands it over: CUDA path vs
+    oracle on every level, ids exact, meshes equal; also writes nothing to disk."""
+    from gempy_b200.engine.io import engine_inputs_from_npz
+    path = os.path.join(os.path.dirname(__file__), "golden", "bridge_graben.npz")
+    sol = gc.compute_model(*engine_inputs_from_npz(path))
+    ref = orc.compute_model(*engine_inputs_from_npz(path))
+    assert len(sol.octrees_output) == len(ref.levels)
+    for a, b in zip(sol.octrees_output, ref.levels):
+        nv = b.centers.shape[0]
+        assert a.grid_centers.octree_grid.values.shape[0] == nv
+        for oa, ob in zip(a.outputs_centers, b.fields.stacks):
+            assert _rel_err(oa.exported_fields.scalar_field[:nv], ob.Z[:nv]) < RTOL
+        near = np.zeros(nv, bool)
+        for ob in b.fields.stacks:
+            near |= (np.abs(ob.Z[:nv, None] - ob.isovalues[None, :]) < 1e-6).any(axis=1)
+        np.testing.assert_array_equal(np.rint(a.outputs_centers[-1].block[:nv])[~near], b.fields.lith_ids[:nv][~near])
+    assert len(sol.dc_meshes) == len(ref.meshes)
+    for a, b in zip(sol.dc_meshes, ref.meshes):
+        assert a.vertices.shape == b.vertices.shape
+        if a.vertices.shape[0]:
+            assert np.abs(a.vertices - b.vertices).max() < 1e-6 * 0.5
+
+
 def test_greenstone_isovalues_stored_by_the_engine_gpu():
     """Engine outputs kept in the reference's Greenstone.gempy header, reproduced by the CUDA path (assembly with 26
     orientations in one stack, LU, evaluation at the surface points)."""
