@@ -84,6 +84,7 @@ SIGNATURES = {
     "gpb_bench_mixed": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), _P]),
     "gpb_system_size": (C.c_int, [C.POINTER(GpbStack)]),
     "gpb_assemble_cov": (C.c_int, [C.POINTER(GpbStack), _P, C.c_int, _P, _P]),
+    "gpb_assemble_cov_ex": (C.c_int, [C.POINTER(GpbStack), _P, C.c_int, _P, C.c_int, _P]),
     "gpb_lu_solve": (C.c_int, [C.c_int, _P, C.c_int, _P, C.c_int, C.c_int, _P, _P, _P]),
     "gpb_sym_solve": (C.c_int, [C.c_int, C.c_int, _P, C.c_int, _P, C.c_int, C.c_int, _P, _P]),
     "gpb_lu_set_outer_min_n": (C.c_int, [C.c_int]),

@@ -10,6 +10,7 @@
 // Entry formulas: oracle/gempy_oracle.py header ("Conventions"); constants pinned by the reference's
 // approved scalar-field vectors.
 #include "gpb_common.cuh"
+#include <cstdlib>
 
 namespace {
 
@@ -155,6 +156,291 @@ __global__ void __launch_bounds__(256) cov_kernel(const gpb_stack st, int n, dou
         b[i] = (i < 3 * st.n_ori) ? st.ori_grad[i] : 0.0;      // ori_grad is [3][n_ori] = exactly this order
 }
 
+
+// =====================================================================================================================
+// Blocked assembly for larger systems: one kernel per block class, every distance computed once.
+//   cov_ii_kernel  increments x increments: 4 distances -> 1 entry (C only); lower tiles, mirrored through shared memory
+//   cov_ig_kernel  increments x orientations: 2 distances -> 3 entries (one per gradient axis), + mirrored upper block
+//   cov_gg_kernel  orientations x orientations: 1 distance -> 9 entries (3 x 3 axis blocks)
+//   cov_du_kernel  universal-drift and fault-drift rows / columns, zero corner, right-hand side
+// All coordinates are divided by the range once (no division per entry), sqrt is the MUFU-seeded gpb_fast_sqrt.
+// Roofline: HBM write, 8 B per entry; the arithmetic (about 64 FP64 operations per increment-increment entry) stays under
+// it once nothing is recomputed.
+// =====================================================================================================================
+constexpr int kBT = 32;
+
+// range-normalised kernel terms: u = r^2 / a^2 (with the distance epsilon), t = sqrt(u)
+//   C(r), kp_n = a^2 C'(r)/r, dd_n = a^2 (C'(r)/r - C''(r))
+template <int KERNEL>
+__device__ __forceinline__ double cov_c_n(double u, double t) {
+    if constexpr (KERNEL == GPB_KERNEL_CUBIC) {
+        return fma(t * u, fma(u, fma(0.75, u, -3.5), 8.75), fma(-7.0, u, 1.0));
+    } else if constexpr (KERNEL == GPB_KERNEL_EXPONENTIAL) {
+        return exp(-0.5 * u);
+    } else {
+        const double s = 2.23606797749978969641 * t;
+        return fma(s, fma(s, 1.0 / 3.0, 1.0), 1.0) * exp(-s);
+    }
+}
+template <int KERNEL>
+__device__ __forceinline__ double cov_kp_n(double u, double t) {
+    if constexpr (KERNEL == GPB_KERNEL_CUBIC) {
+        return fma(t, fma(u, fma(5.25, u, -17.5), 26.25), -14.0);
+    } else if constexpr (KERNEL == GPB_KERNEL_EXPONENTIAL) {
+        return -exp(-0.5 * u);
+    } else {
+        const double s = 2.23606797749978969641 * t;
+        return (-5.0 / 3.0) * (1.0 + s) * exp(-s);
+    }
+}
+template <int KERNEL>
+__device__ __forceinline__ void cov_kp_dd_n(double u, double t, double& kp, double& dd) {
+    if constexpr (KERNEL == GPB_KERNEL_CUBIC) {
+        kp = fma(t, fma(u, fma(5.25, u, -17.5), 26.25), -14.0);
+        const double om = 1.0 - u;
+        dd = -26.25 * t * om * om;                         // a^2 (C'/r - C'') = -(105/4) t (1 - u)^2
+    } else if constexpr (KERNEL == GPB_KERNEL_EXPONENTIAL) {
+        const double e = exp(-0.5 * u);
+        kp = -e;
+        dd = -e * u;
+    } else {
+        const double s = 2.23606797749978969641 * t;
+        const double e = exp(-s);
+        kp = (-5.0 / 3.0) * (1.0 + s) * e;
+        dd = (-5.0 / 3.0) * e * s * s;
+    }
+}
+
+__device__ __forceinline__ double u_of(double ax, double ay, double az, double bx, double by, double bz, double eps_u) {
+    const double dx = ax - bx, dy = ay - by, dz = az - bz;
+    return fma(dz, dz, fma(dy, dy, fma(dx, dx, eps_u)));
+}
+
+struct CovGeom {
+    int n_ori, n_rest, n_g;        // n_g = 3 n_ori
+    double inv_a, eps_u, eps_reg, c_o, c_i, c_gi, c_gg;     // c_i = c_o i_res, c_gi = c_o gi_res / a, c_gg = c_o / a^2
+};
+
+// increments x increments.  grid.x enumerates the lower tiles (ti >= tj) of the n_rest x n_rest block.
+template <int KERNEL>
+__global__ void __launch_bounds__(256) cov_ii_kernel(const gpb_stack st, const CovGeom g, double* __restrict__ A, int lda, int lower_only) {
+    __shared__ double cr[6][kBT];                  // column points: rest xyz, ref xyz (range-normalised)
+    __shared__ double S[kBT][kBT + 1];
+    // triangular decode: t = ti (ti + 1) / 2 + tj
+    const long long t = blockIdx.x;
+    int ti = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+    while ((long long)ti * (ti + 1) / 2 > t) --ti;
+    while ((long long)(ti + 1) * (ti + 2) / 2 <= t) ++ti;
+    const int tj = (int)(t - (long long)ti * (ti + 1) / 2);
+    const int i0 = ti * kBT, j0 = tj * kBT;
+    const int lane = threadIdx.x, ty = threadIdx.y;
+    const int tid = ty * 32 + lane;
+    const int nr = g.n_rest;
+    if (tid < 6 * kBT) {
+        const int c = tid / kBT, jl = tid - c * kBT;
+        const int j = min(j0 + jl, nr - 1);
+        const double* src = (c < 3) ? st.rest + (long long)c * nr : st.ref + (long long)(c - 3) * nr;
+        cr[c][jl] = src[j] * g.inv_a;
+    }
+    const int i = i0 + lane;
+    const int ic = min(i, nr - 1);
+    const double rx = st.rest[ic] * g.inv_a, ry = st.rest[nr + ic] * g.inv_a, rz = st.rest[2LL * nr + ic] * g.inv_a;
+    const double fx = st.ref[ic] * g.inv_a, fy = st.ref[nr + ic] * g.inv_a, fz = st.ref[2LL * nr + ic] * g.inv_a;
+    const double nug = g.c_o * st.sp_nugget[ic];
+    __syncthreads();
+    double* const Ab = A + (long long)g.n_g * lda + g.n_g;          // the block's (0, 0)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int jl = ty + 8 * q;
+        const int j = j0 + jl;
+        const double u11 = u_of(rx, ry, rz, cr[0][jl], cr[1][jl], cr[2][jl], g.eps_u);
+        const double u10 = u_of(rx, ry, rz, cr[3][jl], cr[4][jl], cr[5][jl], g.eps_u);
+        const double u01 = u_of(fx, fy, fz, cr[0][jl], cr[1][jl], cr[2][jl], g.eps_u);
+        const double u00 = u_of(fx, fy, fz, cr[3][jl], cr[4][jl], cr[5][jl], g.eps_u);
+        const double C11 = cov_c_n<KERNEL>(u11, gpb_fast_sqrt(u11));
+        const double C10 = cov_c_n<KERNEL>(u10, gpb_fast_sqrt(u10));
+        const double C01 = cov_c_n<KERNEL>(u01, gpb_fast_sqrt(u01));
+        const double C00 = cov_c_n<KERNEL>(u00, gpb_fast_sqrt(u00));
+        double v = g.c_i * ((C11 + C00) - (C10 + C01));              // symmetric under (i, j) swap, bit for bit
+        if (i == j) v += nug;
+        S[jl][lane] = v;
+        if (i < nr && j < nr && (ti > tj || i >= j || !lower_only)) Ab[(long long)j * lda + i] = v;
+    }
+    if (ti == tj || lower_only) return;
+    __syncthreads();
+    // mirrored tile: A[j, i] = A[i, j], written with the tile's column index along the lanes
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int il = ty + 8 * q;                 // row of the original tile = column of the mirrored one
+        const int ii = i0 + il, jj = j0 + lane;
+        if (ii < nr && jj < nr) Ab[(long long)ii * lda + jj] = S[lane][il];
+    }
+}
+
+// increments (rows, lanes) x orientations (columns): entry (I_i, G_(o, a)) = c_gi ((x_o - rest_i)_a kp(o, rest_i) - (x_o - ref_i)_a kp(o, ref_i))
+template <int KERNEL>
+__global__ void __launch_bounds__(256) cov_ig_kernel(const gpb_stack st, const CovGeom g, double* __restrict__ A, int lda, int lower_only) {
+    __shared__ double co[3][kBT];                  // column points: orientation positions (range-normalised)
+    __shared__ double S[3][kBT][kBT + 1];
+    const int i0 = blockIdx.x * kBT, o0 = blockIdx.y * kBT;
+    const int lane = threadIdx.x, ty = threadIdx.y;
+    const int tid = ty * 32 + lane;
+    const int nr = g.n_rest, no = g.n_ori;
+    if (tid < 3 * kBT) {
+        const int c = tid / kBT, ol = tid - c * kBT;
+        co[c][ol] = st.ori_pos[(long long)c * no + min(o0 + ol, no - 1)] * g.inv_a;
+    }
+    const int i = i0 + lane;
+    const int ic = min(i, nr - 1);
+    const double rx = st.rest[ic] * g.inv_a, ry = st.rest[nr + ic] * g.inv_a, rz = st.rest[2LL * nr + ic] * g.inv_a;
+    const double fx = st.ref[ic] * g.inv_a, fy = st.ref[nr + ic] * g.inv_a, fz = st.ref[2LL * nr + ic] * g.inv_a;
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int ol = ty + 8 * q;
+        const int o = o0 + ol;
+        const double ox = co[0][ol], oy = co[1][ol], oz = co[2][ol];
+        const double u1 = u_of(ox, oy, oz, rx, ry, rz, g.eps_u), u0 = u_of(ox, oy, oz, fx, fy, fz, g.eps_u);
+        const double k1 = cov_kp_n<KERNEL>(u1, gpb_fast_sqrt(u1)), k0 = cov_kp_n<KERNEL>(u0, gpb_fast_sqrt(u0));
+        const double vx = g.c_gi * ((ox - rx) * k1 - (ox - fx) * k0);
+        const double vy = g.c_gi * ((oy - ry) * k1 - (oy - fy) * k0);
+        const double vz = g.c_gi * ((oz - rz) * k1 - (oz - fz) * k0);
+        S[0][ol][lane] = vx; S[1][ol][lane] = vy; S[2][ol][lane] = vz;
+        if (i < nr && o < no) {                    // lower block: row n_g + i, column a n_ori + o
+            double* p = A + (long long)o * lda + g.n_g + i;
+            p[0] = vx;
+            p[(long long)no * lda] = vy;
+            p[2LL * no * lda] = vz;
+        }
+    }
+    if (lower_only) return;
+    __syncthreads();
+    // mirrored (upper) block: row a n_ori + o, column n_g + i, written with o along the lanes
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int il = ty + 8 * q;
+        const int ii = i0 + il, oo = o0 + lane;
+        if (ii < nr && oo < no) {
+            double* p = A + (long long)(g.n_g + ii) * lda + oo;
+            p[0] = S[0][lane][il];
+            p[no] = S[1][lane][il];
+            p[2 * no] = S[2][lane][il];
+        }
+    }
+}
+
+// orientations x orientations: one distance per pair, nine entries (full block: it is 3 n_ori squared, small next to the rest)
+template <int KERNEL>
+__global__ void __launch_bounds__(256) cov_gg_kernel(const gpb_stack st, const CovGeom g, double* __restrict__ A, int lda) {
+    __shared__ double co[3][kBT];
+    const int o0 = blockIdx.x * kBT, p0 = blockIdx.y * kBT;
+    const int lane = threadIdx.x, ty = threadIdx.y;
+    const int tid = ty * 32 + lane;
+    const int no = g.n_ori;
+    if (tid < 3 * kBT) {
+        const int c = tid / kBT, pl = tid - c * kBT;
+        co[c][pl] = st.ori_pos[(long long)c * no + min(p0 + pl, no - 1)] * g.inv_a;
+    }
+    const int o = o0 + lane;
+    const int oc = min(o, no - 1);
+    const double ox = st.ori_pos[oc] * g.inv_a, oy = st.ori_pos[no + oc] * g.inv_a, oz = st.ori_pos[2LL * no + oc] * g.inv_a;
+    const double nug = g.c_o * st.ori_nugget[oc];
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int pl = ty + 8 * q;
+        const int p = p0 + pl;
+        const double hx = ox - co[0][pl], hy = oy - co[1][pl], hz = oz - co[2][pl];
+        const double u = fma(hz, hz, fma(hy, hy, fma(hx, hx, g.eps_u)));
+        double kp, dd;
+        cov_kp_dd_n<KERNEL>(u, gpb_fast_sqrt(u), kp, dd);
+        const double T = dd * gpb_fast_rcp(u + g.eps_reg);          // (C'/r - C'') / (r^2 + 1e-5), range-normalised
+        const double kpc = g.c_gg * kp;
+        const double Tc = g.c_gg * T;
+        const double d0 = (o == p) ? nug : 0.0;
+        if (o < no && p < no) {
+            const double h[3] = {hx, hy, hz};
+#pragma unroll
+            for (int b = 0; b < 3; ++b)
+#pragma unroll
+                for (int a = 0; a < 3; ++a) {
+                    double v = h[a] * h[b] * Tc;
+                    if (a == b) v = v - kpc + d0;
+                    A[(long long)(b * no + p) * lda + a * no + o] = v;
+                }
+        }
+    }
+}
+
+// drift and fault rows / columns + zero corner + right-hand side
+__global__ void cov_du_kernel(const gpb_stack st, int n, double* __restrict__ A, int lda, double* __restrict__ b, int lower_only) {
+    const int n_g = 3 * st.n_ori, nk = n_g + st.n_rest, nd = st.n_drift + st.n_faults;
+    const long long total = (long long)n * nd;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(e / n), r = (int)(e - (long long)k * n);      // column nk + k, row r
+        double v = 0.0;
+        if (r < n_g) {
+            if (k < st.n_drift) {
+                const int ax = r / st.n_ori, o = r - ax * st.n_ori;
+                const double x[3] = {st.ori_pos[o], st.ori_pos[st.n_ori + o], st.ori_pos[2LL * st.n_ori + o]};
+                v = drift_df(x, k, ax);
+            }
+        } else if (r < nk) {
+            const int i = r - n_g;
+            if (k < st.n_drift) {
+                const double xr[3] = {st.rest[i], st.rest[st.n_rest + i], st.rest[2LL * st.n_rest + i]};
+                const double xf[3] = {st.ref[i], st.ref[st.n_rest + i], st.ref[2LL * st.n_rest + i]};
+                v = st.gi_res * (drift_f(xr, k) - drift_f(xf, k));
+            } else {
+                const int f = k - st.n_drift;
+                v = st.fault_rest[(long long)f * st.n_rest + i] - st.fault_ref[(long long)f * st.n_rest + i];
+            }
+        }
+        if (!lower_only || r >= nk) A[(long long)(nk + k) * lda + r] = v;        // column nk + k (upper part + corner)
+        if (r < nk) A[(long long)r * lda + nk + k] = v;                           // row nk + k (lower part)
+    }
+    if (b != nullptr)
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+            b[i] = (i < n_g) ? st.ori_grad[i] : 0.0;
+}
+
+template <int KERNEL>
+int launch_blocked(const gpb_stack* st, int n, double* A, int lda, double* b, int lower_only, cudaStream_t s) {
+    CovGeom g;
+    g.n_ori = st->n_ori; g.n_rest = st->n_rest; g.n_g = 3 * st->n_ori;
+    const double a = st->range;
+    g.inv_a = 1.0 / a;
+    g.eps_u = GPB_DIST_EPS / (a * a);
+    g.eps_reg = GPB_REG_EPS / (a * a);
+    g.c_o = st->c_o;
+    g.c_i = st->c_o * st->i_res;
+    g.c_gi = st->c_o * st->gi_res / a;
+    g.c_gg = st->c_o / (a * a);
+    const dim3 block(32, 8);
+    const int To = (st->n_ori + kBT - 1) / kBT, Tr = (st->n_rest + kBT - 1) / kBT;
+    if (Tr > 0) {
+        const long long tiles = (long long)Tr * (Tr + 1) / 2;
+        cov_ii_kernel<KERNEL><<<(unsigned)tiles, block, 0, s>>>(*st, g, A, lda, lower_only);
+        GPB_LAUNCH_CHECK();
+    }
+    if (Tr > 0 && To > 0) {
+        cov_ig_kernel<KERNEL><<<dim3(Tr, To), block, 0, s>>>(*st, g, A, lda, lower_only);
+        GPB_LAUNCH_CHECK();
+    }
+    if (To > 0) {
+        cov_gg_kernel<KERNEL><<<dim3(To, To), block, 0, s>>>(*st, g, A, lda);
+        GPB_LAUNCH_CHECK();
+    }
+    {
+        const long long work = (long long)n * max(1, st->n_drift + st->n_faults);
+        long long nb = (work + 255) / 256;
+        const int blocks = (int)(nb > 4096 ? 4096 : (nb < 1 ? 1 : nb));
+        cov_du_kernel<<<blocks, 256, 0, s>>>(*st, n, A, lda, b, lower_only);
+        GPB_LAUNCH_CHECK();
+    }
+    return GPB_OK;
+}
+
 }  // namespace
 
 extern "C" int gpb_system_size(const gpb_stack* st) {
@@ -162,15 +448,30 @@ extern "C" int gpb_system_size(const gpb_stack* st) {
     return 3 * st->n_ori + st->n_rest + st->n_drift + st->n_faults;
 }
 
-extern "C" int gpb_assemble_cov(const gpb_stack* st, double* A, int lda, double* b, void* stream) {
+// Systems up to this order use the single generic kernel (one launch; every reference example model), larger ones the
+// blocked kernels above.
+constexpr int kBlockedMinN = 512;
+
+extern "C" int gpb_assemble_cov_ex(const gpb_stack* st, double* A, int lda, double* b, int flags, void* stream) {
     GPB_REQUIRE(st && A, "null argument");
     const int n = gpb_system_size(st);
     GPB_REQUIRE(n > 0 && lda >= n, "bad system size / lda");
     GPB_REQUIRE(st->n_drift == 0 || st->n_drift == 3 || st->n_drift == 9, "n_drift must be 0, 3 or 9");
     GPB_REQUIRE(st->n_faults == 0 || (st->fault_rest && st->fault_ref), "fault tables missing");
+    GPB_REQUIRE(st->range > 0, "range must be positive");
+    cudaStream_t s = (cudaStream_t)stream;
+    static const bool force_generic = getenv("GPB_COV_GENERIC") != nullptr;
+    if (n >= kBlockedMinN && !force_generic) {
+        const int lower_only = (flags & GPB_COV_LOWER_ONLY) ? 1 : 0;
+        switch (st->kernel) {
+            case GPB_KERNEL_CUBIC: return launch_blocked<GPB_KERNEL_CUBIC>(st, n, A, lda, b, lower_only, s);
+            case GPB_KERNEL_EXPONENTIAL: return launch_blocked<GPB_KERNEL_EXPONENTIAL>(st, n, A, lda, b, lower_only, s);
+            case GPB_KERNEL_MATERN52: return launch_blocked<GPB_KERNEL_MATERN52>(st, n, A, lda, b, lower_only, s);
+            default: return gpb_set_error(GPB_E_INVALID, "unknown kernel function %d", st->kernel);
+        }
+    }
     const dim3 block(32, 8);
     const dim3 grid((n + kTile - 1) / kTile, (n + kTile - 1) / kTile);
-    cudaStream_t s = (cudaStream_t)stream;
     switch (st->kernel) {
         case GPB_KERNEL_CUBIC: cov_kernel<GPB_KERNEL_CUBIC><<<grid, block, 0, s>>>(*st, n, A, lda, b); break;
         case GPB_KERNEL_EXPONENTIAL: cov_kernel<GPB_KERNEL_EXPONENTIAL><<<grid, block, 0, s>>>(*st, n, A, lda, b); break;
@@ -179,4 +480,8 @@ extern "C" int gpb_assemble_cov(const gpb_stack* st, double* A, int lda, double*
     }
     GPB_LAUNCH_CHECK();
     return GPB_OK;
+}
+
+extern "C" int gpb_assemble_cov(const gpb_stack* st, double* A, int lda, double* b, void* stream) {
+    return gpb_assemble_cov_ex(st, A, lda, b, 0, stream);
 }

@@ -19,6 +19,7 @@
 #include <cstring>
 
 extern "C" int gpb_assemble_cov(const gpb_stack* st, double* A, int lda, double* b, void* stream);
+extern "C" int gpb_assemble_cov_ex(const gpb_stack* st, double* A, int lda, double* b, int flags, void* stream);
 extern "C" int gpb_sym_solve(int n, int nk, double* A, int lda, double* b, int nrhs, int ldb, int* info, void* stream);
 extern "C" int gpb_lu_solve(int n, double* A, int lda, double* b, int nrhs, int ldb, int* ipiv, int* info, void* stream);
 extern "C" int gpb_pack_eval_table(const gpb_stack* st, const double* w, double* src, void* stream);
@@ -189,7 +190,7 @@ extern "C" int gpb_model_solve_stack(gpb_model* m, int i, const gpb_level* level
     int* info = ipiv + n;
     int path = 0, rc = GPB_OK, info_h = 0;
     if (try_sym) {
-        rc = gpb_assemble_cov(&st, A, lda, ms.weights, s);
+        rc = gpb_assemble_cov_ex(&st, A, lda, ms.weights, GPB_COV_LOWER_ONLY, s);
         if (!rc) rc = gpb_sym_solve(n, nk, A, lda, ms.weights, 1, n, info, s);
         if (!rc && cudaMemcpyAsync(&info_h, info, sizeof(int), cudaMemcpyDeviceToHost, s) != cudaSuccess) rc = gpb_set_error(GPB_E_CUDA, "info copy failed");
         if (!rc && cudaStreamSynchronize(s) != cudaSuccess) rc = gpb_set_error(GPB_E_CUDA, "stream synchronisation failed: %s", cudaGetErrorString(cudaGetLastError()));

@@ -325,17 +325,18 @@ class B200Engine:
         return torch.empty(*shape, dtype=dtype, device=self.device)
 
     # -- stages ----------------------------------------------------------------------------------------------
-    def assemble(self, st: StackTables, extra_rows: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
+    def assemble(self, st: StackTables, extra_rows: int = 0, lower_only: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
         """System matrix (column-major: tensor row j = matrix column j) and right-hand side.  With ``extra_rows`` the
         leading dimension is n + extra_rows rounded up to an even number (16-byte aligned columns; the symmetric solve
-        carries its right-hand sides as extra rows) and the tensor has shape (n, lda)."""
+        carries its right-hand sides as extra rows) and the tensor has shape (n, lda).  ``lower_only``: systems of order
+        >= 512 get only their lower triangle written (all the symmetric solve reads)."""
         n = st.n
         lda = n if extra_rows == 0 else (n + extra_rows + 1) & ~1
         A = self.empty(n, lda)              # symmetric at this point
         b = self.empty(n)
         s = st.struct()
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.gpb_assemble_cov(C.byref(s), _ptr(A), lda, _ptr(b), self.stream))
+            _lib.check(self.lib.gpb_assemble_cov_ex(C.byref(s), _ptr(A), lda, _ptr(b), 1 if lower_only else 0, self.stream))
         return A, b
 
     def _check_info(self, info: torch.Tensor, what: str) -> int:
@@ -372,7 +373,7 @@ class B200Engine:
         n = st.n
         nk = 3 * st.n_ori + st.n_rest
         if n > self.SMALL_N and nk >= 1 and os.environ.get("GPB_SOLVER", "sym") != "lu":
-            A, b = self.assemble(st, extra_rows=1)
+            A, b = self.assemble(st, extra_rows=1, lower_only=True)
             info = torch.zeros(1, dtype=torch.int32, device=self.device)
             with torch.cuda.device(self.device):
                 _lib.check(self.lib.gpb_sym_solve(n, nk, _ptr(A), A.shape[1], _ptr(b), 1, n, _ptr(info), self.stream))

@@ -91,15 +91,25 @@ def extract_meshes(solutions: Solutions, extent: Sequence[float], resolution: Se
 def set_meshes_with_marching_cubes(model) -> None:
     """Same contract as the reference function (marching_cubes.py:13-55): reads ``model.solutions``,
     ``model.grid.regular_grid`` and ``model.structural_frame.structural_groups``; writes ``vertices``/``edges`` on
-    every structural element."""
+    every structural element.  Like the reference (marching_cubes.py:36-47) every element gets the mesh of ITS OWN
+    isovalue, ``element.scalar_field_at_interface``: the ``GeoModel.solutions`` setter has already reordered each group's
+    elements by decreasing scalar value (geo_model.py:121-127), so pairing meshes and elements by position would hand
+    elements their neighbours' surfaces whenever that reorder was not the identity."""
     rg = model.grid.regular_grid
-    meshes = extract_meshes(model.solutions, rg.extent, rg.resolution)
-    n_out = len(model.solutions.octrees_output[0].outputs)
+    sol = model.solutions
+    meshes = extract_meshes(sol, rg.extent, rg.resolution)
+    f = sol.octrees_output[0]._device_fields
+    n_out = len(sol.octrees_output[0].outputs)
     k = 0
     for e, group in enumerate(model.structural_frame.structural_groups):
         if e >= n_out:
             continue
-        for element in group.elements:
-            element.vertices = meshes[k].vertices
-            element.edges = meshes[k].edges
-            k += 1
+        iso = f.isovalues[e].cpu().numpy()
+        group_meshes = meshes[k:k + iso.shape[0]]
+        k += iso.shape[0]
+        for pos, element in enumerate(group.elements):
+            level = getattr(element, "scalar_field_at_interface", None)
+            j = pos if level is None else int(np.argmin(np.abs(iso - float(level))))
+            if j < len(group_meshes):
+                element.vertices = group_meshes[j].vertices
+                element.edges = group_meshes[j].edges

@@ -100,6 +100,10 @@ int gpb_bench_mixed(int iters, int ratio, double* dfma_tflops_host, double* dmma
  * right-hand side b = [G_x; G_y; G_z; 0]. */
 int gpb_system_size(const gpb_stack* st);
 int gpb_assemble_cov(const gpb_stack* st, double* A, int lda, double* b, void* stream);
+/* flags: GPB_COV_LOWER_ONLY writes the lower triangle (+ diagonal) only -- all the symmetric solve reads; for systems of
+ * order >= 512 this halves the HBM traffic of the assembly (smaller systems are always written in full). */
+#define GPB_COV_LOWER_ONLY 1
+int gpb_assemble_cov_ex(const gpb_stack* st, double* A, int lda, double* b, int flags, void* stream);
 
 /* ---- (2) dense solve  [engine stage "solver", kernel_solver = 1 (direct)] ------------------------- */
 /* In-place blocked right-looking LU with partial pivoting (DMMA trailing updates), then the triangular

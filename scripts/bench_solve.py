@@ -6,6 +6,7 @@ block) through torch.linalg, same process, same matrix (BASELINE north_star: "ti
     python scripts/bench_solve.py --sizes 250,1000,2500 [--kernel matern_5_2] [--reps 5]
 `--sizes` are surface points per surface (4 surfaces) with as many orientations: n = 3 n_o + 4 n_sp - 4 + 3."""
 import argparse
+import ctypes
 import json
 import os
 import sys
@@ -76,7 +77,15 @@ def run(eng, n_sp, n_ori, kernel, reps, skip_cusolver=False):
     def clone_full():
         A0.clone()
 
-    fns = [sym, lu, copy_only, clone_full] + ([] if skip_cusolver else [cus_getrf, cus_potrf])
+    sct = st.struct()
+
+    def cov_full():
+        _lib.check(eng.lib.gpb_assemble_cov_ex(ctypes.byref(sct), Apad.data_ptr(), lda, b0.data_ptr(), 0, eng.stream))
+
+    def cov_lower():
+        _lib.check(eng.lib.gpb_assemble_cov_ex(ctypes.byref(sct), Apad.data_ptr(), lda, b0.data_ptr(), 1, eng.stream))
+
+    fns = [sym, lu, copy_only, clone_full, cov_full, cov_lower] + ([] if skip_cusolver else [cus_getrf, cus_potrf])
     for f in fns:
         f()
     torch.cuda.synchronize()
@@ -96,6 +105,12 @@ def run(eng, n_sp, n_ori, kernel, reps, skip_cusolver=False):
         # torch.linalg.lu_factor / cholesky clone their input internally; subtract the same clone we subtract from ours
         rec["cusolver_getrf_getrs_ms"] = t["cus_getrf"][0] - t["clone_full"][0]
         rec["cusolver_potrf_potrs_ms_cov_block_only"] = t["cus_potrf"][0] - t["clone_full"][0]
+    hbm = 6550.4e9
+    rec["cov_assemble_full_ms"] = t["cov_full"][0]
+    rec["cov_assemble_lower_ms"] = t["cov_lower"][0]
+    rec["cov_full_gbs"] = 8.0 * n * n / (t["cov_full"][0] * 1e-3) / 1e9
+    rec["cov_full_frac_of_measured_hbm"] = 8.0 * n * n / (t["cov_full"][0] * 1e-3) / hbm
+    rec["cov_lower_frac_of_measured_hbm"] = 4.0 * n * (n + 1) / (t["cov_lower"][0] * 1e-3) / hbm
     rec["sym_tflops_chol_model"] = (nk ** 3 / 3.0) / (rec["gpb_sym_solve_ms"] * 1e-3) / 1e12
     rec["lu_tflops"] = (2.0 * n ** 3 / 3.0) / (rec["gpb_lu_solve_ms"] * 1e-3) / 1e12
     return rec

@@ -84,6 +84,44 @@ def test_covariance_with_fault_columns(eng):
     assert np.abs(A.cpu().numpy() - A_ref).max() <= 1e-12 * np.abs(A_ref).max()
 
 
+@pytest.mark.parametrize("kernel", [K.cubic, K.exponential, K.matern_5_2])
+@pytest.mark.parametrize("degree", [0, 1, 2])
+def test_covariance_assembly_blocked_kernels(eng, kernel, degree):
+    """Systems of order >= 512 are assembled block by block (cov_ii / cov_ig / cov_gg / cov_du kernels: every distance
+    computed once, range-normalised coordinates, mirrored stores): against the oracle, bitwise symmetric, with fault-drift
+    columns and ragged tile edges (n_ori = 93, n_rest = 4 x 161); lower-only mode writes the lower triangle and nothing else."""
+    m = ex.synthetic_stress(n_sp_per_surface=162, n_surfaces=4, n_ori=93, resolution=(4, 4, 4))
+    ii, opt, desc = m.args()
+    opt.kernel_options.kernel_function = kernel
+    opt.kernel_options.uni_degree = degree
+    rng = np.random.default_rng(7)
+    n_sp = int(desc.stack_structure.number_of_points_per_stack[0])
+    f_on_sp = rng.integers(0, 3, size=(2, n_sp)).astype(float)
+    st = gc.StackTables(ii, desc, 0, opt.kernel_options, eng.device)
+    st.set_faults(torch.as_tensor(f_on_sp, device=eng.device))
+    A, b = eng.assemble(st)
+    so = _oracle_stack(m, 0, f_on_sp)
+    A_ref = orc.assemble_covariance(so, opt.kernel_options)
+    A_h = A.cpu().numpy()
+    n = A_ref.shape[0]
+    assert n >= 512 and A_h.shape == A_ref.shape
+    np.testing.assert_array_equal(A_h, A_h.T)
+    assert np.abs(A_h - A_ref).max() <= 1e-12 * np.abs(A_ref).max()
+    np.testing.assert_array_equal(b.cpu().numpy(), orc.rhs(so, opt.kernel_options))
+    # lower-only: same lower triangle (column-major storage: tensor[j, i] = A[i, j]), upper triangle untouched
+    lda = n + 2
+    Ad = torch.full((n, lda), float("nan"), dtype=torch.float64, device=eng.device)
+    bd = eng.empty(n)
+    sct = st.struct()
+    _lib.check(eng.lib.gpb_assemble_cov_ex(C.byref(sct), Ad.data_ptr(), lda, bd.data_ptr(), 1, eng.stream))
+    L = Ad.cpu().numpy()[:, :n].T                               # L[i, j] = A[i, j]
+    il = np.tril_indices(n)
+    np.testing.assert_array_equal(L[il], A_h[il])
+    nk = 3 * st.n_ori + st.n_rest
+    iu = np.triu_indices(nk, 1)
+    assert np.isnan(L[:nk, :nk][iu][(iu[0] >= 3 * st.n_ori)]).all()          # increment block: strictly upper part not written
+
+
 # ------------------------------------------------------------------------------------------- (2) solve
 @pytest.mark.parametrize("n", [1, 7, 33, 104, 160, 161, 500, 1000, 2049])
 def test_lu_solve_random(eng, n):
@@ -791,6 +829,13 @@ def test_marching_cubes_reference_vertex_counts(eng):
     assert groups[1].elements[0].vertices.shape == (860, 3)
     assert groups[2].elements[0].vertices.shape == (1256, 3)
     assert groups[2].elements[1].vertices.shape == (1680, 3)
+    # elements the GeoModel.solutions setter has reordered (geo_model.py:121-127) still get the mesh of their OWN isovalue
+    iso2 = sol.octrees_output[0]._device_fields.isovalues[2].cpu().numpy()
+    swapped = [NS(is_fault=True, elements=[NS()]), NS(is_fault=False, elements=[NS()]),
+               NS(is_fault=False, elements=[NS(scalar_field_at_interface=float(iso2[1])), NS(scalar_field_at_interface=float(iso2[0]))])]
+    model.structural_frame = NS(structural_groups=swapped)
+    set_meshes_with_marching_cubes(model)
+    assert swapped[2].elements[0].vertices.shape == (1680, 3) and swapped[2].elements[1].vertices.shape == (1256, 3)
     # octree-only solutions are refused like the reference does (marching_cubes.py:26-28)
     so = gc.compute_model(*ex.combination(refinement=2).args(), engine=eng)
     with pytest.raises(ValueError):
