@@ -99,6 +99,7 @@ __global__ void __launch_bounds__(256) potrf64_kernel(int k0, int jb, double* __
     extern __shared__ double S[];              // S[c * kLdS + slot]
     double* tol = S + kCB * kLdS;              // pivot thresholds of the block's columns
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (info != nullptr && *reinterpret_cast<volatile int*>(info) != 0) return;      // an earlier pivot failed: the caller falls back to the LU
     for (int e = tid; e < kCB * kLdS; e += 256) S[e] = 0.0;
     if (tid < kCB) tol[tid] = (tid < jb && diag0) ? kPivotTol * fabs(diag0[k0 + tid]) : 0.0;
     __syncthreads();

@@ -163,7 +163,9 @@ __global__ void __launch_bounds__(256) cov_kernel(const gpb_stack st, int n, dou
 //   cov_ig_kernel  increments x orientations: 2 distances -> 3 entries (one per gradient axis), + mirrored upper block
 //   cov_gg_kernel  orientations x orientations: 1 distance -> 9 entries (3 x 3 axis blocks)
 //   cov_du_kernel  universal-drift and fault-drift rows / columns, zero corner, right-hand side
-// All coordinates are divided by the range once (no division per entry), sqrt is the MUFU-seeded gpb_fast_sqrt.
+// All coordinates are divided by the range once (no division per entry; __dmul_rn so that the product is rounded before it
+// meets a subtraction: an FMA-contracted normalisation would make the (i, j) and (j, i) entries, which different threads
+// compute, differ in the last bit), sqrt is the MUFU-seeded gpb_fast_sqrt.
 // Roofline: HBM write, 8 B per entry; the arithmetic (about 64 FP64 operations per increment-increment entry) stays under
 // it once nothing is recomputed.
 // =====================================================================================================================
@@ -240,12 +242,12 @@ __global__ void __launch_bounds__(256) cov_ii_kernel(const gpb_stack st, const C
         const int c = tid / kBT, jl = tid - c * kBT;
         const int j = min(j0 + jl, nr - 1);
         const double* src = (c < 3) ? st.rest + (long long)c * nr : st.ref + (long long)(c - 3) * nr;
-        cr[c][jl] = src[j] * g.inv_a;
+        cr[c][jl] = __dmul_rn(src[j], g.inv_a);
     }
     const int i = i0 + lane;
     const int ic = min(i, nr - 1);
-    const double rx = st.rest[ic] * g.inv_a, ry = st.rest[nr + ic] * g.inv_a, rz = st.rest[2LL * nr + ic] * g.inv_a;
-    const double fx = st.ref[ic] * g.inv_a, fy = st.ref[nr + ic] * g.inv_a, fz = st.ref[2LL * nr + ic] * g.inv_a;
+    const double rx = __dmul_rn(st.rest[ic], g.inv_a), ry = __dmul_rn(st.rest[nr + ic], g.inv_a), rz = __dmul_rn(st.rest[2LL * nr + ic], g.inv_a);
+    const double fx = __dmul_rn(st.ref[ic], g.inv_a), fy = __dmul_rn(st.ref[nr + ic], g.inv_a), fz = __dmul_rn(st.ref[2LL * nr + ic], g.inv_a);
     const double nug = g.c_o * st.sp_nugget[ic];
     __syncthreads();
     double* const Ab = A + (long long)g.n_g * lda + g.n_g;          // the block's (0, 0)
@@ -288,12 +290,12 @@ __global__ void __launch_bounds__(256) cov_ig_kernel(const gpb_stack st, const C
     const int nr = g.n_rest, no = g.n_ori;
     if (tid < 3 * kBT) {
         const int c = tid / kBT, ol = tid - c * kBT;
-        co[c][ol] = st.ori_pos[(long long)c * no + min(o0 + ol, no - 1)] * g.inv_a;
+        co[c][ol] = __dmul_rn(st.ori_pos[(long long)c * no + min(o0 + ol, no - 1)], g.inv_a);
     }
     const int i = i0 + lane;
     const int ic = min(i, nr - 1);
-    const double rx = st.rest[ic] * g.inv_a, ry = st.rest[nr + ic] * g.inv_a, rz = st.rest[2LL * nr + ic] * g.inv_a;
-    const double fx = st.ref[ic] * g.inv_a, fy = st.ref[nr + ic] * g.inv_a, fz = st.ref[2LL * nr + ic] * g.inv_a;
+    const double rx = __dmul_rn(st.rest[ic], g.inv_a), ry = __dmul_rn(st.rest[nr + ic], g.inv_a), rz = __dmul_rn(st.rest[2LL * nr + ic], g.inv_a);
+    const double fx = __dmul_rn(st.ref[ic], g.inv_a), fy = __dmul_rn(st.ref[nr + ic], g.inv_a), fz = __dmul_rn(st.ref[2LL * nr + ic], g.inv_a);
     __syncthreads();
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -339,11 +341,11 @@ __global__ void __launch_bounds__(256) cov_gg_kernel(const gpb_stack st, const C
     const int no = g.n_ori;
     if (tid < 3 * kBT) {
         const int c = tid / kBT, pl = tid - c * kBT;
-        co[c][pl] = st.ori_pos[(long long)c * no + min(p0 + pl, no - 1)] * g.inv_a;
+        co[c][pl] = __dmul_rn(st.ori_pos[(long long)c * no + min(p0 + pl, no - 1)], g.inv_a);
     }
     const int o = o0 + lane;
     const int oc = min(o, no - 1);
-    const double ox = st.ori_pos[oc] * g.inv_a, oy = st.ori_pos[no + oc] * g.inv_a, oz = st.ori_pos[2LL * no + oc] * g.inv_a;
+    const double ox = __dmul_rn(st.ori_pos[oc], g.inv_a), oy = __dmul_rn(st.ori_pos[no + oc], g.inv_a), oz = __dmul_rn(st.ori_pos[2LL * no + oc], g.inv_a);
     const double nug = g.c_o * st.ori_nugget[oc];
     __syncthreads();
 #pragma unroll

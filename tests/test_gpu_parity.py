@@ -936,3 +936,94 @@ def test_tiny_dense_grids(eng, shape):
     assert sl.stop - sl.start == int(np.prod(shape))
     assert _rel_err(zf[sl], ref.stacks[0].Z[n_oct:n_oct + g.n_points]) < RTOL
     np.testing.assert_array_equal(sol.raw_arrays.lith_block, ref.lith_ids[n_oct:n_oct + g.n_points])
+
+
+# ------------------------------------------------------------------------------------------- BASELINE configs in the suite
+def _full_model_check(build, vertex_tol_extent=0.5):
+    """compute_model vs oracle on every level: leaf lists equal, fields < 1e-9 relative, lith ids exact on every voxel more
+    than 1e-6 from an isovalue, squeezed masks equal there, refinement marks equal, mesh vertices within 1e-6 of the extent
+    (transformed extent: 0.5) and the same triangles."""
+    sol = gc.compute_model(*build().args())
+    ref = orc.compute_model(*build().args())
+    assert len(sol.octrees_output) == len(ref.levels)
+    for lvl, (a, b) in enumerate(zip(sol.octrees_output, ref.levels)):
+        nv = b.centers.shape[0]
+        np.testing.assert_allclose(a.grid_centers.octree_grid.values, b.centers, rtol=0, atol=1e-15)
+        near = np.zeros(nv, bool)
+        for i, (oa, ob) in enumerate(zip(a.outputs_centers, b.fields.stacks)):
+            assert _rel_err(oa.exported_fields.scalar_field[:nv], ob.Z[:nv]) < RTOL, (lvl, i)
+            near |= (np.abs(ob.Z[:nv, None] - ob.isovalues[None, :]) < 1e-6).any(axis=1)
+        np.testing.assert_array_equal(np.rint(a.outputs_centers[-1].block[:nv])[~near], b.fields.lith_ids[:nv][~near])
+        if b.selected is not None:
+            np.testing.assert_array_equal(a.marked_voxels, b.selected)
+    if ref.meshes:
+        assert len(sol.dc_meshes) == len(ref.meshes)
+        for a, b in zip(sol.dc_meshes, ref.meshes):
+            assert a.vertices.shape == b.vertices.shape
+            if a.vertices.shape[0]:
+                assert np.abs(a.vertices - b.vertices).max() < 1e-6 * vertex_tol_extent
+            assert set(map(tuple, a.edges.tolist())) == set(map(tuple, b.edges.tolist()))
+    return sol, ref
+
+
+def test_baseline_config2_combination_octree_level_6():
+    """BASELINE configs[1]: COMBINATION (fault + two series, fault drift) with octree refinement to level 6."""
+    sol, ref = _full_model_check(lambda: ex.combination(refinement=6))
+    assert [l.grid_centers.octree_grid.values.shape[0] for l in sol.octrees_output][-1] == ref.levels[-1].centers.shape[0] > 50_000
+
+
+def test_baseline_config4_multi_fault_octree_level_4_and_prefix_of_deeper_run():
+    """BASELINE configs[3] shape (10 fault stacks + 5 series with 10 fault-drift columns each, 15 stacks) at the depth the
+    oracle can afford (octree level 4, dual contouring on), and the first four levels of a level-6 run are the level-4 run
+    (same leaf lists, same ids): refinement does not depend on how deep the run goes."""
+    sol4, _ = _full_model_check(lambda: ex.synthetic_multi_fault(refinement=4))
+    sol6 = gc.compute_model(*ex.synthetic_multi_fault(refinement=6).args())
+    assert sol6.octrees_output[-1].grid_centers.octree_grid.values.shape[0] > 100_000
+    for a, b in zip(sol4.octrees_output[:3], sol6.octrees_output[:3]):
+        np.testing.assert_array_equal(a.grid_centers.octree_grid.values, b.grid_centers.octree_grid.values)
+        nv = a.grid_centers.octree_grid.values.shape[0]
+        np.testing.assert_array_equal(a.outputs_centers[-1].block[:nv], b.outputs_centers[-1].block[:nv])
+        np.testing.assert_array_equal(a.marked_voxels, b.marked_voxels)
+    np.testing.assert_array_equal(sol4.octrees_output[3].grid_centers.octree_grid.values, sol6.octrees_output[3].grid_centers.octree_grid.values)
+    lb = sol6.raw_arrays.lith_block
+    assert lb.shape == (64 ** 3,) and set(np.unique(lb)) <= set(float(v) for v in range(1, 27))
+
+
+def test_baseline_config5_reduced_matern_symmetric_solve_path():
+    """BASELINE configs[4] at reduced size: 2 000 surface points + 500 orientations (n = 3 499), Matern-5/2 kernel, octree
+    level 4.  The system takes the symmetric (Cholesky + Schur) path.  UNPINNED: the reference holds no fixture for the
+    Matern kernel, so this proves CUDA = oracle (restated from the literature), not CUDA = reference."""
+    build = lambda: ex.synthetic_stress(n_sp_per_surface=500, n_surfaces=4, n_ori=500, kernel=K.matern_5_2, refinement=4)
+    sol, _ = _full_model_check(build)
+    assert sol._tables.solver_paths() == ["sym"]
+
+
+def test_singular_system_raises_through_compute_model():
+    """Two identical surface points with zero nugget make two identical rows: the reference's dense solve raises
+    (numpy.linalg.LinAlgError); so does the backend -- no garbage weights, fields or ids (VERDICT r1 weak #3)."""
+    m = ex.anticline(refinement=2)
+    sp = m.interpolation_input.surface_points
+    sp.sp_coords[2] = sp.sp_coords[1]
+    sp.nugget_effect_scalar[:] = 0.0
+    with pytest.raises(_lib.GpbError, match="singular"):
+        gc.compute_model(*m.args())
+    # the same through the symmetric path (n > 160): an all-zero fault-drift column
+    from gempy_b200.engine.data import StackRelationType as R
+    big = ex.synthetic_stress(n_sp_per_surface=80, n_surfaces=4, n_ori=40, refinement=2)
+    ii, opt, desc = big.args()
+    ii2 = ex.anticline(refinement=2)          # (only used for its class objects)
+    del ii2
+    # prepend a "fault" stack whose block is constant over the model: its drift column in the series' system is zero
+    from gempy_b200.engine.data import (InputDataDescriptor, InterpolationInput, Orientations, StacksStructure, SurfacePoints,
+                                        TensorsStructure)
+    f_sp = np.array([[0.0, 0.0, 5.0], [0.1, 0.0, 5.0], [0.0, 0.1, 5.0]])        # a plane far above the model: every point on one side
+    f_or = np.array([[0.0, 0.0, 5.0]])
+    ii_f = InterpolationInput(SurfacePoints(np.vstack([f_sp, ii.surface_points.sp_coords]), 2e-5),
+                              Orientations(np.vstack([f_or, ii.orientations.dip_positions]),
+                                           np.vstack([[[0.0, 0.0, 1.0]], ii.orientations.dip_gradients]), 0.01),
+                              ii.grid, unit_values=np.arange(1, 7), weights=[])
+    desc_f = InputDataDescriptor(TensorsStructure(np.concatenate([[3], desc.tensors_structure.number_of_points_per_surface])),
+                                 StacksStructure([3, ii.surface_points.n_points], [1, ii.orientations.n_items], [1, 4],
+                                                 [R.FAULT, R.BASEMENT], faults_relations=np.array([[0, 1], [0, 0]], bool)))
+    with pytest.raises(_lib.GpbError, match="singular"):
+        gc.compute_model(ii_f, opt, desc_f)
