@@ -98,10 +98,11 @@ SIGNATURES = {
     "gpb_eval_points": (C.c_int, [C.POINTER(GpbStack), _P, _P, _LL, _LL, _P, _LL, _P, _P, _P, _P, _P]),
     "gpb_model_create": (C.c_int, [C.POINTER(GpbModelDesc), C.POINTER(C.c_void_p)]),
     "gpb_model_destroy": (None, [C.c_void_p]),
-    "gpb_model_solve_stack": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(GpbLevel), C.POINTER(C.c_int), _P]),
+    "gpb_model_solve_stack": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(GpbLevel), C.POINTER(C.c_int), _P, _LL, _P]),
+    "gpb_model_workspace_bytes": (_LL, [C.c_void_p]),
     "gpb_model_eval_stack": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(GpbLevel), _P]),
     "gpb_model_combine": (C.c_int, [C.c_void_p, C.POINTER(GpbLevel), _P]),
-    "gpb_model_run_level": (C.c_int, [C.c_void_p, C.POINTER(GpbLevel), C.c_int, _P]),
+    "gpb_model_run_level": (C.c_int, [C.c_void_p, C.POINTER(GpbLevel), C.c_int, _P, _LL, _P]),
     "gpb_model_solver_path": (C.c_int, [C.c_void_p, C.c_int]),
     "gpb_copy_2d": (C.c_int, [_P, _LL, _P, _LL, _LL, _LL, _P]),
     "gpb_scan_elems": (_LL, [_LL]),

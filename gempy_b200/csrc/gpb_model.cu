@@ -164,7 +164,20 @@ extern "C" int gpb_model_create(const gpb_model_desc* d, gpb_model** out) {
 
 extern "C" void gpb_model_destroy(gpb_model* m) { delete m; }
 
-extern "C" int gpb_model_solve_stack(gpb_model* m, int i, const gpb_level* level0, int* path_host, void* stream) {
+extern "C" long long gpb_model_workspace_bytes(const gpb_model* m) {
+    long long best = 0;
+    if (!m) return 0;
+    for (const gpb_model_stack& ms : m->stacks) {
+        const long long n = 3LL * ms.st.n_ori + ms.st.n_rest + ms.st.n_drift + ms.st.n_faults;
+        const long long lda = (n + 2) & ~1LL;
+        const long long b = 8 * lda * n + 4 * (n + 4);
+        if (b > best) best = b;
+    }
+    return best;
+}
+
+extern "C" int gpb_model_solve_stack(gpb_model* m, int i, const gpb_level* level0, int* path_host, void* workspace,
+                                     long long workspace_bytes, void* stream) {
     GPB_REQUIRE(m && i >= 0 && i < (int)m->stacks.size() && level0, "bad arguments");
     GPB_REQUIRE(level0->sp_offset >= 0 && level0->Z && level0->block, "level 0 must carry the surface-point tail");
     cudaStream_t s = (cudaStream_t)stream;
@@ -184,7 +197,11 @@ extern "C" int gpb_model_solve_stack(gpb_model* m, int i, const gpb_level* level
     const int lda = (n + 2) & ~1;                                   // even, >= n + 1: room for the right-hand side row of the symmetric path
     char* ws = nullptr;
     const size_t a_bytes = sizeof(double) * (size_t)lda * n;
-    GPB_CHECK_CUDA(cudaMallocAsync((void**)&ws, a_bytes + sizeof(int) * (size_t)(n + 4), s));
+    // the caller's workspace when it is large enough (a 9.8 GB stream-ordered allocation costs more than the solve it is
+    // for: the pool gives the memory back at every synchronisation), else a stream-ordered allocation
+    const bool own_ws = !(workspace != nullptr && (size_t)workspace_bytes >= a_bytes + sizeof(int) * (size_t)(n + 4));
+    if (own_ws) GPB_CHECK_CUDA(cudaMallocAsync((void**)&ws, a_bytes + sizeof(int) * (size_t)(n + 4), s));
+    else ws = (char*)workspace;
     double* A = reinterpret_cast<double*>(ws);
     int* ipiv = reinterpret_cast<int*>(ws + a_bytes);
     int* info = ipiv + n;
@@ -205,7 +222,7 @@ extern "C" int gpb_model_solve_stack(gpb_model* m, int i, const gpb_level* level
             rc = gpb_set_error(GPB_E_SINGULAR, "stack %d: zero pivot at column %d -- the co-kriging system is singular (duplicate data with zero nugget, or an all-zero drift column)", i, info_h);
         path = 2;
     }
-    cudaFreeAsync(ws, s);
+    if (own_ws) cudaFreeAsync(ws, s);
     if (rc) return rc;
     m->solved[i] = path;
     if (path_host) *path_host = path;
@@ -250,11 +267,12 @@ extern "C" int gpb_model_combine(gpb_model* m, const gpb_level* lvl, void* strea
                        lvl->final_block, lvl->faults_block, lvl->squeezed, lvl->mask, stream);
 }
 
-extern "C" int gpb_model_run_level(gpb_model* m, const gpb_level* lvl, int solve, void* stream) {
+extern "C" int gpb_model_run_level(gpb_model* m, const gpb_level* lvl, int solve, void* workspace, long long workspace_bytes,
+                                   void* stream) {
     GPB_REQUIRE(m && lvl, "bad arguments");
     for (int i = 0; i < (int)m->stacks.size(); ++i) {
         int rc;
-        if (solve && (rc = gpb_model_solve_stack(m, i, lvl, nullptr, stream))) return rc;
+        if (solve && (rc = gpb_model_solve_stack(m, i, lvl, nullptr, workspace, workspace_bytes, stream))) return rc;
         if ((rc = gpb_model_eval_stack(m, i, lvl, stream))) return rc;
     }
     return gpb_model_combine(m, lvl, stream);

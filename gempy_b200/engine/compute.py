@@ -449,12 +449,16 @@ class B200Engine:
         lvl = _lib.GpbLevel(L, len(segs), arr, L - n_sp, _ptr(Z), _ptr(G), _ptr(block), _ptr(final_block), _ptr(faults_block),
                             _ptr(squeezed), _ptr(mask))
         lib, h, stream = self.lib, tables.handle, self.stream
+        ws, ws_bytes = None, 0
+        if solve:                                         # scratch of the largest system, owned by torch's allocator
+            ws_bytes = int(lib.gpb_model_workspace_bytes(h))
+            ws = self.empty((ws_bytes + 7) // 8)
         if comm.world == 1:
-            _lib.check(lib.gpb_model_run_level(h, C.byref(lvl), int(solve), stream))
+            _lib.check(lib.gpb_model_run_level(h, C.byref(lvl), int(solve), _ptr(ws), ws_bytes, stream))
         else:
             for i in range(n_st):
                 if solve:
-                    _lib.check(lib.gpb_model_solve_stack(h, i, C.byref(lvl), None, stream))
+                    _lib.check(lib.gpb_model_solve_stack(h, i, C.byref(lvl), None, _ptr(ws), ws_bytes, stream))
                 _lib.check(lib.gpb_model_eval_stack(h, i, C.byref(lvl), stream))
                 if tables.rel[i] == StackRelationType.FAULT.value:
                     comm.all_reduce_min(tables.fault_min[i:i + 1])

@@ -228,13 +228,18 @@ void gpb_model_destroy(gpb_model* m);
 /* Assemble + solve stack i (weights, evaluation table, isovalues).  The earlier fault stacks must have been evaluated on
  * `level0` (their block rows and minima feed the fault-drift columns).  Synchronises the stream (reads the solver's
  * info); GPB_E_SINGULAR on a zero pivot.  path_host (may be NULL): 1 = symmetric path, 2 = pivoted LU. */
-int  gpb_model_solve_stack(gpb_model* m, int i, const gpb_level* level0, int* path_host, void* stream);
+int  gpb_model_solve_stack(gpb_model* m, int i, const gpb_level* level0, int* path_host, void* workspace,
+                           long long workspace_bytes, void* stream);
+/* Scratch the largest system of the model needs (matrix + pivots).  Passing a device buffer of that size as `workspace`
+ * avoids a stream-ordered allocation per solve (NULL / too small: the library allocates). */
+long long gpb_model_workspace_bytes(const gpb_model* m);
 /* Fused evaluation of stack i on every segment of the level: Z (+G), block, and for a fault stack the minimum of its
  * block in fault_min[i] (multi-GPU callers all-reduce it before the next dependent stack). */
 int  gpb_model_eval_stack(gpb_model* m, int i, const gpb_level* lvl, void* stream);
 int  gpb_model_combine(gpb_model* m, const gpb_level* lvl, void* stream);
 /* solve (if `solve`) + evaluate every stack in order, then combine: the single-GPU path, one call per level. */
-int  gpb_model_run_level(gpb_model* m, const gpb_level* lvl, int solve, void* stream);
+int  gpb_model_run_level(gpb_model* m, const gpb_level* lvl, int solve, void* workspace, long long workspace_bytes,
+                         void* stream);
 int  gpb_model_solver_path(const gpb_model* m, int i);
 
 /* dst[r][0..cols) = src[r][0..cols) for r < rows (device to device, on the copy engine). */
