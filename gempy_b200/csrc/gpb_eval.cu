@@ -18,6 +18,16 @@
 #include "gpb_common.cuh"
 #include <cstdlib>
 
+// GPB_EVAL_SQRT3: third-order sqrt / reciprocal corrections (1e-20) instead of the second-order ones (2e-14 / 6e-14):
+// one more FP64 instruction per pair each.  Measured on the 512^3 benchmark: see DESIGN.md section 5.
+#ifdef GPB_EVAL_SQRT3
+#define EVAL_SQRT gpb_fast_sqrt
+#define EVAL_RCP gpb_fast_rcp
+#else
+#define EVAL_SQRT gpb_fast_sqrt2
+#define EVAL_RCP gpb_fast_rcp2
+#endif
+
 namespace {
 
 constexpr int kTileSp = 256;                  // sources per tile: 256 * 32 B = 8 KB
@@ -269,7 +279,7 @@ eval_kernel(const EvalParams prm) {
                     for (int k = 0; k < P; ++k) {
                         const double dx = X[k] - a0.x, dy = Y[k] - a0.y, dz = Zc[k] - a1.x;
                         const double u = fma(dz, dz, fma(dy, dy, fma(dx, dx, prm.eps_u)));
-                        const double t = gpb_fast_sqrt(u);
+                        const double t = EVAL_SQRT(u);
                         double cv, kp;
                         cov_sp<KERNEL>(u, t, cv, kp);
                         const double wq = (KERNEL == GPB_KERNEL_CUBIC) ? a1.y * t : a1.y;     // W t for the cubic split
@@ -315,13 +325,13 @@ eval_kernel(const EvalParams prm) {
                     for (int k = 0; k < P; ++k) {
                         const double dx = X[k] - a0.x, dy = Y[k] - a0.y, dz = Zc[k] - a1.x;
                         const double u = fma(dz, dz, fma(dy, dy, fma(dx, dx, prm.eps_u)));
-                        const double t = gpb_fast_sqrt(u);
+                        const double t = EVAL_SQRT(u);
                         double kp, dd;
                         cov_ori<KERNEL>(u, t, kp, dd);
                         const double hw = fma(dz, a2.y, fma(dy, a2.x, dx * a1.y));
                         accZ[k] = fma(kp, hw, accZ[k]);
                         if constexpr (GRAD) {
-                            const double c1 = -(dd * gpb_fast_rcp(u + prm.eps_reg)) * hw;
+                            const double c1 = -(dd * EVAL_RCP(u + prm.eps_reg)) * hw;
                             hx[k] = fma(c1, dx, fma(kp, a1.y, hx[k]));
                             hy[k] = fma(c1, dy, fma(kp, a2.x, hy[k]));
                             hz[k] = fma(c1, dz, fma(kp, a2.y, hz[k]));
@@ -547,7 +557,7 @@ eval_zrun_kernel(const EvalParams prm) {
                     for (int k = 0; k < P; ++k) {
                         const double dz = Zc[k] - a1.x;
                         const double u = fma(dz, dz, pxy);
-                        const double t = gpb_fast_sqrt(u);
+                        const double t = EVAL_SQRT(u);
                         double cv, kp;
                         cov_sp<KERNEL>(u, t, cv, kp);
                         const double wq = (KERNEL == GPB_KERNEL_CUBIC) ? a1.y * t : a1.y;     // W t for the cubic split
@@ -595,13 +605,13 @@ eval_zrun_kernel(const EvalParams prm) {
                     for (int k = 0; k < P; ++k) {
                         const double dz = Zc[k] - a1.x;
                         const double u = fma(dz, dz, pxy);
-                        const double t = gpb_fast_sqrt(u);
+                        const double t = EVAL_SQRT(u);
                         double kp, dd;
                         cov_ori<KERNEL>(u, t, kp, dd);
                         const double hw = fma(dz, a2.y, hwxy);
                         accZ[k] = fma(kp, hw, accZ[k]);
                         if constexpr (GRAD) {
-                            const double c1 = -(dd * gpb_fast_rcp(u + prm.eps_reg)) * hw;
+                            const double c1 = -(dd * EVAL_RCP(u + prm.eps_reg)) * hw;
                             hx[k] = fma(c1, dx, fma(kp, a1.y, hx[k]));
                             hy[k] = fma(c1, dy, fma(kp, a2.x, hy[k]));
                             hz[k] = fma(c1, dz, fma(kp, a2.y, hz[k]));
