@@ -68,6 +68,8 @@ class GpbLevel(C.Structure):
         ("ld", C.c_longlong), ("n_segments", C.c_int), ("segments", C.POINTER(GpbSegment)), ("sp_offset", C.c_longlong),
         ("Z", C.c_void_p), ("G", C.c_void_p), ("block", C.c_void_p), ("final_block", C.c_void_p),
         ("faults_block", C.c_void_p), ("squeezed", C.c_void_p), ("mask", C.c_void_p),
+        ("expand_map", C.c_void_p), ("expand_src", C.c_longlong), ("expand_dst", C.c_longlong), ("expand_count", C.c_longlong),
+        ("m_combine", C.c_longlong),
     ]
 
 
@@ -104,6 +106,10 @@ SIGNATURES = {
     "gpb_model_combine": (C.c_int, [C.c_void_p, C.POINTER(GpbLevel), _P]),
     "gpb_model_run_level": (C.c_int, [C.c_void_p, C.POINTER(GpbLevel), C.c_int, _P, _LL, _P]),
     "gpb_model_solver_path": (C.c_int, [C.c_void_p, C.c_int]),
+    "gpb_corner_scratch_bytes": (_LL, [_LL]),
+    "gpb_corner_unique_count": (C.c_int, [_P, _LL, _LL, C.POINTER(GpbRegularGrid), _P, _LL, C.POINTER(_LL), _P]),
+    "gpb_corner_unique_emit": (C.c_int, [_P, _LL, _LL, C.c_double, C.c_double, C.c_double, _P, _LL, _P, _LL, _P, _P]),
+    "gpb_expand_rows": (C.c_int, [_P, _LL, _P, C.c_int, _LL, _P, _LL, _P]),
     "gpb_copy_2d": (C.c_int, [_P, _LL, _P, _LL, _LL, _LL, _P]),
     "gpb_scan_elems": (_LL, [_LL]),
     "gpb_count_marked": (C.c_int, [_P, _LL, _P, C.POINTER(_LL), _P]),

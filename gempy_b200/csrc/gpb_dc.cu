@@ -294,6 +294,80 @@ __global__ void store_counts_kernel(const long long* n_valid, const long long* n
     counts[2] = 2 * *n_tri;
 }
 
+
+// ---- corner de-duplication of an octree level --------------------------------------------------------------------------
+// The 8 corners of neighbouring voxels coincide (a lattice corner belongs to up to 8 voxels; among the children of one
+// parent 27 of the 64 corner slots are distinct).  The reference evaluates every slot; here a hash table over the corner
+// lattice finds, for every slot, the FIRST slot with the same lattice corner (atomicMin on the slot index: deterministic),
+// the owners are compacted into the list of unique corners, and the fields are evaluated on that list only; the level's
+// corner segment is then filled by a gather (gpb_expand_rows).  Duplicates therefore carry exactly the owner's value.
+__device__ __forceinline__ unsigned long long corner_code(const Lattice& L, const double* __restrict__ cen, long long ld_c, long long e) {
+    const long long v = e >> 3;
+    const int c = (int)(e & 7);
+    long long i, j, k;
+    lattice_ijk(L, cen[v], cen[ld_c + v], cen[2 * ld_c + v], i, j, k);
+    return lattice_code(L, i + ((c >> 2) & 1), j + ((c >> 1) & 1), k + (c & 1));
+}
+
+__global__ void corner_insert_kernel(const double* __restrict__ cen, long long ld_c, long long nslots, Lattice L,
+                                     unsigned long long* __restrict__ keys, int* __restrict__ vals, unsigned long long cap_mask) {
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < nslots; e += (long long)gridDim.x * blockDim.x) {
+        const unsigned long long code = corner_code(L, cen, ld_c, e);
+        unsigned long long h = hash64(code) & cap_mask;
+        while (true) {
+            const unsigned long long old = atomicCAS(&keys[h], kEmpty, code);
+            if (old == kEmpty || old == code) { atomicMin(&vals[h], (int)e); break; }
+            h = (h + 1) & cap_mask;
+        }
+    }
+}
+
+__global__ void corner_owner_kernel(const double* __restrict__ cen, long long ld_c, long long nslots, Lattice L,
+                                    const unsigned long long* __restrict__ keys, const int* __restrict__ vals,
+                                    unsigned long long cap_mask, int* __restrict__ owner, unsigned char* __restrict__ is_owner) {
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < nslots; e += (long long)gridDim.x * blockDim.x) {
+        const int o = hash_find(keys, vals, cap_mask, corner_code(L, cen, ld_c, e));
+        owner[e] = o;
+        is_owner[e] = (o == (int)e) ? 1 : 0;
+    }
+}
+
+__global__ void fill_int_kernel(int* p, long long n, int v) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
+}
+
+// unique corner coordinates (same expression as corners_kernel: centre +- half cell) and the rank of every owner
+__global__ void corner_emit_kernel(const unsigned char* __restrict__ is_owner, long long nslots, const long long* __restrict__ offsets,
+                                   const double* __restrict__ cen, long long ld_c, double hx, double hy, double hz,
+                                   int* __restrict__ uid, double* __restrict__ xyz_u, long long ld_u) {
+    __shared__ int warp_off[kScanB / 32];
+    const long long e = (long long)blockIdx.x * kScanB + threadIdx.x;
+    const int m = (e < nslots) ? (int)is_owner[e] : 0;
+    const long long p = block_rank(m, offsets, warp_off);
+    if (e < nslots) uid[e] = m ? (int)p : -1;
+    if (m) {
+        const long long v = e >> 3;
+        const int c = (int)(e & 7);
+        xyz_u[p] = cen[v] + ((c & 4) ? hx : -hx);
+        xyz_u[ld_u + p] = cen[ld_c + v] + ((c & 2) ? hy : -hy);
+        xyz_u[2 * ld_u + p] = cen[2 * ld_c + v] + ((c & 1) ? hz : -hz);
+    }
+}
+
+__global__ void corner_map_kernel(const int* __restrict__ owner, const int* __restrict__ uid, long long nslots, int* __restrict__ map) {
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < nslots; e += (long long)gridDim.x * blockDim.x)
+        map[e] = uid[owner[e]];
+}
+
+__global__ void expand_rows_kernel(const double* __restrict__ src, long long ld_src, const int* __restrict__ map, int n_rows,
+                                   long long count, double* __restrict__ dst, long long ld_dst) {
+    const long long total = (long long)n_rows * count;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const long long r = t / count, e = t - r * count;
+        dst[r * ld_dst + e] = src[r * ld_src + map[e]];
+    }
+}
+
 }  // namespace
 
 extern "C" long long gpb_dc_scratch_bytes(long long nvox) {
@@ -408,6 +482,99 @@ extern "C" int gpb_dual_contour(const gpb_stack* st, const double* eval_table, c
     tri_emit_kernel<<<(unsigned)nb3, kScanB, 0, s>>>(tflag, valid, nvox, off3, centers, ld_c, L, keys, vals, cap - 1, vid, triangles);
     GPB_LAUNCH_CHECK();
     store_counts_kernel<<<1, 1, 0, s>>>(off12 + nb12, off1 + nb1, off3 + nb3, counts);
+    GPB_LAUNCH_CHECK();
+    return GPB_OK;
+}
+
+
+// ---- corner de-duplication (see the kernels above) -----------------------------------------------------------------------
+extern "C" long long gpb_corner_scratch_bytes(long long nvox) {
+    if (nvox <= 0) return 256;
+    const long long ns = 8 * nvox;
+    unsigned long long cap = 16;
+    while (cap < (unsigned long long)(2 * ns)) cap <<= 1;
+    const long long nb = (ns + kScanB - 1) / kScanB + 1;
+    long long bytes = 0;
+    auto add = [&](long long b) { bytes += (b + 255) / 256 * 256; };
+    add((long long)cap * 8); add((long long)cap * 4); add(ns * 4); add(ns); add(nb * 8); add(ns * 4);
+    return bytes;
+}
+
+// Step 1: classify the 8 nvox corner slots (owner = first slot on the same lattice corner) and count the unique corners
+// (returned on the host: synchronises).  Step 2 (gpb_corner_unique_emit, same scratch): unique coordinates [3][ld_u] and the
+// slot -> unique index map [8 nvox].
+extern "C" int gpb_corner_unique_count(const double* centers, long long ld_c, long long nvox, const gpb_regular_grid* lattice,
+                                       void* scratch, long long scratch_bytes, long long* n_unique_host, void* stream) {
+    GPB_REQUIRE(centers && lattice && n_unique_host && nvox >= 0 && ld_c >= nvox, "bad arguments");
+    *n_unique_host = 0;
+    if (nvox == 0) return GPB_OK;
+    GPB_REQUIRE(8 * nvox < 2000000000LL, "too many corner slots for 32-bit slot indices");
+    GPB_REQUIRE(scratch && scratch_bytes >= gpb_corner_scratch_bytes(nvox), "scratch too small (gpb_corner_scratch_bytes)");
+    cudaStream_t s = (cudaStream_t)stream;
+    const long long ns = 8 * nvox;
+    unsigned long long cap = 16;
+    while (cap < (unsigned long long)(2 * ns)) cap <<= 1;
+    const long long nb = (ns + kScanB - 1) / kScanB;
+    char* p = (char*)scratch;
+    auto take = [&](long long b) { char* q = p; p += (b + 255) / 256 * 256; return q; };
+    unsigned long long* keys = (unsigned long long*)take((long long)cap * 8);
+    int* vals = (int*)take((long long)cap * 4);
+    int* owner = (int*)take(ns * 4);
+    unsigned char* is_owner = (unsigned char*)take(ns);
+    long long* off = (long long*)take((nb + 1) * 8);
+    Lattice L;
+    L.x0 = lattice->x0; L.y0 = lattice->y0; L.z0 = lattice->z0;
+    L.dx = lattice->dx; L.dy = lattice->dy; L.dz = lattice->dz;
+    L.ny1 = (long long)lattice->ny + 2; L.nz1 = (long long)lattice->nz + 2;
+    fill_u64_kernel<<<grid_for((long long)cap), kT, 0, s>>>(keys, (long long)cap, kEmpty);
+    GPB_LAUNCH_CHECK();
+    fill_int_kernel<<<grid_for((long long)cap), kT, 0, s>>>(vals, (long long)cap, 0x7fffffff);
+    GPB_LAUNCH_CHECK();
+    corner_insert_kernel<<<grid_for(ns), kT, 0, s>>>(centers, ld_c, ns, L, keys, vals, cap - 1);
+    GPB_LAUNCH_CHECK();
+    corner_owner_kernel<<<grid_for(ns), kT, 0, s>>>(centers, ld_c, ns, L, keys, vals, cap - 1, owner, is_owner);
+    GPB_LAUNCH_CHECK();
+    block_count_kernel<<<(unsigned)nb, kScanB, 0, s>>>(is_owner, ns, off);
+    GPB_LAUNCH_CHECK();
+    scan_blocks_kernel<<<1, 1024, 0, s>>>(off, nb, off + nb);
+    GPB_LAUNCH_CHECK();
+    GPB_CHECK_CUDA(cudaMemcpyAsync(n_unique_host, off + nb, sizeof(long long), cudaMemcpyDeviceToHost, s));
+    GPB_CHECK_CUDA(cudaStreamSynchronize(s));
+    return GPB_OK;
+}
+
+extern "C" int gpb_corner_unique_emit(const double* centers, long long ld_c, long long nvox, double hx, double hy, double hz,
+                                      void* scratch, long long scratch_bytes, double* xyz_unique, long long ld_u, int* map,
+                                      void* stream) {
+    GPB_REQUIRE(centers && xyz_unique && map && nvox >= 0 && ld_c >= nvox, "bad arguments");
+    if (nvox == 0) return GPB_OK;
+    GPB_REQUIRE(scratch && scratch_bytes >= gpb_corner_scratch_bytes(nvox), "scratch too small (gpb_corner_scratch_bytes)");
+    cudaStream_t s = (cudaStream_t)stream;
+    const long long ns = 8 * nvox;
+    unsigned long long cap = 16;
+    while (cap < (unsigned long long)(2 * ns)) cap <<= 1;
+    const long long nb = (ns + kScanB - 1) / kScanB;
+    char* p = (char*)scratch;
+    auto take = [&](long long b) { char* q = p; p += (b + 255) / 256 * 256; return q; };
+    take((long long)cap * 8);
+    take((long long)cap * 4);
+    int* owner = (int*)take(ns * 4);
+    unsigned char* is_owner = (unsigned char*)take(ns);
+    long long* off = (long long*)take((nb + 1) * 8);
+    int* uid = (int*)take(ns * 4);
+    corner_emit_kernel<<<(unsigned)nb, kScanB, 0, s>>>(is_owner, ns, off, centers, ld_c, hx, hy, hz, uid, xyz_unique, ld_u);
+    GPB_LAUNCH_CHECK();
+    corner_map_kernel<<<grid_for(ns), kT, 0, s>>>(owner, uid, ns, map);
+    GPB_LAUNCH_CHECK();
+    return GPB_OK;
+}
+
+// dst[r][e] = src[r][map[e]], r < n_rows, e < count (fills a level's corner segment from the unique-corner results)
+extern "C" int gpb_expand_rows(const double* src, long long ld_src, const int* map, int n_rows, long long count, double* dst,
+                               long long ld_dst, void* stream) {
+    GPB_REQUIRE(src && map && dst && n_rows >= 0 && count >= 0, "bad arguments");
+    if (n_rows == 0 || count == 0) return GPB_OK;
+    expand_rows_kernel<<<grid_for((long long)n_rows * count), kT, 0, (cudaStream_t)stream>>>(src, ld_src, map, n_rows, count, dst, ld_dst);
     GPB_LAUNCH_CHECK();
     return GPB_OK;
 }

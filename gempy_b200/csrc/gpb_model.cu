@@ -23,6 +23,8 @@ extern "C" int gpb_assemble_cov_ex(const gpb_stack* st, double* A, int lda, doub
 extern "C" int gpb_sym_solve(int n, int nk, double* A, int lda, double* b, int nrhs, int ldb, int* info, void* stream);
 extern "C" int gpb_lu_solve(int n, double* A, int lda, double* b, int nrhs, int ldb, int* ipiv, int* info, void* stream);
 extern "C" int gpb_pack_eval_table(const gpb_stack* st, const double* w, double* src, void* stream);
+extern "C" int gpb_expand_rows(const double* src, long long ld_src, const int* map, int n_rows, long long count, double* dst,
+                               long long ld_dst, void* stream);
 extern "C" int gpb_combine(const double* Z, const double* block, long long ld, long long m, int n_stacks,
                            const int* relations_host, const double* iso_min, const double* iso_max, double* final_block,
                            double* faults_block, unsigned char* squeezed_mask, unsigned char* mask, void* stream);
@@ -258,12 +260,21 @@ extern "C" int gpb_model_eval_stack(gpb_model* m, int i, const gpb_level* lvl, v
 
 extern "C" int gpb_model_combine(gpb_model* m, const gpb_level* lvl, void* stream) {
     GPB_REQUIRE(m && lvl && lvl->final_block && lvl->faults_block && lvl->squeezed, "bad arguments");
-    long long mtot = 0;
-    for (int k = 0; k < lvl->n_segments; ++k) {
-        const long long e = lvl->segments[k].out_offset + lvl->segments[k].count;
-        if (e > mtot) mtot = e;
+    const int n_st = (int)m->stacks.size();
+    if (lvl->expand_map != nullptr && lvl->expand_count > 0) {       // corner segment <- unique-corner results
+        int rc = gpb_expand_rows(lvl->Z + lvl->expand_src, lvl->ld, lvl->expand_map, n_st, lvl->expand_count, lvl->Z + lvl->expand_dst, lvl->ld, stream);
+        if (!rc) rc = gpb_expand_rows(lvl->block + lvl->expand_src, lvl->ld, lvl->expand_map, n_st, lvl->expand_count, lvl->block + lvl->expand_dst, lvl->ld, stream);
+        if (!rc && lvl->G != nullptr)
+            rc = gpb_expand_rows(lvl->G + lvl->expand_src, lvl->ld, lvl->expand_map, 3 * n_st, lvl->expand_count, lvl->G + lvl->expand_dst, lvl->ld, stream);
+        if (rc) return rc;
     }
-    return gpb_combine(lvl->Z, lvl->block, lvl->ld, mtot, (int)m->stacks.size(), m->rel.data(), m->iso_min, m->iso_max,
+    long long mtot = lvl->m_combine;
+    if (mtot <= 0)
+        for (int k = 0; k < lvl->n_segments; ++k) {
+            const long long e = lvl->segments[k].out_offset + lvl->segments[k].count;
+            if (e > mtot) mtot = e;
+        }
+    return gpb_combine(lvl->Z, lvl->block, lvl->ld, mtot, n_st, m->rel.data(), m->iso_min, m->iso_max,
                        lvl->final_block, lvl->faults_block, lvl->squeezed, lvl->mask, stream);
 }
 

@@ -410,44 +410,44 @@ class B200Engine:
                                                     fv, L, _ptr(Z, o8), gp[0], gp[1], gp[2], self.stream))
 
     # -- all stacks on one domain: the level executor ------------------------------------------------------------
-    def run_level(self, tables: ModelTables, xyz: Optional[torch.Tensor], parts: List[Tuple[str, int]],
-                  dense: Optional[Tuple[_lib.GpbRegularGrid, int, int]], solve: bool, gradient: bool,
-                  comm: Optional[Comm] = None) -> FieldsOnDevice:
-        """Evaluate every stack on one level.  ``xyz`` [3, Lx]: the explicit points in the order of ``parts``
-        (name, count) without the dense grid; ``dense`` = (grid descriptor, first index, count) is evaluated from the
-        linear index and sits right after the first part (the octree centres) in the outputs.  The last part must be
-        the model's surface points.  With a multi-rank ``comm`` the stacks are walked one by one and every fault
-        block's minimum is all-reduced before the next stack needs it; otherwise one native call does the level."""
+    def run_level(self, tables: ModelTables, eval_segs: List[tuple], out_parts: List[Tuple[str, int]], solve: bool,
+                  gradient: bool, comm: Optional[Comm] = None, hidden: int = 0,
+                  expand: Optional[Tuple[torch.Tensor, int, int, int]] = None) -> FieldsOnDevice:
+        """Evaluate every stack on one level.
+
+        ``out_parts``: the level's output segments (name, count) in output order WITHOUT the surface-point tail, which
+        always comes last; ``eval_segs``: what is evaluated, tuples ("points", count, out_offset, xyz_tensor_view) or
+        ("regular", count, out_offset, (grid descriptor, first index)) -- the surface-point tail must be covered by one of
+        them.  ``hidden`` extra output columns beyond the official length hold the de-duplicated corners; ``expand`` =
+        (map, src_offset, dst_offset, count) fills the corner segment from them before the combination.
+        With a multi-rank ``comm`` the stacks are walked one by one and every fault block's minimum is all-reduced before
+        the next stack needs it; otherwise one native call does the level."""
         comm = comm or Comm()
         n_st = len(tables)
-        n_dense = dense[2] if dense is not None else 0
-        Lx = sum(c for _, c in parts)
-        L = Lx + n_dense
         n_sp = int(tables.sp_all.shape[1])
-        assert parts[-1] == ("surface_points", n_sp)
-        Z = self.empty(n_st, L)
-        G = self.empty(n_st, 3, L) if gradient else None
-        block = self.empty(n_st, L)
-        final_block = self.empty(L)
-        faults_block = self.empty(L)
-        squeezed = self.empty(n_st, L, dtype=torch.uint8)
-        mask = self.empty(n_st, L, dtype=torch.uint8)
-        ld_xyz = int(xyz.stride(0)) if xyz is not None else 0
-        segs = []
-        if dense is None:
-            segs.append((_lib.GPB_SEG_POINTS, Lx, 0, _ptr(xyz), ld_xyz, None, 0))
-        else:
-            n0 = parts[0][1]
-            segs.append((_lib.GPB_SEG_POINTS, n0, 0, _ptr(xyz), ld_xyz, None, 0))
-            segs.append((_lib.GPB_SEG_REGULAR, n_dense, n0, None, 0, dense[0], dense[1]))
-            segs.append((_lib.GPB_SEG_POINTS, Lx - n0, n0 + n_dense, _ptr(xyz, 8 * n0), ld_xyz, None, 0))
-        arr = (_lib.GpbSegment * len(segs))()
-        for k, (kind, cnt, off, xp, ldx, gd, i0) in enumerate(segs):
-            arr[k].kind, arr[k].count, arr[k].out_offset, arr[k].xyz, arr[k].ld_xyz, arr[k].i0 = kind, cnt, off, xp, ldx, i0
-            if gd is not None:
-                arr[k].grid = gd
-        lvl = _lib.GpbLevel(L, len(segs), arr, L - n_sp, _ptr(Z), _ptr(G), _ptr(block), _ptr(final_block), _ptr(faults_block),
-                            _ptr(squeezed), _ptr(mask))
+        L = sum(c for _, c in out_parts) + n_sp
+        ld = L + hidden
+        Z = self.empty(n_st, ld)
+        G = self.empty(n_st, 3, ld) if gradient else None
+        block = self.empty(n_st, ld)
+        final_block = self.empty(ld)
+        faults_block = self.empty(ld)
+        squeezed = self.empty(n_st, ld, dtype=torch.uint8)
+        mask = self.empty(n_st, ld, dtype=torch.uint8)
+        arr = (_lib.GpbSegment * len(eval_segs))()
+        keep = []
+        for k, (kind, cnt, off, what) in enumerate(eval_segs):
+            arr[k].count, arr[k].out_offset = int(cnt), int(off)
+            if kind == "regular":
+                arr[k].kind, arr[k].grid, arr[k].i0 = _lib.GPB_SEG_REGULAR, what[0], int(what[1])
+            else:
+                arr[k].kind, arr[k].xyz, arr[k].ld_xyz = _lib.GPB_SEG_POINTS, _ptr(what), int(what.stride(0))
+                keep.append(what)
+        lvl = _lib.GpbLevel(ld, len(eval_segs), arr, L - n_sp, _ptr(Z), _ptr(G), _ptr(block), _ptr(final_block), _ptr(faults_block),
+                            _ptr(squeezed), _ptr(mask), None, 0, 0, 0, L)
+        if expand is not None:
+            lvl.expand_map, lvl.expand_src, lvl.expand_dst, lvl.expand_count = _ptr(expand[0]), int(expand[1]), int(expand[2]), int(expand[3])
+            keep.append(expand[0])
         lib, h, stream = self.lib, tables.handle, self.stream
         ws, ws_bytes = None, 0
         if solve:                                         # scratch of the largest system, owned by torch's allocator
@@ -463,12 +463,12 @@ class B200Engine:
                 if tables.rel[i] == StackRelationType.FAULT.value:
                     comm.all_reduce_min(tables.fault_min[i:i + 1])
             _lib.check(lib.gpb_model_combine(h, C.byref(lvl), stream))
-        out_segments = [Segment(parts[0][0], parts[0][1])]
-        if dense is not None:
-            out_segments.append(Segment("dense_grid", n_dense))
-        out_segments += [Segment(nm, c) for nm, c in parts[1:-1]]
-        return FieldsOnDevice(out_segments, L - n_sp, Z, G, block, final_block, faults_block, squeezed, mask,
-                              tables.isovalues, tables.weights, [None] * n_st, tables.eval_tables)
+        out_segments = [Segment(nm, c) for nm, c in out_parts]
+        f = FieldsOnDevice(out_segments, L - n_sp, Z[:, :L], None if G is None else G[:, :, :L], block[:, :L], final_block[:L],
+                           faults_block[:L], squeezed[:, :L], mask[:, :L], tables.isovalues, tables.weights, [None] * n_st,
+                           tables.eval_tables)
+        f._keep = keep
+        return f
 
     def gradient_at(self, st: StackTables, src: torch.Tensor, xyz: torch.Tensor) -> torch.Tensor:
         """Engine-convention gradient [3, m] of one stack's field at explicit points.  The fault drift has no
@@ -493,7 +493,8 @@ class B200Engine:
     def corners_of(self, centers: torch.Tensor, d: np.ndarray) -> torch.Tensor:
         nv = centers.shape[1]
         out = self.empty(3, 8 * nv)
-        self.corners_into(centers, nv, d, out)
+        with torch.cuda.device(self.device):
+            self.corners_into(centers, nv, d, out)
         return out
 
     def mark(self, nv: int, lith_corners: torch.Tensor, fault_corners: torch.Tensor, force_all: bool) -> torch.Tensor:
@@ -752,69 +753,91 @@ def _compute_model(eng: B200Engine, interpolation_input, options, data_descripto
     prev_regular = root
     dc_payload = None
     gravity = None
-    centers_full: Optional[torch.Tensor] = None        # [3, nv] (possibly a strided view) of the current level
+    dedupe = os.environ.get("GPB_NO_CORNER_DEDUPE") is None
     pending = None                                      # (parent centres, nv_parent, d_parent, mark, offsets) of the next emission
     nv = int(np.prod(root.regular_grid_shape))
     for lvl in range(n_levels):
         need_corners = (lvl < n_levels - 1) or (lvl == dc_level)
         v0, v1 = comm.shard(nv)
         nvl = v1 - v0
-        parts: List[Tuple[str, int]] = [("octree_grid", nvl)]
+        # ---- this level's voxel centres: [3, nv], the whole list on every rank (children are emitted by every rank)
+        if lvl == 0:
+            ax = root.axis_coords()
+            gx, gy, gz = np.meshgrid(*ax, indexing="ij")
+            centers_full = torch.as_tensor(np.stack([gx.ravel(), gy.ravel(), gz.ravel()]) + GRID_SHIFT, dtype=F64, device=eng.device)
+        else:
+            p_cen, p_nv, p_d, p_mark, p_off = pending
+            centers_full = eng.empty(3, nv)
+            eng.emit_into(p_cen, p_nv, p_d, p_mark, p_off, centers_full)
+        centers_loc = centers_full[:, v0:v1]
+        out_parts: List[Tuple[str, int]] = [("octree_grid", nvl)]
         totals = [nv]
-        dense = None
+        eval_segs: List[tuple] = [("points", nvl, 0, centers_loc)]
+        off = nvl
         ex_loc = []
         if lvl == 0:
             if dense_desc is not None:
                 i0, i1 = comm.shard(grid.dense_grid.n_points)
-                dense = (dense_desc, i0, i1 - i0)
+                out_parts.append(("dense_grid", i1 - i0))
                 totals.append(grid.dense_grid.n_points)
+                eval_segs.append(("regular", i1 - i0, off, (dense_desc, i0)))
+                off += i1 - i0
             for name, vals in extras_host:
                 i0, i1 = comm.shard(vals.shape[1])
-                ex_loc.append((name, vals[:, i0:i1]))
-                parts.append((name, i1 - i0))
+                ex_loc.append(vals[:, i0:i1])
+                out_parts.append((name, i1 - i0))
                 totals.append(vals.shape[1])
-        if need_corners:
-            parts.append(("corners", 8 * nvl))
-            totals.append(8 * nv)
-        parts.append(("surface_points", n_sp))
-        Lx = sum(c for _, c in parts)
-        xyz = eng.empty(3, Lx)
-        # ---- this level's voxel centres
-        if lvl == 0:
-            ax = root.axis_coords()
-            gx, gy, gz = np.meshgrid(*ax, indexing="ij")
-            c_host = np.stack([gx.ravel(), gy.ravel(), gz.ravel()]) + GRID_SHIFT
-            c_dev = torch.as_tensor(c_host, dtype=F64, device=eng.device)
-            if comm.world == 1:
-                eng.copy_rows(xyz[:, :nv], c_dev)
-                centers_full = xyz[:, :nv]
-            else:
-                centers_full = c_dev
-        else:
-            p_cen, p_nv, p_d, p_mark, p_off = pending
-            if comm.world == 1:
-                eng.emit_into(p_cen, p_nv, p_d, p_mark, p_off, xyz)          # children land in the level's buffer directly
-                centers_full = xyz[:, :nv]
-            else:
-                centers_full = eng.empty(3, nv)
-                eng.emit_into(p_cen, p_nv, p_d, p_mark, p_off, centers_full)
-        if comm.world > 1 and nvl:
-            eng.copy_rows(xyz[:, :nvl], centers_full[:, v0:v1])
-        off = nvl
-        for name, vals in ex_loc:
+        n_ex = sum(v.shape[1] for v in ex_loc)
+        # ---- corners: de-duplicated (unique lattice corners evaluated once, the corner segment filled by a gather) or explicit
+        n_u, cmap, scratch = 0, None, None
+        use_dedupe = need_corners and dedupe and nvl > 0
+        if use_dedupe:
+            lat = _lattice(root, lvl)
+            sb = int(eng.lib.gpb_corner_scratch_bytes(nvl))
+            scratch = eng.empty((sb + 7) // 8)
+            nu_host = C.c_longlong(0)
+            _lib.check(eng.lib.gpb_corner_unique_count(_ptr(centers_loc), centers_loc.stride(0), nvl, C.byref(lat), _ptr(scratch), sb,
+                                                       C.byref(nu_host), eng.stream))
+            n_u = int(nu_host.value)
+        n_cor_explicit = 8 * nvl if (need_corners and not use_dedupe) else 0
+        pts = eng.empty(3, n_ex + n_cor_explicit + n_sp + n_u)          # explicit grids | (corners) | surface points | unique corners
+        o = 0
+        for vals in ex_loc:
             k = vals.shape[1]
             if k:
-                eng.copy_rows(xyz[:, off:off + k], torch.as_tensor(np.ascontiguousarray(vals), dtype=F64, device=eng.device))
-            off += k
-        corners_loc = None
+                eng.copy_rows(pts[:, o:o + k], torch.as_tensor(np.ascontiguousarray(vals), dtype=F64, device=eng.device))
+            o += k
+        if n_ex:
+            eval_segs.append(("points", n_ex, off, pts[:, :n_ex]))
+        off += n_ex
         if need_corners:
-            corners_loc = xyz[:, off:off + 8 * nvl]
-            eng.corners_into(xyz, nvl, d, corners_loc)
+            out_parts.append(("corners", 8 * nvl))
+            totals.append(8 * nv)
+        corner_off = off
+        if n_cor_explicit:
+            eng.corners_into(centers_loc, nvl, d, pts[:, n_ex:n_ex + n_cor_explicit])
+            # explicit grids and corners are contiguous in `pts` and in the outputs: one segment
+            if n_ex:
+                eval_segs.pop()
+                off -= n_ex
+            eval_segs.append(("points", n_ex + n_cor_explicit, off, pts[:, :n_ex + n_cor_explicit]))
+            off += n_ex + n_cor_explicit
+        elif need_corners:
             off += 8 * nvl
-        eng.copy_rows(xyz[:, off:off + n_sp], tables.sp_all)
+        sp_off = off                                                    # = L - n_sp
+        eng.copy_rows(pts[:, n_ex + n_cor_explicit:n_ex + n_cor_explicit + n_sp], tables.sp_all)
+        expand = None
+        if use_dedupe:
+            cmap = eng.empty(8 * nvl, dtype=torch.int32)
+            tail = pts[:, n_ex + n_sp:]
+            _lib.check(eng.lib.gpb_corner_unique_emit(_ptr(centers_loc), centers_loc.stride(0), nvl, d[0] / 2, d[1] / 2, d[2] / 2,
+                                                      _ptr(scratch), sb, _ptr(tail), tail.stride(0), _ptr(cmap), eng.stream))
+            expand = (cmap, sp_off + n_sp, corner_off, 8 * nvl)
+        # surface points and (behind them, beyond the official length) the unique corners: one segment
+        eval_segs.append(("points", n_sp + n_u, sp_off, pts[:, n_ex + n_cor_explicit:]))
         # ---- all stacks (one native call on a single rank)
-        f_loc = eng.run_level(tables, xyz, parts, dense, solve=(lvl == 0), gradient=gradient, comm=comm)
-        f_loc._xyz = xyz                                  # keeps the centres / corners views alive with the fields
+        f_loc = eng.run_level(tables, eval_segs, out_parts, solve=(lvl == 0), gradient=gradient, comm=comm, hidden=n_u, expand=expand)
+        f_loc._xyz = (centers_full, pts)                 # keeps the coordinate buffers alive with the fields
         if lvl == 0 and getattr(ko, "compute_condition_number", False):
             conds = []
             for i, st in enumerate(tables):
@@ -826,14 +849,10 @@ def _compute_model(eng: B200Engine, interpolation_input, options, data_descripto
         # ---- refinement marks: local test, all-gathered so that every rank emits the identical child list
         mark_full = None
         if lvl < n_levels - 1:
-            c_off = f_loc.seg_offset("corners")
-            mark_loc = eng.mark(nvl, f_loc.final_block[c_off:c_off + 8 * nvl], f_loc.faults_block[c_off:c_off + 8 * nvl],
-                                force_all=lvl < int(eo.octree_min_level))
+            mark_loc = eng.mark(nvl, f_loc.final_block[corner_off:corner_off + 8 * nvl],
+                                f_loc.faults_block[corner_off:corner_off + 8 * nvl], force_all=lvl < int(eo.octree_min_level))
             mark_full = comm.all_gather_cat(mark_loc, nv)
         f = eng.gather_fields(f_loc, totals, comm)
-        corners = corners_loc
-        if comm.world > 1 and need_corners:
-            corners = eng.corners_of(centers_full, d)
         # ---- host containers of this level
         centers_host = Deferred(lambda c=centers_full: _np(c).T.copy())     # explicit centres (shift included), as evaluated
         if lvl == 0:
@@ -849,15 +868,15 @@ def _compute_model(eng: B200Engine, interpolation_input, options, data_descripto
             lvl_grid = EngineGrid(octree_grid=og)
         outs = _level_outputs(f, lvl_grid, rel_enum, tables.iso_host)
         level = OctreeLevel(grid_centers=lvl_grid, outputs_centers=outs,
-                            _grid_corners=None if corners is None else
-                            Deferred(lambda c=corners: EngineGrid.from_xyz_coords(_np(c).T)))
+                            _grid_corners=None if not need_corners else
+                            Deferred(lambda c=centers_full, dd=d.copy(): EngineGrid.from_xyz_coords(_np(eng.corners_of(c, dd)).T)))
         level._device_fields = f
         octree_levels.append(level)
         levels_dev.append((centers_full, nv, f))
         if lvl == 0 and geophysics_input is not None:
             gravity = _forward_gravity(eng, geophysics_input, grid.geophysics_grid, f)
         if lvl == dc_level:
-            dc_payload = (lvl, centers_full, d.copy(), corners, f)
+            dc_payload = (lvl, centers_full, d.copy(), eng.corners_of(centers_full, d), f)
         if lvl == n_levels - 1:
             break
         level._marked_voxels = Deferred(lambda mk=mark_full: _np(mk).astype(bool))

@@ -220,6 +220,12 @@ typedef struct gpb_level {
     double* faults_block;          /* [ld] */
     unsigned char* squeezed;       /* [n_stacks][ld] */
     unsigned char* mask;           /* [n_stacks][ld] or NULL */
+    /* de-duplicated corners (optional, expand_map != NULL): the unique corners were evaluated at output positions
+     * [expand_src, ...); gpb_model_combine first fills the corner segment [expand_dst, expand_dst + expand_count) of Z, G
+     * and block with out[expand_dst + e] = out[expand_src + expand_map[e]], and combines m_combine points. */
+    const int* expand_map;
+    long long expand_src, expand_dst, expand_count;
+    long long m_combine;           /* points the combination covers (0: up to the end of the last segment) */
 } gpb_level;
 
 typedef struct gpb_model gpb_model;
@@ -241,6 +247,19 @@ int  gpb_model_combine(gpb_model* m, const gpb_level* lvl, void* stream);
 int  gpb_model_run_level(gpb_model* m, const gpb_level* lvl, int solve, void* workspace, long long workspace_bytes,
                          void* stream);
 int  gpb_model_solver_path(const gpb_model* m, int i);
+
+/* Corner de-duplication of an octree level: the 8 nvox corner slots of the voxel list (8 per voxel, the sign pattern of
+ * gpb_voxel_corners) are grouped by lattice corner; _count returns the number of distinct corners (host; synchronises),
+ * _emit writes their coordinates [3][ld_u] and map[8 nvox] (slot -> unique index; the representative of a group is its
+ * first slot, so the result does not depend on scheduling).  Both calls share `scratch` (gpb_corner_scratch_bytes).
+ * gpb_expand_rows: dst[r][e] = src[r][map[e]]. */
+long long gpb_corner_scratch_bytes(long long nvox);
+int gpb_corner_unique_count(const double* centers, long long ld_c, long long nvox, const gpb_regular_grid* lattice,
+                            void* scratch, long long scratch_bytes, long long* n_unique_host, void* stream);
+int gpb_corner_unique_emit(const double* centers, long long ld_c, long long nvox, double hx, double hy, double hz,
+                           void* scratch, long long scratch_bytes, double* xyz_unique, long long ld_u, int* map, void* stream);
+int gpb_expand_rows(const double* src, long long ld_src, const int* map, int n_rows, long long count, double* dst,
+                    long long ld_dst, void* stream);
 
 /* dst[r][0..cols) = src[r][0..cols) for r < rows (device to device, on the copy engine). */
 int gpb_copy_2d(double* dst, long long ld_dst, const double* src, long long ld_src, long long rows, long long cols, void* stream);
