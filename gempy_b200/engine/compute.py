@@ -21,6 +21,7 @@ import contextlib
 import ctypes as C
 import os
 import warnings
+import weakref
 from dataclasses import dataclass
 from typing import List, Optional, Sequence, Tuple
 
@@ -999,8 +1000,12 @@ def _raw_arrays(eng: B200Engine, sol: Solutions, levels_dev, grid: EngineGrid, o
         ra.set_lazy("mask_matrix", lambda: np.stack([o.scalar_fields.mask_components[sl] for o in outs]))
         ra.set_lazy("mask_matrix_squeezed", lambda: np.stack([o.combined_scalar_field.squeezed_mask_array[sl] for o in outs]))
 
+        ra_ref = weakref.ref(ra)          # no strong self-reference: a cycle would keep the level's device buffers alive
+                                          # until the cyclic garbage collector runs (4.6 GB per octree-8 solution)
+
         def litho_faults():
-            lb, fbk = ra.lith_block, ra.fault_block
+            r = ra_ref()
+            lb, fbk = r.lith_block, r.fault_block
             return lb + fbk * max(len(np.unique(lb)), 1)
         ra.set_lazy("litho_faults_block", litho_faults)
     for name, attr in (("custom", "custom_grid_slice"), ("topography", "topography_slice"), ("sections", "sections_slice")):
