@@ -553,7 +553,7 @@ class B200Engine:
 def compute_dense_fields(interpolation_input: InterpolationInput, options: InterpolationOptions,
                          data_descriptor: InputDataDescriptor, *, stack: int = 0, engine: Optional[B200Engine] = None,
                          point_range: Optional[Tuple[int, int]] = None, out: Optional[torch.Tensor] = None,
-                         n_slabs: int = 8, device: Optional[int] = None) -> torch.Tensor:
+                         n_slabs: int = 16, device: Optional[int] = None) -> torch.Tensor:
     """Scalar field and gradient of one (fault-free) stack on the dense regular grid, host in / host out.
 
     The reference obtains these with ``compute_model`` + ``evaluation_options.compute_scalar_gradient = True`` and reads
