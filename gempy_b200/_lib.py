@@ -59,7 +59,7 @@ GPB_SEG_POINTS, GPB_SEG_REGULAR = 0, 1
 class GpbSegment(C.Structure):
     _fields_ = [
         ("kind", C.c_int), ("count", C.c_longlong), ("out_offset", C.c_longlong), ("xyz", C.c_void_p),
-        ("ld_xyz", C.c_longlong), ("grid", GpbRegularGrid), ("i0", C.c_longlong),
+        ("ld_xyz", C.c_longlong), ("grid", GpbRegularGrid), ("i0", C.c_longlong), ("count_dev", C.c_void_p),
     ]
 
 
@@ -108,7 +108,7 @@ SIGNATURES = {
     "gpb_model_solver_path": (C.c_int, [C.c_void_p, C.c_int]),
     "gpb_corner_scratch_bytes": (_LL, [_LL]),
     "gpb_corner_unique_count": (C.c_int, [_P, _LL, _LL, C.POINTER(GpbRegularGrid), _P, _LL, C.POINTER(_LL), _P]),
-    "gpb_corner_unique_emit": (C.c_int, [_P, _LL, _LL, C.c_double, C.c_double, C.c_double, _P, _LL, _P, _LL, _P, _P]),
+    "gpb_corner_unique_emit": (C.c_int, [_P, _LL, _LL, C.c_double, C.c_double, C.c_double, _P, _LL, _P, _LL, _P, _LL, _P, _P]),
     "gpb_expand_rows": (C.c_int, [_P, _LL, _P, C.c_int, _LL, _P, _LL, _P]),
     "gpb_copy_2d": (C.c_int, [_P, _LL, _P, _LL, _LL, _LL, _P]),
     "gpb_scan_elems": (_LL, [_LL]),

@@ -359,6 +359,8 @@ __global__ void corner_map_kernel(const int* __restrict__ owner, const int* __re
         map[e] = uid[owner[e]];
 }
 
+__global__ void add_base_kernel(const long long* n, long long base, long long* out) { *out = base + *n; }
+
 __global__ void expand_rows_kernel(const double* __restrict__ src, long long ld_src, const int* __restrict__ map, int n_rows,
                                    long long count, double* __restrict__ dst, long long ld_dst) {
     const long long total = (long long)n_rows * count;
@@ -505,8 +507,8 @@ extern "C" long long gpb_corner_scratch_bytes(long long nvox) {
 // slot -> unique index map [8 nvox].
 extern "C" int gpb_corner_unique_count(const double* centers, long long ld_c, long long nvox, const gpb_regular_grid* lattice,
                                        void* scratch, long long scratch_bytes, long long* n_unique_host, void* stream) {
-    GPB_REQUIRE(centers && lattice && n_unique_host && nvox >= 0 && ld_c >= nvox, "bad arguments");
-    *n_unique_host = 0;
+    GPB_REQUIRE(centers && lattice && nvox >= 0 && ld_c >= nvox, "bad arguments");
+    if (n_unique_host) *n_unique_host = 0;
     if (nvox == 0) return GPB_OK;
     GPB_REQUIRE(8 * nvox < 2000000000LL, "too many corner slots for 32-bit slot indices");
     GPB_REQUIRE(scratch && scratch_bytes >= gpb_corner_scratch_bytes(nvox), "scratch too small (gpb_corner_scratch_bytes)");
@@ -538,14 +540,16 @@ extern "C" int gpb_corner_unique_count(const double* centers, long long ld_c, lo
     GPB_LAUNCH_CHECK();
     scan_blocks_kernel<<<1, 1024, 0, s>>>(off, nb, off + nb);
     GPB_LAUNCH_CHECK();
-    GPB_CHECK_CUDA(cudaMemcpyAsync(n_unique_host, off + nb, sizeof(long long), cudaMemcpyDeviceToHost, s));
-    GPB_CHECK_CUDA(cudaStreamSynchronize(s));
+    if (n_unique_host != nullptr) {
+        GPB_CHECK_CUDA(cudaMemcpyAsync(n_unique_host, off + nb, sizeof(long long), cudaMemcpyDeviceToHost, s));
+        GPB_CHECK_CUDA(cudaStreamSynchronize(s));
+    }
     return GPB_OK;
 }
 
 extern "C" int gpb_corner_unique_emit(const double* centers, long long ld_c, long long nvox, double hx, double hy, double hz,
                                       void* scratch, long long scratch_bytes, double* xyz_unique, long long ld_u, int* map,
-                                      void* stream) {
+                                      long long count_base, long long* count_dev_out, void* stream) {
     GPB_REQUIRE(centers && xyz_unique && map && nvox >= 0 && ld_c >= nvox, "bad arguments");
     if (nvox == 0) return GPB_OK;
     GPB_REQUIRE(scratch && scratch_bytes >= gpb_corner_scratch_bytes(nvox), "scratch too small (gpb_corner_scratch_bytes)");
@@ -566,6 +570,10 @@ extern "C" int gpb_corner_unique_emit(const double* centers, long long ld_c, lon
     GPB_LAUNCH_CHECK();
     corner_map_kernel<<<grid_for(ns), kT, 0, s>>>(owner, uid, ns, map);
     GPB_LAUNCH_CHECK();
+    if (count_dev_out != nullptr) {
+        add_base_kernel<<<1, 1, 0, s>>>(off + nb, count_base, count_dev_out);
+        GPB_LAUNCH_CHECK();
+    }
     return GPB_OK;
 }
 

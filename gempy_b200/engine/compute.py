@@ -418,8 +418,8 @@ class B200Engine:
 
         ``out_parts``: the level's output segments (name, count) in output order WITHOUT the surface-point tail, which
         always comes last; ``eval_segs``: what is evaluated, tuples ("points", count, out_offset, xyz_tensor_view) or
-        ("regular", count, out_offset, (grid descriptor, first index)) -- the surface-point tail must be covered by one of
-        them.  ``hidden`` extra output columns beyond the official length hold the de-duplicated corners; ``expand`` =
+        ("regular", count, out_offset, (grid descriptor, first index)), optionally followed by a device int64 tensor with the
+        actual point count (<= count) -- the surface-point tail must be covered by one of them.  ``hidden`` extra output columns beyond the official length hold the de-duplicated corners; ``expand`` =
         (map, src_offset, dst_offset, count) fills the corner segment from them before the combination.
         With a multi-rank ``comm`` the stacks are walked one by one and every fault block's minimum is all-reduced before
         the next stack needs it; otherwise one native call does the level."""
@@ -437,8 +437,12 @@ class B200Engine:
         mask = self.empty(n_st, ld, dtype=torch.uint8)
         arr = (_lib.GpbSegment * len(eval_segs))()
         keep = []
-        for k, (kind, cnt, off, what) in enumerate(eval_segs):
+        for k, seg in enumerate(eval_segs):
+            kind, cnt, off, what = seg[:4]
             arr[k].count, arr[k].out_offset = int(cnt), int(off)
+            if len(seg) > 4 and seg[4] is not None:           # device-side point count (compacted list)
+                arr[k].count_dev = _ptr(seg[4])
+                keep.append(seg[4])
             if kind == "regular":
                 arr[k].kind, arr[k].grid, arr[k].i0 = _lib.GPB_SEG_REGULAR, what[0], int(what[1])
             else:
@@ -721,6 +725,19 @@ def compute_model(interpolation_input: InterpolationInput, options: Interpolatio
         return _compute_model(eng, interpolation_input, options, data_descriptor, geophysics_input, comm)
 
 
+def compute_model_at(interpolation_input: InterpolationInput, options: InterpolationOptions,
+                     data_descriptor: InputDataDescriptor, at: np.ndarray, **kwargs) -> np.ndarray:
+    """Engine-level mirror of ``gp.compute_model_at`` (gempy/API/compute_API.py:89-114): the custom grid becomes the only
+    active extra grid (``set_custom_grid(..., reset=True)``, grid_API.py:91-96; the octree grid always rides along,
+    _engine_factory.py:88-96), the model is computed, and the lithology ids at ``at`` (TRANSFORMED coordinates, like
+    everything at the engine boundary) come back as ``raw_arrays.custom``.  Like the reference, this replaces
+    ``interpolation_input.grid`` (side effect)."""
+    g = interpolation_input.grid
+    interpolation_input.grid = EngineGrid(octree_grid=g.octree_grid, custom_grid=GenericGrid(np.asarray(at, dtype=np.float64)))
+    sol = compute_model(interpolation_input, options, data_descriptor, **kwargs)
+    return sol.raw_arrays.custom
+
+
 def _compute_model(eng: B200Engine, interpolation_input, options, data_descriptor, geophysics_input, comm: Comm) -> Solutions:
     ii, desc = interpolation_input, data_descriptor
     eo = options.evaluation_options
@@ -796,10 +813,11 @@ def _compute_model(eng: B200Engine, interpolation_input, options, data_descripto
             lat = _lattice(root, lvl)
             sb = int(eng.lib.gpb_corner_scratch_bytes(nvl))
             scratch = eng.empty((sb + 7) // 8)
-            nu_host = C.c_longlong(0)
+            # no synchronisation: the count stays on the device; below the root a level is made of sibling octets with at most
+            # 27 distinct corners per 8 voxels (+ slack for octets cut by a rank boundary), which bounds the buffers
             _lib.check(eng.lib.gpb_corner_unique_count(_ptr(centers_loc), centers_loc.stride(0), nvl, C.byref(lat), _ptr(scratch), sb,
-                                                       C.byref(nu_host), eng.stream))
-            n_u = int(nu_host.value)
+                                                       None, eng.stream))
+            n_u = 8 * nvl if lvl == 0 else min(8 * nvl, 27 * ((nvl + 7) // 8 + 2))
         n_cor_explicit = 8 * nvl if (need_corners and not use_dedupe) else 0
         pts = eng.empty(3, n_ex + n_cor_explicit + n_sp + n_u)          # explicit grids | (corners) | surface points | unique corners
         o = 0
@@ -831,11 +849,13 @@ def _compute_model(eng: B200Engine, interpolation_input, options, data_descripto
         if use_dedupe:
             cmap = eng.empty(8 * nvl, dtype=torch.int32)
             tail = pts[:, n_ex + n_sp:]
+            cnt_dev = eng.empty(1, dtype=torch.int64)                       # n_sp + number of unique corners, on the device
             _lib.check(eng.lib.gpb_corner_unique_emit(_ptr(centers_loc), centers_loc.stride(0), nvl, d[0] / 2, d[1] / 2, d[2] / 2,
-                                                      _ptr(scratch), sb, _ptr(tail), tail.stride(0), _ptr(cmap), eng.stream))
+                                                      _ptr(scratch), sb, _ptr(tail), tail.stride(0), _ptr(cmap), n_sp, _ptr(cnt_dev),
+                                                      eng.stream))
             expand = (cmap, sp_off + n_sp, corner_off, 8 * nvl)
         # surface points and (behind them, beyond the official length) the unique corners: one segment
-        eval_segs.append(("points", n_sp + n_u, sp_off, pts[:, n_ex + n_cor_explicit:]))
+        eval_segs.append(("points", n_sp + n_u, sp_off, pts[:, n_ex + n_cor_explicit:], cnt_dev if use_dedupe else None))
         # ---- all stacks (one native call on a single rank)
         f_loc = eng.run_level(tables, eval_segs, out_parts, solve=(lvl == 0), gradient=gradient, comm=comm, hidden=n_u, expand=expand)
         f_loc._xyz = (centers_full, pts)                 # keeps the coordinate buffers alive with the fields

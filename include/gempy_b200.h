@@ -205,6 +205,8 @@ typedef struct gpb_segment {
     long long ld_xyz;
     gpb_regular_grid grid;         /* REGULAR */
     long long i0;                  /* REGULAR: first grid index */
+    const long long* count_dev;    /* POINTS, optional (device): the actual number of points (<= count), read by the kernel --
+                                      lets a compacted list be evaluated without a host synchronisation */
 } gpb_segment;
 
 typedef struct gpb_level {
@@ -256,8 +258,12 @@ int  gpb_model_solver_path(const gpb_model* m, int i);
 long long gpb_corner_scratch_bytes(long long nvox);
 int gpb_corner_unique_count(const double* centers, long long ld_c, long long nvox, const gpb_regular_grid* lattice,
                             void* scratch, long long scratch_bytes, long long* n_unique_host, void* stream);
+/* n_unique_host == NULL: no synchronisation, the count stays on the device.  A voxel list made of complete sibling
+ * octets (every octree level below the root) has at most 27 distinct corners per 8 voxels, so buffers can be sized
+ * without knowing the count.  count_dev_out (optional, device): receives count_base + number of unique corners. */
 int gpb_corner_unique_emit(const double* centers, long long ld_c, long long nvox, double hx, double hy, double hz,
-                           void* scratch, long long scratch_bytes, double* xyz_unique, long long ld_u, int* map, void* stream);
+                           void* scratch, long long scratch_bytes, double* xyz_unique, long long ld_u, int* map,
+                           long long count_base, long long* count_dev_out, void* stream);
 int gpb_expand_rows(const double* src, long long ld_src, const int* map, int n_rows, long long count, double* dst,
                     long long ld_dst, void* stream);
 

@@ -85,6 +85,15 @@ def test_backend_selector_dispatches_into_the_b200_backend(gp):
             gp.compute_model(m, cfg)
     with pytest.raises(ValueError):
         gp.compute_model(m, gp.data.GemPyEngineConfig(backend=gp.data.AvailableBackends.legacy))
+    # gp.compute_model_at (compute_API.py:89-114) resolves compute_model through the same module attribute: same arm
+    at = np.array([[0, 0, 0], [1000, 1000, 1000]], dtype=float)
+    if torch.cuda.is_available():
+        ids = gp.compute_model_at(m, at, engine_config=cfg)
+        assert ids.tolist() == [3.0, 1.0]
+    else:
+        with pytest.raises(_lib.GpbError, match="CUDA device"):
+            gp.compute_model_at(m, at, engine_config=cfg)
+        assert m.grid.custom_grid.values.shape == (2, 3)          # the side effect the reference warns about happened first
 
 
 def test_geomodel_solutions_setter_consumes_backend_solutions(gp):

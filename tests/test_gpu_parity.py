@@ -508,6 +508,13 @@ def test_custom_grid_known_answer_gpu():
     m.options.number_octree_levels = 2
     sol = gc.compute_model(*m.args())
     np.testing.assert_array_equal(sol.raw_arrays.custom, np.array([3., 3., 3., 3., 1., 1., 1., 1.]))
+    # the compute_model_at flow (compute_API.py:89-114): reset the grids to the custom points, compute, return the ids there
+    m2 = ex.anticline()
+    m2.options.number_octree_levels = 2
+    at = m2.transform.apply(xyz)
+    ids = gc.compute_model_at(m2.interpolation_input, m2.options, m2.descriptor, at)
+    np.testing.assert_array_equal(ids, np.array([3., 3., 3., 3., 1., 1., 1., 1.]))
+    assert m2.interpolation_input.grid.dense_grid is None and m2.interpolation_input.grid.custom_grid.n_points == 8
 
 
 def test_gravity_known_answer_gpu():
