@@ -722,18 +722,10 @@ int launch_eval(const EvalParams& prm, cudaStream_t stream) {
         if (variant < 100 && zrun_ok<8>(prm)) return launch_zrun_cfg<KERNEL, GRAD, 8, 256, 1>(prm, stream);
         if (variant < 100 && zrun_ok<4>(prm)) return launch_zrun_cfg<KERNEL, GRAD, 4, 256, 1>(prm, stream);
     }
-    if constexpr (KERNEL == GPB_KERNEL_CUBIC) {
-        switch (variant) {
-            case 1: return launch_eval_cfg<KERNEL, GRAD, REGULAR, 2, 256, 2>(prm, stream);
-            case 2: return launch_eval_cfg<KERNEL, GRAD, REGULAR, 4, 384, 1>(prm, stream);
-            case 3: return launch_eval_cfg<KERNEL, GRAD, REGULAR, 2, 512, 1>(prm, stream);
-            case 4: return launch_eval_cfg<KERNEL, GRAD, REGULAR, 4, 128, 3>(prm, stream);
-            case 5: return launch_eval_cfg<KERNEL, GRAD, REGULAR, 2, 128, 4>(prm, stream);
-            case 6: return launch_eval_cfg<KERNEL, GRAD, REGULAR, 3, 128, 3>(prm, stream);
-            case 7: return launch_eval_cfg<KERNEL, GRAD, REGULAR, 4, 64, 6>(prm, stream);
-            default: break;
-        }
-    }
+    // point lists (octree levels, corners, custom grids): P = 4 strided points per thread, 256 threads.  Measured on the
+    // multi-fault octree-8 model (round 2): P = 8 / T = 256 41.6 ms, CTA sizes shrinking with the list length
+    // (P = 2 / 1, T = 128 for the shallow levels) 42-45 ms, this configuration 35 ms -- the per-CTA set-up (table load,
+    // barrier init) outweighs the better spread of tiny levels.
     return launch_eval_cfg<KERNEL, GRAD, REGULAR, 4, 256, 1>(prm, stream);
 }
 
