@@ -53,7 +53,7 @@ class GpbModelDesc(C.Structure):
     ]
 
 
-GPB_SEG_POINTS, GPB_SEG_REGULAR = 0, 1
+GPB_SEG_POINTS, GPB_SEG_REGULAR, GPB_SEG_OCTETS = 0, 1, 2
 
 
 class GpbSegment(C.Structure):

@@ -71,6 +71,7 @@ struct GpbEvalCall {
     long long ld_xyz = 0;
     long long m = 0;
     const long long* m_dev = nullptr;     // explicit points only: actual count on the device (m is then the upper bound)
+    int octets = 0;                       // explicit points only: points 8g .. 8g+7 are sibling octets (centre +- quarter cell)
     const double* fault_vals = nullptr;   // row f: fault_vals + (fault_ids ? fault_ids[f] : f) * ld_fault, minus fault_min[row]
     long long ld_fault = 0;
     const int* fault_ids = nullptr;

@@ -669,6 +669,212 @@ eval_zrun_kernel(const EvalParams prm) {
     act_min_commit(prm, vmin);
 }
 
+// ---- octet variant: point lists made of complete sibling octets (the children of refined octree voxels) ---------------
+// Points 8g .. 8g+7 are a parent centre +- a quarter cell in the pattern x:----++++ y:--++--++ z:-+-+-+-+
+// (gpb_emit_marked / gpb_emit_children), so they take two x, two y and two z values.  Per (thread, source): six
+// differences and four sums dx_a^2 + dy_b^2, then ONE FMA per point for the squared distance -- 2.5 instead of 6 FP64
+// instructions per pair -- with the register tiling of the z-run kernel (8 points per thread).
+template <int KERNEL, bool GRAD, int kThreads>
+__global__ void __launch_bounds__(kThreads, 1)
+eval_octet_kernel(const EvalParams prm) {
+    __shared__ __align__(128) double stage[2][kTileBytes / 8];
+    __shared__ __align__(8) uint64_t full[2];
+    __shared__ ActShared act;
+    double vmin = __longlong_as_double(0x7ff0000000000000LL);
+
+    const int tid = threadIdx.x;
+    act_load(prm, act);
+    if (tid == 0) {
+        gpb_mbar_init(&full[0], 1);
+        gpb_mbar_init(&full[1], 1);
+        gpb_fence_mbar_init();
+    }
+    __syncthreads();
+
+    const long long n_sp_tiles = prm.n_sps_pad / kTileSp;
+    const long long n_ori_tiles = prm.n_ori_pad / kTileOri;
+    const long long n_tiles = n_sp_tiles + n_ori_tiles;
+    const double* src_ori = prm.src + 4 * prm.n_sps_pad;
+    const double* tail = src_ori + 6 * prm.n_ori_pad;
+
+    const long long n_oct = prm.m / 8;
+    const long long n_chunks = (n_oct + kThreads - 1) / kThreads;
+    unsigned long long gt = 0;
+
+    auto issue = [&](long long j, unsigned long long g) {
+        const int b = (int)(g & 1);
+        if (j < n_sp_tiles) {
+            gpb_mbar_expect_tx(&full[b], kTileSp * 32);
+            gpb_bulk_g2s(stage[b], prm.src + 4 * (long long)kTileSp * j, kTileSp * 32, &full[b]);
+        } else {
+            gpb_mbar_expect_tx(&full[b], kTileOri * 48);
+            gpb_bulk_g2s(stage[b], src_ori + 6 * (long long)kTileOri * (j - n_sp_tiles), kTileOri * 48, &full[b]);
+        }
+    };
+
+    const bool resident = n_tiles <= 2;
+    if (resident && n_tiles > 0) {
+        if (tid == 0) {
+            issue(0, 0);
+            if (n_tiles > 1) issue(1, 1);
+        }
+        gpb_mbar_wait(&full[0], 0);
+        if (n_tiles > 1) gpb_mbar_wait(&full[1], 0);
+    }
+
+    for (long long c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+        const long long oct = c * kThreads + tid;
+        const bool live = oct < n_oct;
+        const long long base = 8 * (live ? oct : n_oct - 1);
+        // the two values per axis, read from the points that carry them (point k: x index k >> 2, y (k >> 1) & 1, z k & 1)
+        const double X[2] = {prm.xyz[base] * prm.inv_a, prm.xyz[base + 4] * prm.inv_a};
+        const double Y[2] = {prm.xyz[prm.ld_xyz + base] * prm.inv_a, prm.xyz[prm.ld_xyz + base + 2] * prm.inv_a};
+        const double Zc[2] = {prm.xyz[2 * prm.ld_xyz + base] * prm.inv_a, prm.xyz[2 * prm.ld_xyz + base + 1] * prm.inv_a};
+        double accZ[8], hx[8], hy[8], hz[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { accZ[k] = 0.0; hx[k] = 0.0; hy[k] = 0.0; hz[k] = 0.0; }
+
+        if (!resident && tid == 0 && n_tiles > 0) issue(0, gt);
+        for (long long j = 0; j < n_tiles; ++j, ++gt) {
+            int b = (int)j;
+            if (!resident) {
+                if (tid == 0 && j + 1 < n_tiles) issue(j + 1, gt + 1);
+                b = (int)(gt & 1);
+                gpb_mbar_wait(&full[b], (uint32_t)((gt >> 1) & 1));
+            }
+            const double* s = stage[b];
+            if (j < n_sp_tiles) {
+                const int cnt_sp = (int)min((long long)kTileSp, (prm.n_sps - j * kTileSp + 1) & ~1LL);
+#pragma unroll 2
+                for (int q = 0; q < cnt_sp; ++q) {
+                    const double2 a0 = *reinterpret_cast<const double2*>(s + 4 * q);
+                    const double2 a1 = *reinterpret_cast<const double2*>(s + 4 * q + 2);
+                    const double dx[2] = {X[0] - a0.x, X[1] - a0.x}, dy[2] = {Y[0] - a0.y, Y[1] - a0.y};
+                    const double dz[2] = {Zc[0] - a1.x, Zc[1] - a1.x};
+                    const double px[2] = {fma(dx[0], dx[0], prm.eps_u), fma(dx[1], dx[1], prm.eps_u)};
+                    const double pxy[4] = {fma(dy[0], dy[0], px[0]), fma(dy[1], dy[1], px[0]), fma(dy[0], dy[0], px[1]), fma(dy[1], dy[1], px[1])};
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const double u = fma(dz[k & 1], dz[k & 1], pxy[k >> 1]);
+                        const double t = EVAL_SQRT(u);
+                        double cv, kp;
+                        cov_sp<KERNEL>(u, t, cv, kp);
+                        const double wq = (KERNEL == GPB_KERNEL_CUBIC) ? a1.y * t : a1.y;
+                        accZ[k] = fma(wq, cv, accZ[k]);
+                        if constexpr (GRAD) {
+                            const double g = wq * kp;
+                            hx[k] = fma(g, dx[k >> 2], hx[k]);
+                            hy[k] = fma(g, dy[(k >> 1) & 1], hy[k]);
+                            hz[k] = fma(g, dz[k & 1], hz[k]);
+                        }
+                    }
+                }
+                if (j == n_sp_tiles - 1) {
+                    if constexpr (KERNEL == GPB_KERNEL_CUBIC) {
+                        const double S0 = tail[20], M1x = tail[21], M1y = tail[22], M1z = tail[23], M2 = tail[24];
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            const double x = X[k >> 2], y = Y[(k >> 1) & 1], z = Zc[k & 1];
+                            const double x2 = fma(x, x, fma(y, y, fma(z, z, prm.eps_u)));
+                            const double xm = fma(x, M1x, fma(y, M1y, z * M1z));
+                            accZ[k] = fma(-7.0, fma(x2, S0, fma(-2.0, xm, M2)), accZ[k]);
+                            if constexpr (GRAD) {
+                                hx[k] = fma(-14.0, fma(x, S0, -M1x), hx[k]);
+                                hy[k] = fma(-14.0, fma(y, S0, -M1y), hy[k]);
+                                hz[k] = fma(-14.0, fma(z, S0, -M1z), hz[k]);
+                            }
+                        }
+                    }
+                    if constexpr (GRAD) {
+                        const double rr = tail[18];
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) { hx[k] *= rr; hy[k] *= rr; hz[k] *= rr; }
+                    }
+                }
+            } else {
+                const int cnt_or = (int)min((long long)kTileOri, (prm.n_ori - (j - n_sp_tiles) * kTileOri + 1) & ~1LL);
+#pragma unroll 2
+                for (int q = 0; q < cnt_or; ++q) {
+                    const double2 a0 = *reinterpret_cast<const double2*>(s + 6 * q);
+                    const double2 a1 = *reinterpret_cast<const double2*>(s + 6 * q + 2);
+                    const double2 a2 = *reinterpret_cast<const double2*>(s + 6 * q + 4);
+                    const double dx[2] = {X[0] - a0.x, X[1] - a0.x}, dy[2] = {Y[0] - a0.y, Y[1] - a0.y};
+                    const double dz[2] = {Zc[0] - a1.x, Zc[1] - a1.x};
+                    const double px[2] = {fma(dx[0], dx[0], prm.eps_u), fma(dx[1], dx[1], prm.eps_u)};
+                    const double pxy[4] = {fma(dy[0], dy[0], px[0]), fma(dy[1], dy[1], px[0]), fma(dy[0], dy[0], px[1]), fma(dy[1], dy[1], px[1])};
+                    const double wx[2] = {dx[0] * a1.y, dx[1] * a1.y};
+                    const double hwxy[4] = {fma(dy[0], a2.x, wx[0]), fma(dy[1], a2.x, wx[0]), fma(dy[0], a2.x, wx[1]), fma(dy[1], a2.x, wx[1])};
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const double u = fma(dz[k & 1], dz[k & 1], pxy[k >> 1]);
+                        const double t = EVAL_SQRT(u);
+                        double kp, dd;
+                        cov_ori<KERNEL>(u, t, kp, dd);
+                        const double hw = fma(dz[k & 1], a2.y, hwxy[k >> 1]);
+                        accZ[k] = fma(kp, hw, accZ[k]);
+                        if constexpr (GRAD) {
+                            const double c1 = -(dd * EVAL_RCP(u + prm.eps_reg)) * hw;
+                            hx[k] = fma(c1, dx[k >> 2], fma(kp, a1.y, hx[k]));
+                            hy[k] = fma(c1, dy[(k >> 1) & 1], fma(kp, a2.x, hy[k]));
+                            hz[k] = fma(c1, dz[k & 1], fma(kp, a2.y, hz[k]));
+                        }
+                    }
+                }
+            }
+            if (!resident) __syncthreads();
+        }
+
+        const double inv_agi = tail[19];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const double x = X[k >> 2], y = Y[(k >> 1) & 1], zc = Zc[k & 1];
+            double z = accZ[k];
+            double g0v = hx[k] * inv_agi, g1v = hy[k] * inv_agi, g2v = hz[k] * inv_agi;
+            if (prm.n_drift >= 3) {
+                z = fma(tail[0], x, fma(tail[1], y, fma(tail[2], zc, z)));
+                if constexpr (GRAD) { g0v += tail[9]; g1v += tail[10]; g2v += tail[11]; }
+            }
+            if (prm.n_drift == 9) {
+                z = fma(tail[3], x * x, fma(tail[4], y * y, fma(tail[5], zc * zc, z)));
+                z = fma(tail[6], x * y, fma(tail[7], x * zc, fma(tail[8], y * zc, z)));
+                if constexpr (GRAD) {
+                    g0v += 2.0 * tail[12] * x + tail[15] * y + tail[16] * zc;
+                    g1v += 2.0 * tail[13] * y + tail[15] * x + tail[17] * zc;
+                    g2v += 2.0 * tail[14] * zc + tail[16] * x + tail[17] * y;
+                }
+            }
+            if (live) {
+                const long long idx = base + k;
+                z = fault_term(prm, tail + kTailDoubles, idx, z);
+                prm.Z[idx] = z;
+                if constexpr (GRAD) {
+                    prm.gx[idx] = g0v;
+                    prm.gy[idx] = g1v;
+                    prm.gz[idx] = g2v;
+                }
+                if (prm.block != nullptr) {
+                    const double v = act_value(prm, act, z);
+                    prm.block[idx] = v;
+                    vmin = fmin(vmin, v);
+                }
+            }
+        }
+    }
+    act_min_commit(prm, vmin);
+}
+
+template <int KERNEL, bool GRAD>
+int launch_octet(const EvalParams& prm, cudaStream_t stream) {
+    constexpr int T = 256;
+    const long long n_chunks = (prm.m / 8 + T - 1) / T;
+    if (n_chunks == 0) return GPB_OK;
+    long long grid = gpb_sm_count();
+    if (grid > n_chunks) grid = n_chunks;
+    eval_octet_kernel<KERNEL, GRAD, T><<<(unsigned)grid, T, 0, stream>>>(prm);
+    GPB_LAUNCH_CHECK();
+    return GPB_OK;
+}
+
 template <int KERNEL, bool GRAD, int P, int T, int MINB>
 int launch_zrun_cfg(const EvalParams& prm, cudaStream_t stream) {
     const long long n_runs = prm.m / P;
@@ -727,6 +933,17 @@ int launch_eval(const EvalParams& prm, cudaStream_t stream) {
     // (P = 2 / 1, T = 128 for the shallow levels) 42-45 ms, this configuration 35 ms -- the per-CTA set-up (table load,
     // barrier init) outweighs the better spread of tiny levels.
     return launch_eval_cfg<KERNEL, GRAD, REGULAR, 4, 256, 1>(prm, stream);
+}
+
+int dispatch_octet(int kernel, bool grad, const EvalParams& prm, cudaStream_t stream) {
+#define GPB_OCT(K) case K: return grad ? launch_octet<K, true>(prm, stream) : launch_octet<K, false>(prm, stream);
+    switch (kernel) {
+        GPB_OCT(GPB_KERNEL_CUBIC)
+        GPB_OCT(GPB_KERNEL_EXPONENTIAL)
+        GPB_OCT(GPB_KERNEL_MATERN52)
+        default: return gpb_set_error(GPB_E_INVALID, "unknown kernel function %d", kernel);
+    }
+#undef GPB_OCT
 }
 
 template <bool REGULAR>
@@ -818,6 +1035,10 @@ int gpb_eval_call(const GpbEvalCall& c, cudaStream_t stream) {
     prm.block_min = c.block_min;
     prm.m_dev = c.regular ? nullptr : c.m_dev;
     prm.Z = c.Z; prm.gx = c.gx; prm.gy = c.gy; prm.gz = c.gz;
+    static const bool no_octets = getenv("GPB_NO_OCTETS") != nullptr;
+    // complete sibling octets, enough of them to fill the machine: the octet kernel (8 points per thread)
+    if (!c.regular && c.octets && !no_octets && c.m_dev == nullptr && c.m % 8 == 0 && c.m >= 8LL * 256 * 64)
+        return dispatch_octet(c.st->kernel, c.gx != nullptr, prm, stream);
     return c.regular ? dispatch_eval<true>(c.st->kernel, c.gx != nullptr, prm, stream)
                      : dispatch_eval<false>(c.st->kernel, c.gx != nullptr, prm, stream);
 }

@@ -99,6 +99,7 @@ int eval_segments(gpb_model* m, int i, const gpb_level* lvl, bool activate, cuda
             c.xyz = sg.xyz;
             c.ld_xyz = sg.ld_xyz;
             c.m_dev = sg.count_dev;
+            c.octets = (sg.kind == GPB_SEG_OCTETS) ? 1 : 0;
         }
         const long long o = sg.out_offset;
         if (ms.st.n_faults > 0) {

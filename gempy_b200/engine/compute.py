@@ -446,7 +446,8 @@ class B200Engine:
             if kind == "regular":
                 arr[k].kind, arr[k].grid, arr[k].i0 = _lib.GPB_SEG_REGULAR, what[0], int(what[1])
             else:
-                arr[k].kind, arr[k].xyz, arr[k].ld_xyz = _lib.GPB_SEG_POINTS, _ptr(what), int(what.stride(0))
+                arr[k].kind = _lib.GPB_SEG_OCTETS if kind == "octets" else _lib.GPB_SEG_POINTS
+                arr[k].xyz, arr[k].ld_xyz = _ptr(what), int(what.stride(0))
                 keep.append(what)
         lvl = _lib.GpbLevel(ld, len(eval_segs), arr, L - n_sp, _ptr(Z), _ptr(G), _ptr(block), _ptr(final_block), _ptr(faults_block),
                             _ptr(squeezed), _ptr(mask), None, 0, 0, 0, L)
@@ -790,7 +791,9 @@ def _compute_model(eng: B200Engine, interpolation_input, options, data_descripto
         centers_loc = centers_full[:, v0:v1]
         out_parts: List[Tuple[str, int]] = [("octree_grid", nvl)]
         totals = [nv]
-        eval_segs: List[tuple] = [("points", nvl, 0, centers_loc)]
+        # below the root a level is a list of sibling octets (8 children per refined voxel, in emission order)
+        octets = lvl > 0 and v0 % 8 == 0 and nvl % 8 == 0
+        eval_segs: List[tuple] = [("octets" if octets else "points", nvl, 0, centers_loc)]
         off = nvl
         ex_loc = []
         if lvl == 0:

@@ -197,6 +197,8 @@ typedef struct gpb_model_desc {
 
 #define GPB_SEG_POINTS  0
 #define GPB_SEG_REGULAR 1
+#define GPB_SEG_OCTETS  2      /* POINTS whose entries 8g .. 8g+7 are the 8 children of one voxel (what gpb_emit_marked writes):
+                                  evaluated by the octet kernel, which shares the per-axis distances among the 8 points */
 typedef struct gpb_segment {
     int kind;
     long long count;               /* points of the segment */

@@ -119,3 +119,19 @@ def test_interpolation_options_defaults_follow_the_serialization_golden():
             e.octree_error_threshold, e.octree_min_level, e.evaluation_chunk_size) == (3, 4, -1.0, 1.0, 2, 500_000)
     assert o.sigmoid_slope == 5_000_000 and o.cache_mode == 3 and e.mesh_extraction is True
     assert o.number_octree_levels_surface == 3      # capped by the number of levels
+
+
+def test_engine_inputs_npz_round_trip(tmp_path):
+    """gempy_b200.engine.io: the three compute_model arguments survive the .npz form the bridge fixtures use."""
+    from gempy_b200 import examples as ex
+    from gempy_b200.engine.io import engine_inputs_from_npz, engine_inputs_to_npz
+    m = ex.combination(refinement=3)
+    p = str(tmp_path / "m.npz")
+    engine_inputs_to_npz(p, *m.args())
+    ii, opt, desc = engine_inputs_from_npz(p)
+    np.testing.assert_array_equal(ii.surface_points.sp_coords, m.interpolation_input.surface_points.sp_coords)
+    np.testing.assert_array_equal(ii.orientations.dip_gradients, m.interpolation_input.orientations.dip_gradients)
+    np.testing.assert_array_equal(ii.grid.octree_grid.regular_grid_shape, [4, 2, 2])
+    assert opt.number_octree_levels == 3 and opt.number_octree_levels_surface == 3
+    assert [r.name for r in desc.stack_structure.masking_descriptor] == ["FAULT", "ERODE", "BASEMENT"]
+    np.testing.assert_array_equal(desc.stack_structure.faults_relations, m.descriptor.stack_structure.faults_relations)
