@@ -695,8 +695,8 @@ def _warn_unsupported(options: InterpolationOptions, ii: InterpolationInput) -> 
     if float(getattr(eo, "octree_error_threshold", 1.0)) != 1.0:
         notes.append("evaluation_options.octree_error_threshold (refinement is by corner ids only)")
     mo = getattr(eo, "mesh_extraction_masking_options", MeshExtractionMaskingOptions.INTERSECT)
-    if getattr(mo, "name", mo) not in ("INTERSECT", 3):
-        notes.append("evaluation_options.mesh_extraction_masking_options (meshes are masked by the squeezed stack mask = INTERSECT)")
+    if getattr(mo, "name", mo) not in ("INTERSECT", 3, "RAW", 4, "DISJOINT", 2):
+        notes.append("evaluation_options.mesh_extraction_masking_options = NOTHING (meshes are masked by the squeezed stack mask = INTERSECT)")
     if int(getattr(eo, "evaluation_chunk_size", 500_000)) != 500_000:
         notes.append("evaluation_options.evaluation_chunk_size (the kernel matrix is never materialised: nothing to chunk)")
     if ii.weights:
@@ -911,7 +911,7 @@ def _compute_model(eng: B200Engine, interpolation_input, options, data_descripto
 
     meshes = None
     if eo.mesh_extraction and dc_payload is not None:
-        meshes = _dual_contouring(eng, tables, dc_payload, root)
+        meshes = _dual_contouring(eng, tables, dc_payload, root, getattr(eo, "mesh_extraction_masking_options", None))
 
     sol = Solutions(octree_levels, meshes, gravity, options.block_solutions_type)
     sol.raw_arrays = _raw_arrays(eng, sol, levels_dev, grid, options, meshes)
@@ -967,10 +967,16 @@ class _DeviceMesh:
         return DualContouringData(_np(self.xyz_c[:, :E]).T.copy(), valid, _np(self.grad_c[:, :E]).T.copy())
 
 
-def _dual_contouring(eng: B200Engine, tables: ModelTables, payload, root: RegularGrid) -> List[DualContouringMesh]:
+def _dual_contouring(eng: B200Engine, tables: ModelTables, payload, root: RegularGrid, masking=None) -> List[DualContouringMesh]:
     """Every surface of every stack on the surface level, queued without a host round trip (gpb_dual_contour); the meshes
-    are read back lazily."""
+    are read back lazily.  ``masking`` (evaluation_options.mesh_extraction_masking_options): INTERSECT (default) keeps the
+    voxels the stack owns at any of their corners (squeezed mask; fault stacks are never masked), RAW masks nothing,
+    DISJOINT is not implemented (nor is it upstream)."""
     lvl, centers, d, corners, f = payload
+    mname = getattr(masking, "name", masking)
+    if mname in ("DISJOINT", 2):
+        raise NotImplementedError("mesh_extraction_masking_options = DISJOINT is not implemented")
+    raw = mname in ("RAW", 4)
     nv = int(centers.shape[1])
     c_off = f.seg_offset("corners")
     lat = _lattice(root, lvl)
@@ -981,7 +987,7 @@ def _dual_contouring(eng: B200Engine, tables: ModelTables, payload, root: Regula
     for i, st in enumerate(tables):
         sct = st.struct()
         Zc = _ptr(f.Z[i], 8 * c_off)
-        sq = None if tables.rel[i] == StackRelationType.FAULT.value else _ptr(f.squeezed[i], c_off)
+        sq = None if (raw or tables.rel[i] == StackRelationType.FAULT.value) else _ptr(f.squeezed[i], c_off)
         for s_idx in range(st.n_surf):
             counts = eng.empty(3, dtype=torch.int64)
             verts = eng.empty(3, max(nv, 1))

@@ -560,6 +560,22 @@ def test_dual_contouring_meshes_match_oracle(build, n_meshes):
     assert [v.shape for v in sol.raw_arrays.vertices] == [m.vertices.shape for m in sol.dc_meshes]
 
 
+def test_mesh_extraction_masking_options():
+    """RAW: no stack mask on the meshes (every crossing of every stack's own isovalues is meshed: at least as many vertices as
+    with the default INTERSECT mask, strictly more where an older series is eroded); DISJOINT raises."""
+    from gempy_b200.engine.data import MeshExtractionMaskingOptions as MO
+    a = gc.compute_model(*ex.combination(refinement=4).args())
+    m = ex.combination(refinement=4)
+    m.options.evaluation_options.mesh_extraction_masking_options = MO.RAW
+    b = gc.compute_model(*m.args())
+    va, vb = [x.vertices.shape[0] for x in a.dc_meshes], [x.vertices.shape[0] for x in b.dc_meshes]
+    assert va[0] == vb[0]                                   # the fault stack is never masked
+    assert all(y >= x for x, y in zip(va, vb)) and sum(vb) > sum(va)
+    m.options.evaluation_options.mesh_extraction_masking_options = MO.DISJOINT
+    with pytest.raises(NotImplementedError):
+        gc.compute_model(*m.args())
+
+
 def test_recompute_with_stale_weights_attached_sees_the_edit():
     """The reference bridge hands the previous solution's weights back on every compute_model after the first
     (_engine_factory.py:45-48).  They are a solver warm start upstream; the direct solver here needs none, so an edited
