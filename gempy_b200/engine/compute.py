@@ -4,12 +4,13 @@ Mirrors ``gempy_engine.compute_model(interpolation_input, options, data_descript
 (the call GemPy makes at /root/reference/gempy/API/compute_API.py:68-73) and returns a ``Solutions`` object
 with the attributes GemPy reads (gempy/core/data/geo_model.py:100-127).  The pipeline per octree level is
 
-    per stack:  ref/rest split -> [assemble covariance -> LU solve | cached weights] -> pack weights
-                -> fused field(+gradient) evaluation on {octree centres, dense, custom, topography, sections,
-                   corners} ++ surface points -> activator
-    all stacks: masks + combination -> lith / fault blocks
-    next level: corner-id refinement test -> child emission
-    finally:    dual contouring on the surface level
+    host:       level buffers (centres emitted by the previous level, unique corners through a lattice hash, surface points)
+    one C call: per stack [level 0: fault values at the stack's points -> lower-triangle covariance -> symmetric solve
+                (pivoted LU for tiny / indefinite systems) -> packed weights -> isovalues]
+                -> ONE fused launch per segment: field (+gradient) + fault drift + activator (octet / point-list / z-run kernel)
+                then corner segment <- unique corners, masks + combination -> lith / fault blocks       (gpb_model_run_level)
+    next level: corner-id refinement test -> count (the level's one synchronisation) -> children
+    finally:    dual contouring on the surface level (gpb_dual_contour, no synchronisation), lazy host containers
 
 Every arithmetic step is a CUDA kernel of libgempy_b200.so called through the C ABI (gempy_b200/_lib.py).
 torch is used for device-memory ownership, streams and (multi-GPU) torch.distributed only.
@@ -75,14 +76,6 @@ def regular_descriptor(g: RegularGrid) -> _lib.GpbRegularGrid:
     d = np.array([(e[1] - e[0]) / s[0], (e[3] - e[2]) / s[1], (e[5] - e[4]) / s[2]])
     return _lib.GpbRegularGrid(e[0] + d[0] / 2 + GRID_SHIFT, e[2] + d[1] / 2 + GRID_SHIFT, e[4] + d[2] / 2 + GRID_SHIFT,
                                d[0], d[1], d[2], int(s[0]), int(s[1]), int(s[2]))
-
-
-def regular_centers_device(g: RegularGrid, device) -> Tuple[torch.Tensor, np.ndarray]:
-    """Explicit [3, n] centres of a (small) regular grid, x slowest / z fastest, shift included."""
-    ax = g.axis_coords()
-    gx, gy, gz = np.meshgrid(*ax, indexing="ij")
-    xyz = np.stack([gx.ravel(), gy.ravel(), gz.ravel()]) + GRID_SHIFT
-    return torch.as_tensor(xyz, dtype=F64, device=device).contiguous(), g.dxdydz.copy()
 
 
 # ------------------------------------------------------------------------------------------------ stack tables
