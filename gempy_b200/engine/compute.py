@@ -582,7 +582,10 @@ def compute_dense_fields(interpolation_input: InterpolationInput, options: Inter
         if per > nyz:
             per = -(-per // nyz) * nyz
         compute = torch.cuda.current_stream(eng.device)
-        copier = torch.cuda.Stream(eng.device)
+        if getattr(eng, "_copier", None) is None:
+            eng._copier = torch.cuda.Stream(eng.device)          # one copy stream per engine, created once
+        copier = eng._copier
+        copier.wait_stream(compute)
         bufs = [eng.empty(4, per) for _ in range(2)]
         free_ev = [None, None]
         k = 0
