@@ -37,7 +37,7 @@ summ $OUT/r2_cov_6999.ncu-rep $OUT/r2_cov_kernels_ncu_full_n6999.txt
 fi
 if [[ " $WHICH " == *" 4 "* ]]; then
 # 4. point-list evaluation with the fused activator on the multi-fault octree model: the largest launches of the last level
-ncu --set full --clock-control none --import-source on -k regex:'eval_kernel' -s 240 -c 14 -o $OUT/r2_eval_points_cfg4 -f python scripts/profile_compute_model.py --levels 8 > /dev/null 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'eval_octet_kernel|eval_kernel' -s 330 -c 24 -o $OUT/r2_eval_points_cfg4 -f python scripts/profile_compute_model.py --levels 8 > /dev/null 2>&1
 summ $OUT/r2_eval_points_cfg4.ncu-rep $OUT/r2_eval_points_kernel_ncu_full_cfg4.txt
 fi
 rm -f $OUT/*.ncu-rep
