@@ -95,13 +95,13 @@ constexpr int kLdS = 129;                      // 64 matrix rows + 64 identity r
 constexpr size_t kPotrfSmem = (size_t)(kCB * kLdS + kCB) * sizeof(double);
 
 __global__ void __launch_bounds__(256) potrf64_kernel(int k0, int jb, double* __restrict__ A, int lda, int* __restrict__ info,
-                                                      const double* __restrict__ diag0, double* __restrict__ Wt) {
+                                                      const double* __restrict__ diag0, double* __restrict__ Wt, double pivot_tol) {
     extern __shared__ double S[];              // S[c * kLdS + slot]
     double* tol = S + kCB * kLdS;              // pivot thresholds of the block's columns
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (info != nullptr && *reinterpret_cast<volatile int*>(info) != 0) return;      // an earlier pivot failed: the caller falls back to the LU
     for (int e = tid; e < kCB * kLdS; e += 256) S[e] = 0.0;
-    if (tid < kCB) tol[tid] = (tid < jb && diag0) ? kPivotTol * fabs(diag0[k0 + tid]) : 0.0;
+    if (tid < kCB) tol[tid] = (tid < jb && diag0) ? pivot_tol * fabs(diag0[k0 + tid]) : 0.0;
     __syncthreads();
     {
         double tmp[16];
@@ -618,7 +618,8 @@ int factor_block(int M, int K0, int W, double* A, int lda, int* info, const doub
         const int jb = min(kCB, K0 + W - k0);
         double* Wt = wt_all + (long long)(k0 / kCB) * kCB * kCB;
         int rc0;
-        potrf64_kernel<<<1, 256, kPotrfSmem, q>>>(k0, jb, A, lda, info, diag0, Wt);
+        static const double pivot_tol = [] { const char* e = getenv("GPB_CHOL_PIVOT_TOL"); return e ? atof(e) : kPivotTol; }();
+        potrf64_kernel<<<1, 256, kPotrfSmem, q>>>(k0, jb, A, lda, info, diag0, Wt, pivot_tol);
         GPB_LAUNCH_CHECK();
         if ((rc0 = launch_trsm(M, k0, jb, A, lda, Wt, q))) return rc0;
         if (k0 + jb < K0 + W) {
