@@ -92,6 +92,12 @@ int gpb_eval_call(const GpbEvalCall& c, cudaStream_t stream);
 // ---- fast FP64 primitives -------------------------------------------------------------------------
 // MUFU seeds (2^-22) + one third-order correction: error ~ e^3 ~ 1e-20 relative before rounding,
 // with no divergent slow path (arguments are strictly positive, normal numbers on this path).
+// MUFU seeds.  ncu shows the XU pipe (MUFU.RSQ64H) 70 % busy next to a 65 % busy FP64 pipe in the field-only evaluation
+// kernels (profiles/r2_eval_octet_kernel_ncu_full_cfg4.txt), so a variant that narrows the double to a float with three
+// integer instructions, uses the 32-bit MUFU and widens the result back (same 2^-22 accuracy) was tried: it measured SLOWER
+// (512^3 benchmark 789 -> 854 ms per step, config-5 octree levels 1.15 -> 1.48 s) -- the five extra integer instructions per
+// pair cost more issue slots and latency than the shorter XU occupancy saves.  Kept behind GPB_MUFU32 for the record.
+#ifndef GPB_MUFU32
 __device__ __forceinline__ double gpb_rsqrt_seed(double u) {
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(u));
@@ -102,6 +108,26 @@ __device__ __forceinline__ double gpb_rcp_seed(double d) {
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
     return y;
 }
+#else
+__device__ __forceinline__ float gpb_narrow(double u) {
+    const unsigned hi = (unsigned)__double2hiint(u) - 0x38000000u;          // exponent bias 1023 -> 127
+    return __uint_as_float(__funnelshift_l((unsigned)__double2loint(u), hi, 3));
+}
+__device__ __forceinline__ double gpb_widen(float y) {
+    const unsigned b = __float_as_uint(y);
+    return __hiloint2double((int)((b >> 3) + 0x38000000u), (int)(b << 29));
+}
+__device__ __forceinline__ double gpb_rsqrt_seed(double u) {
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(gpb_narrow(u)));
+    return gpb_widen(y);
+}
+__device__ __forceinline__ double gpb_rcp_seed(double d) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(gpb_narrow(d)));
+    return gpb_widen(y);
+}
+#endif
 // sqrt(u), u > 0
 __device__ __forceinline__ double gpb_fast_sqrt(double u) {
     const double y0 = gpb_rsqrt_seed(u);
