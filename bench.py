@@ -387,22 +387,22 @@ def run_gpu(args):
             return float(host_out[0, 0])
 
         e2e_step()
-        # every step timed on its own (barrier on both sides, max over ranks): the shared hosts stall for tens to hundreds
-        # of milliseconds now and then (scripts/probes/alloc_trace.py shows the same outliers on plain compute_model calls),
-        # so the value is taken from the MEDIAN step; mean and max are reported next to it
+        # every step timed on its own clock on every rank (one barrier before the first step, none in between: the ranks
+        # share nothing on this path), then the per-step MAX over ranks: the shared hosts stall for tens to hundreds of
+        # milliseconds now and then (scripts/probes/alloc_trace.py shows the same outliers on plain compute_model calls), so
+        # the value is taken from the MEDIAN step; mean and max are reported next to it
         n_e2e = max(1, args.steps)
-        step_s = []
+        if world > 1:
+            dist.barrier()
+        local_s = []
         for _ in range(n_e2e):
-            if world > 1:
-                dist.barrier()
             t0 = time.perf_counter()
             e2e_step()
-            if world > 1:
-                dist.barrier()
-            tt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=eng.device)
-            if world > 1:
-                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            step_s.append(float(tt.item()))
+            local_s.append(time.perf_counter() - t0)
+        tt = torch.tensor(local_s, dtype=torch.float64, device=eng.device)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        step_s = [float(v) for v in tt.cpu().numpy()]
         e2e_val = n_total / float(np.median(step_s))
         h2d = int((ii.surface_points.sp_coords.nbytes + ii.surface_points.nugget_effect_scalar.nbytes +
                    ii.orientations.dip_positions.nbytes + ii.orientations.dip_gradients.nbytes +
@@ -511,7 +511,7 @@ def run_gpu(args):
                 "e2e": None if e2e_val is None else {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d,
                                                     "d2h_bytes_per_step": d2h, "steps_timed": max(1, args.steps),
                                                     "step_s": {"median": float(np.median(step_s)), "mean": float(np.mean(step_s)), "max": float(np.max(step_s))},
-                                                    "value_from": "median step (each step timed with a barrier on both sides, max over ranks)",
+                                                    "value_from": "median over the steps of the per-step max over ranks",
                                                     "call": "gempy_b200.engine.compute.compute_dense_fields (streaming form of compute_model + compute_scalar_gradient for outputs too large to keep)"},
                 "roofline": roof, "fp64_peaks": peaks, "cpu_baseline": cpu}
         line.update(extras)
