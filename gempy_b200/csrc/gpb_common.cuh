@@ -97,18 +97,18 @@ int gpb_eval_call(const GpbEvalCall& c, cudaStream_t stream);
 // integer instructions, uses the 32-bit MUFU and widens the result back (same 2^-22 accuracy) was tried: it measured SLOWER
 // (512^3 benchmark 789 -> 854 ms per step, config-5 octree levels 1.15 -> 1.48 s) -- the five extra integer instructions per
 // pair cost more issue slots and latency than the shorter XU occupancy saves.  Kept behind GPB_MUFU32 for the record.
-#ifndef GPB_MUFU32
-__device__ __forceinline__ double gpb_rsqrt_seed(double u) {
+// Mixing the two (32-bit seeds for the reciprocal of the orientation gradient term only, or for 2 / 4 of the 8 points a
+// thread owns) was slower in proportion to the share: 787 -> 803 / 804 / 831 ms.
+__device__ __forceinline__ double gpb_rsqrt_seed64(double u) {
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(u));
     return y;
 }
-__device__ __forceinline__ double gpb_rcp_seed(double d) {
+__device__ __forceinline__ double gpb_rcp_seed64(double d) {
     double y;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
     return y;
 }
-#else
 __device__ __forceinline__ float gpb_narrow(double u) {
     const unsigned hi = (unsigned)__double2hiint(u) - 0x38000000u;          // exponent bias 1023 -> 127
     return __uint_as_float(__funnelshift_l((unsigned)__double2loint(u), hi, 3));
@@ -117,16 +117,22 @@ __device__ __forceinline__ double gpb_widen(float y) {
     const unsigned b = __float_as_uint(y);
     return __hiloint2double((int)((b >> 3) + 0x38000000u), (int)(b << 29));
 }
-__device__ __forceinline__ double gpb_rsqrt_seed(double u) {
+__device__ __forceinline__ double gpb_rsqrt_seed32(double u) {
     float y;
     asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(gpb_narrow(u)));
     return gpb_widen(y);
 }
-__device__ __forceinline__ double gpb_rcp_seed(double d) {
+__device__ __forceinline__ double gpb_rcp_seed32(double d) {
     float y;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(gpb_narrow(d)));
     return gpb_widen(y);
 }
+#ifndef GPB_MUFU32
+__device__ __forceinline__ double gpb_rsqrt_seed(double u) { return gpb_rsqrt_seed64(u); }
+__device__ __forceinline__ double gpb_rcp_seed(double d) { return gpb_rcp_seed64(d); }
+#else
+__device__ __forceinline__ double gpb_rsqrt_seed(double u) { return gpb_rsqrt_seed32(u); }
+__device__ __forceinline__ double gpb_rcp_seed(double d) { return gpb_rcp_seed32(d); }
 #endif
 // sqrt(u), u > 0
 __device__ __forceinline__ double gpb_fast_sqrt(double u) {
@@ -143,8 +149,16 @@ __device__ __forceinline__ double gpb_fast_sqrt(double u) {
 __device__ __forceinline__ double gpb_fast_sqrt2(double u) {
     const double y0 = gpb_rsqrt_seed(u);
     const double g0 = u * y0;
+#ifndef GPB_SQRT2_INT_HALF
     const double e = fma(-g0, y0, 1.0);
     return g0 * fma(0.5, e, 1.0);
+#else
+    // g0 + (u - g0^2) * y0/2 with the halving as an exponent decrement on the integer pipe: three FP64 instructions
+    // instead of four, same error term.  Measured SLOWER on the 512^3 benchmark (779.7 -> 787.4 ms per step): an integer
+    // instruction in the pair loop costs as much issue bandwidth as the FP64 instruction it replaces.
+    const double h = __hiloint2double(__double2hiint(y0) - 0x00100000, __double2loint(y0));
+    return fma(fma(-g0, g0, u), h, g0);
+#endif
 }
 __device__ __forceinline__ double gpb_fast_rcp2(double d) {
     const double y0 = gpb_rcp_seed(d);

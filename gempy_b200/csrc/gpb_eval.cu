@@ -30,9 +30,13 @@
 
 namespace {
 
-constexpr int kTileSp = 256;                  // sources per tile: 256 * 32 B = 8 KB
+constexpr int kTileSp = 256;                  // sources per tile: 256 * 32 B = 8 KB (cubic: 256 * 80 B = 20 KB)
 constexpr int kTileOri = 128;                 // 128 * 48 B = 6 KB
-constexpr int kTileBytes = kTileSp * 32;      // stage buffer size
+// Doubles per surface-point source record: {X, Y, Z, W} and, for the cubic kernel, {W p0, W p1, W p2, W q0, W q1, W q2},
+// the coefficients of W P(u) and W Q(u) multiplied by the weight when the table is packed -- the pair loop then needs
+// t u, W P(u) and one FMA for the field (one FP64 instruction per pair less than multiplying by W t in the loop).
+__host__ __device__ constexpr int sp_rec(int kernel) { return kernel == GPB_KERNEL_CUBIC ? 10 : 4; }
+static_assert(kTileSp * 4 * 8 >= kTileOri * 48, "the stage buffer must hold an orientation tile");
 constexpr int kTailDoubles = 32;              // mu_z[9] mu_g[9] scal[2] moments S0, M1[3], M2 (+pad)
 
 struct EvalParams {
@@ -82,7 +86,7 @@ struct EvalParams {
 //   returns c = u P(u) / t-free part to be multiplied by W t, kp = Q(u)
 template <int KERNEL>
 __device__ __forceinline__ void cov_sp(double u, double t, double& c, double& kp) {
-    if constexpr (KERNEL == GPB_KERNEL_CUBIC) {
+    if constexpr (KERNEL == GPB_KERNEL_CUBIC) {     // P(u) = 8.75 - 3.5 u + 0.75 u^2, Q(u) = 26.25 - 17.5 u + 5.25 u^2 (see sp_pair)
         const double P = fma(u, fma(0.75, u, -3.5), 8.75);
         kp = fma(u, fma(5.25, u, -17.5), 26.25);
         c = u * P;
@@ -115,6 +119,33 @@ __device__ __forceinline__ void cov_ori(double u, double t, double& kp, double& 
         const double e = exp(-s);
         kp = (-5.0 / 3.0) * (1.0 + s) * e;
         dd = (-5.0 / 3.0) * e * s * s;
+    }
+}
+
+// One surface-point pair: acc += W C(u) and (GRAD) g = W a^2 C'(r)/r, from the record's pre-multiplied coefficients (cubic)
+// or its weight (other kernels).
+template <int KERNEL> struct SpCoef {};
+template <> struct SpCoef<GPB_KERNEL_CUBIC> { double2 c0, c1, c2; };     // {Wp0, Wp1}, {Wp2, Wq0}, {Wq1, Wq2}
+template <int KERNEL>
+__device__ __forceinline__ SpCoef<KERNEL> sp_coef(const double* rec) {
+    SpCoef<KERNEL> cf;
+    if constexpr (KERNEL == GPB_KERNEL_CUBIC) {
+        cf.c0 = *reinterpret_cast<const double2*>(rec + 4);
+        cf.c1 = *reinterpret_cast<const double2*>(rec + 6);
+        cf.c2 = *reinterpret_cast<const double2*>(rec + 8);
+    }
+    return cf;
+}
+template <int KERNEL, bool GRAD>
+__device__ __forceinline__ void sp_pair(const SpCoef<KERNEL>& cf, double W, double u, double t, double& acc, double& g) {
+    if constexpr (KERNEL == GPB_KERNEL_CUBIC) {
+        acc = fma(t * u, fma(u, fma(cf.c1.x, u, cf.c0.y), cf.c0.x), acc);
+        if constexpr (GRAD) g = t * fma(u, fma(cf.c2.y, u, cf.c2.x), cf.c1.y);
+    } else {
+        double cv, kp;
+        cov_sp<KERNEL>(u, t, cv, kp);
+        acc = fma(W, cv, acc);
+        if constexpr (GRAD) g = W * kp;
     }
 }
 
@@ -177,7 +208,8 @@ __device__ __forceinline__ void act_min_commit(const EvalParams& prm, double vmi
 template <int KERNEL, bool GRAD, bool REGULAR, int P, int kThreads, int kMinBlocks>
 __global__ void __launch_bounds__(kThreads, kMinBlocks)
 eval_kernel(const EvalParams prm) {
-    __shared__ __align__(128) double stage[2][kTileBytes / 8];
+    constexpr int R = sp_rec(KERNEL);
+    __shared__ __align__(128) double stage[2][kTileSp * R];
     __shared__ __align__(8) uint64_t full[2];
     __shared__ ActShared act;
     double vmin = __longlong_as_double(0x7ff0000000000000LL);
@@ -194,7 +226,7 @@ eval_kernel(const EvalParams prm) {
     const long long n_sp_tiles = prm.n_sps_pad / kTileSp;
     const long long n_ori_tiles = prm.n_ori_pad / kTileOri;
     const long long n_tiles = n_sp_tiles + n_ori_tiles;
-    const double* src_ori = prm.src + 4 * prm.n_sps_pad;
+    const double* src_ori = prm.src + R * prm.n_sps_pad;
     const double* tail = src_ori + 6 * prm.n_ori_pad;
 
     const long long chunk = (long long)kThreads * P;
@@ -206,8 +238,8 @@ eval_kernel(const EvalParams prm) {
         // thread 0 only
         const int b = (int)(g & 1);
         if (j < n_sp_tiles) {
-            gpb_mbar_expect_tx(&full[b], kTileSp * 32);
-            gpb_bulk_g2s(stage[b], prm.src + 4 * (long long)kTileSp * j, kTileSp * 32, &full[b]);
+            gpb_mbar_expect_tx(&full[b], kTileSp * 8 * R);
+            gpb_bulk_g2s(stage[b], prm.src + R * (long long)kTileSp * j, kTileSp * 8 * R, &full[b]);
         } else {
             gpb_mbar_expect_tx(&full[b], kTileOri * 48);
             gpb_bulk_g2s(stage[b], src_ori + 6 * (long long)kTileOri * (j - n_sp_tiles), kTileOri * 48, &full[b]);
@@ -273,19 +305,17 @@ eval_kernel(const EvalParams prm) {
                 const int cnt_sp = (int)min((long long)kTileSp, (prm.n_sps - j * kTileSp + 1) & ~1LL);
 #pragma unroll 2
                 for (int q = 0; q < cnt_sp; ++q) {
-                    const double2 a0 = *reinterpret_cast<const double2*>(s + 4 * q);
-                    const double2 a1 = *reinterpret_cast<const double2*>(s + 4 * q + 2);
+                    const double2 a0 = *reinterpret_cast<const double2*>(s + R * q);
+                    const double2 a1 = *reinterpret_cast<const double2*>(s + R * q + 2);
+                    const SpCoef<KERNEL> cf = sp_coef<KERNEL>(s + R * q);
 #pragma unroll
                     for (int k = 0; k < P; ++k) {
                         const double dx = X[k] - a0.x, dy = Y[k] - a0.y, dz = Zc[k] - a1.x;
                         const double u = fma(dz, dz, fma(dy, dy, fma(dx, dx, prm.eps_u)));
                         const double t = EVAL_SQRT(u);
-                        double cv, kp;
-                        cov_sp<KERNEL>(u, t, cv, kp);
-                        const double wq = (KERNEL == GPB_KERNEL_CUBIC) ? a1.y * t : a1.y;     // W t for the cubic split
-                        accZ[k] = fma(wq, cv, accZ[k]);
+                        double g;
+                        sp_pair<KERNEL, GRAD>(cf, a1.y, u, t, accZ[k], g);
                         if constexpr (GRAD) {
-                            const double g = wq * kp;
                             hx[k] = fma(g, dx, hx[k]);
                             hy[k] = fma(g, dy, hy[k]);
                             hz[k] = fma(g, dz, hz[k]);
@@ -399,6 +429,7 @@ __global__ void pack_kernel(const PackParams p) {
     const double* mu = w_i + st.n_rest;
     const double* w_f = mu + st.n_drift;
     const long long n_sps = (long long)st.n_rest + st.n_surf;
+    const int rec = sp_rec(st.kernel);
     // surface-point sources
     for (long long i = tid; i < p.n_sps_pad; i += stride) {
         double x = 0, y = 0, z = 0, W = 0;
@@ -412,11 +443,15 @@ __global__ void pack_kernel(const PackParams p) {
             for (int r = st.surf_offsets[s]; r < st.surf_offsets[s + 1]; ++r) acc += w_i[r];
             W = -cI * acc;
         }
-        double* o = p.src + 4 * i;
+        double* o = p.src + rec * i;
         o[0] = x * inv_a; o[1] = y * inv_a; o[2] = z * inv_a; o[3] = W;
+        if (rec == 10) {
+            o[4] = 8.75 * W; o[5] = -3.5 * W; o[6] = 0.75 * W;
+            o[7] = 26.25 * W; o[8] = -17.5 * W; o[9] = 5.25 * W;
+        }
     }
     // orientation sources
-    double* so = p.src + 4 * p.n_sps_pad;
+    double* so = p.src + rec * p.n_sps_pad;
     for (long long i = tid; i < p.n_ori_pad; i += stride) {
         double v[6] = {0, 0, 0, 0, 0, 0};
         if (i < st.n_ori) {
@@ -470,7 +505,8 @@ __global__ void pack_kernel(const PackParams p) {
 template <int KERNEL, bool GRAD, int P, int kThreads, int kMinBlocks>
 __global__ void __launch_bounds__(kThreads, kMinBlocks)
 eval_zrun_kernel(const EvalParams prm) {
-    __shared__ __align__(128) double stage[2][kTileBytes / 8];
+    constexpr int R = sp_rec(KERNEL);
+    __shared__ __align__(128) double stage[2][kTileSp * R];
     __shared__ __align__(8) uint64_t full[2];
     __shared__ ActShared act;
     double vmin = __longlong_as_double(0x7ff0000000000000LL);
@@ -487,7 +523,7 @@ eval_zrun_kernel(const EvalParams prm) {
     const long long n_sp_tiles = prm.n_sps_pad / kTileSp;
     const long long n_ori_tiles = prm.n_ori_pad / kTileOri;
     const long long n_tiles = n_sp_tiles + n_ori_tiles;
-    const double* src_ori = prm.src + 4 * prm.n_sps_pad;
+    const double* src_ori = prm.src + R * prm.n_sps_pad;
     const double* tail = src_ori + 6 * prm.n_ori_pad;
 
     const long long n_runs = prm.m / P;                       // runs of P points
@@ -497,8 +533,8 @@ eval_zrun_kernel(const EvalParams prm) {
     auto issue = [&](long long j, unsigned long long g) {
         const int b = (int)(g & 1);
         if (j < n_sp_tiles) {
-            gpb_mbar_expect_tx(&full[b], kTileSp * 32);
-            gpb_bulk_g2s(stage[b], prm.src + 4 * (long long)kTileSp * j, kTileSp * 32, &full[b]);
+            gpb_mbar_expect_tx(&full[b], kTileSp * 8 * R);
+            gpb_bulk_g2s(stage[b], prm.src + R * (long long)kTileSp * j, kTileSp * 8 * R, &full[b]);
         } else {
             gpb_mbar_expect_tx(&full[b], kTileOri * 48);
             gpb_bulk_g2s(stage[b], src_ori + 6 * (long long)kTileOri * (j - n_sp_tiles), kTileOri * 48, &full[b]);
@@ -549,8 +585,9 @@ eval_zrun_kernel(const EvalParams prm) {
                 const int cnt_sp = (int)min((long long)kTileSp, (prm.n_sps - j * kTileSp + 1) & ~1LL);
 #pragma unroll 2
                 for (int q = 0; q < cnt_sp; ++q) {
-                    const double2 a0 = *reinterpret_cast<const double2*>(s + 4 * q);
-                    const double2 a1 = *reinterpret_cast<const double2*>(s + 4 * q + 2);
+                    const double2 a0 = *reinterpret_cast<const double2*>(s + R * q);
+                    const double2 a1 = *reinterpret_cast<const double2*>(s + R * q + 2);
+                    const SpCoef<KERNEL> cf = sp_coef<KERNEL>(s + R * q);
                     const double dx = X - a0.x, dy = Y - a0.y;
                     const double pxy = fma(dy, dy, fma(dx, dx, prm.eps_u));
 #pragma unroll
@@ -558,12 +595,9 @@ eval_zrun_kernel(const EvalParams prm) {
                         const double dz = Zc[k] - a1.x;
                         const double u = fma(dz, dz, pxy);
                         const double t = EVAL_SQRT(u);
-                        double cv, kp;
-                        cov_sp<KERNEL>(u, t, cv, kp);
-                        const double wq = (KERNEL == GPB_KERNEL_CUBIC) ? a1.y * t : a1.y;     // W t for the cubic split
-                        accZ[k] = fma(wq, cv, accZ[k]);
+                        double g;
+                        sp_pair<KERNEL, GRAD>(cf, a1.y, u, t, accZ[k], g);
                         if constexpr (GRAD) {
-                            const double g = wq * kp;
                             hx[k] = fma(g, dx, hx[k]);
                             hy[k] = fma(g, dy, hy[k]);
                             hz[k] = fma(g, dz, hz[k]);
@@ -677,7 +711,8 @@ eval_zrun_kernel(const EvalParams prm) {
 template <int KERNEL, bool GRAD, int kThreads>
 __global__ void __launch_bounds__(kThreads, 1)
 eval_octet_kernel(const EvalParams prm) {
-    __shared__ __align__(128) double stage[2][kTileBytes / 8];
+    constexpr int R = sp_rec(KERNEL);
+    __shared__ __align__(128) double stage[2][kTileSp * R];
     __shared__ __align__(8) uint64_t full[2];
     __shared__ ActShared act;
     double vmin = __longlong_as_double(0x7ff0000000000000LL);
@@ -694,7 +729,7 @@ eval_octet_kernel(const EvalParams prm) {
     const long long n_sp_tiles = prm.n_sps_pad / kTileSp;
     const long long n_ori_tiles = prm.n_ori_pad / kTileOri;
     const long long n_tiles = n_sp_tiles + n_ori_tiles;
-    const double* src_ori = prm.src + 4 * prm.n_sps_pad;
+    const double* src_ori = prm.src + R * prm.n_sps_pad;
     const double* tail = src_ori + 6 * prm.n_ori_pad;
 
     const long long n_oct = prm.m / 8;
@@ -704,8 +739,8 @@ eval_octet_kernel(const EvalParams prm) {
     auto issue = [&](long long j, unsigned long long g) {
         const int b = (int)(g & 1);
         if (j < n_sp_tiles) {
-            gpb_mbar_expect_tx(&full[b], kTileSp * 32);
-            gpb_bulk_g2s(stage[b], prm.src + 4 * (long long)kTileSp * j, kTileSp * 32, &full[b]);
+            gpb_mbar_expect_tx(&full[b], kTileSp * 8 * R);
+            gpb_bulk_g2s(stage[b], prm.src + R * (long long)kTileSp * j, kTileSp * 8 * R, &full[b]);
         } else {
             gpb_mbar_expect_tx(&full[b], kTileOri * 48);
             gpb_bulk_g2s(stage[b], src_ori + 6 * (long long)kTileOri * (j - n_sp_tiles), kTileOri * 48, &full[b]);
@@ -747,8 +782,9 @@ eval_octet_kernel(const EvalParams prm) {
                 const int cnt_sp = (int)min((long long)kTileSp, (prm.n_sps - j * kTileSp + 1) & ~1LL);
 #pragma unroll 2
                 for (int q = 0; q < cnt_sp; ++q) {
-                    const double2 a0 = *reinterpret_cast<const double2*>(s + 4 * q);
-                    const double2 a1 = *reinterpret_cast<const double2*>(s + 4 * q + 2);
+                    const double2 a0 = *reinterpret_cast<const double2*>(s + R * q);
+                    const double2 a1 = *reinterpret_cast<const double2*>(s + R * q + 2);
+                    const SpCoef<KERNEL> cf = sp_coef<KERNEL>(s + R * q);
                     const double dx[2] = {X[0] - a0.x, X[1] - a0.x}, dy[2] = {Y[0] - a0.y, Y[1] - a0.y};
                     const double dz[2] = {Zc[0] - a1.x, Zc[1] - a1.x};
                     const double px[2] = {fma(dx[0], dx[0], prm.eps_u), fma(dx[1], dx[1], prm.eps_u)};
@@ -757,12 +793,9 @@ eval_octet_kernel(const EvalParams prm) {
                     for (int k = 0; k < 8; ++k) {
                         const double u = fma(dz[k & 1], dz[k & 1], pxy[k >> 1]);
                         const double t = EVAL_SQRT(u);
-                        double cv, kp;
-                        cov_sp<KERNEL>(u, t, cv, kp);
-                        const double wq = (KERNEL == GPB_KERNEL_CUBIC) ? a1.y * t : a1.y;
-                        accZ[k] = fma(wq, cv, accZ[k]);
+                        double g;
+                        sp_pair<KERNEL, GRAD>(cf, a1.y, u, t, accZ[k], g);
                         if constexpr (GRAD) {
-                            const double g = wq * kp;
                             hx[k] = fma(g, dx[k >> 2], hx[k]);
                             hy[k] = fma(g, dy[(k >> 1) & 1], hy[k]);
                             hz[k] = fma(g, dz[k & 1], hz[k]);
@@ -980,7 +1013,7 @@ int fill_common(const gpb_stack* st, const double* src, EvalParams& prm) {
 
 extern "C" long long gpb_eval_table_doubles(const gpb_stack* st) {
     if (!st) return 0;
-    return 4 * gpb_round_up((long long)st->n_rest + st->n_surf, kTileSp) + 6 * gpb_round_up(st->n_ori, kTileOri) +
+    return sp_rec(st->kernel) * gpb_round_up((long long)st->n_rest + st->n_surf, kTileSp) + 6 * gpb_round_up(st->n_ori, kTileOri) +
            kTailDoubles + st->n_faults + 8;
 }
 
