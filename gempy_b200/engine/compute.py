@@ -551,7 +551,7 @@ class B200Engine:
 def compute_dense_fields(interpolation_input: InterpolationInput, options: InterpolationOptions,
                          data_descriptor: InputDataDescriptor, *, stack: int = 0, engine: Optional[B200Engine] = None,
                          point_range: Optional[Tuple[int, int]] = None, out: Optional[torch.Tensor] = None,
-                         n_slabs: int = 16, device: Optional[int] = None) -> torch.Tensor:
+                         n_slabs: int = 16, device: Optional[int] = None, wave_aligned: bool = True) -> torch.Tensor:
     """Scalar field and gradient of one (fault-free) stack on the dense regular grid, host in / host out.
 
     The reference obtains these with ``compute_model`` + ``evaluation_options.compute_scalar_gradient = True`` and reads
@@ -577,9 +577,14 @@ def compute_dense_fields(interpolation_input: InterpolationInput, options: Inter
             out = torch.empty((4, m), dtype=F64, pin_memory=True)
         gd = regular_descriptor(g)
         nyz = int(g.regular_grid_shape[1] * g.regular_grid_shape[2])
-        # slabs aligned to whole x planes when possible (keeps every slab on the z-run kernel)
+        # Slab size: a whole number of waves of the persistent evaluation kernel (one CTA per SM, 256 threads x 8 points per
+        # chunk) -- a 4-plane slab of a 512^3 grid is 3.46 waves and would idle 13 % of every launch; smaller ranges fall
+        # back to whole x planes.  Both are multiples of 8 points, which keeps every slab on the z-run kernel.
         per = max(1, -(-m // max(1, n_slabs)))
-        if per > nyz:
+        wave = torch.cuda.get_device_properties(eng.device).multi_processor_count * 256 * 8
+        if wave_aligned and per >= wave:
+            per = -(-per // wave) * wave
+        elif per > nyz:
             per = -(-per // nyz) * nyz
         compute = torch.cuda.current_stream(eng.device)
         if getattr(eng, "_copier", None) is None:

@@ -961,6 +961,31 @@ def test_tiny_dense_grids(eng, shape):
     np.testing.assert_array_equal(sol.raw_arrays.lith_block, ref.lith_ids[n_oct:n_oct + g.n_points])
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape,n_slabs,rng", [((96, 96, 96), 2, None), ((40, 24, 16), 5, None), ((40, 24, 16), 3, (1024, 9000)),
+                                               ((10, 6, 5), 4, (7, 211))])
+def test_compute_dense_fields_streaming(eng, shape, n_slabs, rng):
+    """The streaming host-in / host-out call bench.py's e2e figure goes through: Z and the gradient of a point range of the
+    dense grid, slab by slab (wave-aligned slabs at 96^3, plane-aligned and ragged ones below), against the oracle."""
+    m = ex.anticline(resolution=shape)
+    ii, opt, desc = m.args()
+    g = ii.grid.dense_grid
+    i0, i1 = rng if rng is not None else (0, g.n_points)
+    out = gc.compute_dense_fields(ii, opt, desc, engine=eng, point_range=rng, n_slabs=n_slabs)
+    assert tuple(out.shape) == (4, i1 - i0) and out.is_pinned()
+    st = _oracle_stack(m)
+    ko = opt.kernel_options
+    w = orc.solve(orc.assemble_covariance(st, ko), orc.rhs(st, ko))
+    idx = np.unique(np.concatenate([np.arange(i0, min(i1, i0 + 300)), np.linspace(i0, i1 - 1, 4000).astype(np.int64),
+                                    np.arange(max(i0, i1 - 300), i1)]))
+    Z, G = orc.evaluate(st, ko, w, g.values[idx] + orc.GRID_SHIFT, gradient=True)
+    got = out.numpy()
+    assert _rel_err(got[0, idx - i0], Z) < RTOL
+    gs = np.abs(G).max()
+    for a in range(3):
+        assert np.abs(got[1 + a, idx - i0] - G[:, a]).max() < RTOL * gs
+
+
 # ------------------------------------------------------------------------------------------- BASELINE configs in the suite
 def _full_model_check(build, vertex_tol_extent=0.5):
     """compute_model vs oracle on every level: leaf lists equal, fields < 1e-9 relative, lith ids exact on every voxel more
