@@ -98,7 +98,10 @@ int gpb_eval_call(const GpbEvalCall& c, cudaStream_t stream);
 // (512^3 benchmark 789 -> 854 ms per step, config-5 octree levels 1.15 -> 1.48 s) -- the five extra integer instructions per
 // pair cost more issue slots and latency than the shorter XU occupancy saves.  Kept behind GPB_MUFU32 for the record.
 // Mixing the two (32-bit seeds for the reciprocal of the orientation gradient term only, or for 2 / 4 of the 8 points a
-// thread owns) was slower in proportion to the share: 787 -> 803 / 804 / 831 ms.
+// thread owns) was slower in proportion to the share: 787 -> 803 / 804 / 831 ms.  Field-only kernels (10.5 FP64 instructions per
+// surface-point pair) behave the same: 256^3 z-run 57.36 ms with 64-bit seeds, 58.33 / 58.52 / 59.45 ms with 1 / 2 / 3 of the 8
+// points on 32-bit seeds -- that kernel already issues 97 % of the FP64 instructions per second of the DFMA-chain probe, so the
+// XU pipe is not what binds it, whatever its `xu_realtime` figure suggests.
 __device__ __forceinline__ double gpb_rsqrt_seed64(double u) {
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(u));
