@@ -111,6 +111,7 @@ SIGNATURES = {
     "gpb_corner_unique_emit": (C.c_int, [_P, _LL, _LL, C.c_double, C.c_double, C.c_double, _P, _LL, _P, _LL, _P, _LL, _P, _P]),
     "gpb_expand_rows": (C.c_int, [_P, _LL, _P, C.c_int, _LL, _P, _LL, _P]),
     "gpb_copy_2d": (C.c_int, [_P, _LL, _P, _LL, _LL, _LL, _P]),
+    "gpb_rint": (C.c_int, [_P, _LL, _P, _P]),
     "gpb_scan_elems": (_LL, [_LL]),
     "gpb_count_marked": (C.c_int, [_P, _LL, _P, C.POINTER(_LL), _P]),
     "gpb_emit_marked": (C.c_int, [_P, _LL, _LL, _P, _P, C.c_double, C.c_double, C.c_double, _P, _LL, _P]),

@@ -701,7 +701,7 @@ extern "C" int gpb_sym_solve(int n, int nk, double* A, int lda, double* b, int n
         int rca = chol_panel_attrs();
         if (rca) return rca;
     }
-    GPB_CHECK_CUDA(cudaMallocAsync((void**)&ws, sizeof(double) * (nk_pad + wt_doubles) + sizeof(int) * nblk, s));
+    GPB_CHECK_CUDA(gpb_malloc_async((void**)&ws, sizeof(double) * (nk_pad + wt_doubles) + sizeof(int) * nblk, s));
     double* wt_all = ws + nk_pad;
     int* flags = reinterpret_cast<int*>(ws + nk_pad + wt_doubles);
     save_diag_kernel<<<(nk + 255) / 256, 256, 0, s>>>(nk, A, lda, ws);

@@ -52,6 +52,8 @@ struct GpbSideStream {
     cudaEvent_t ready, done;
 };
 GpbSideStream* gpb_side_stream();
+// cudaMallocAsync from a per-device pool that keeps its memory (release with cudaFreeAsync); see gpb_lib.cu
+cudaError_t gpb_malloc_async(void** p, size_t bytes, cudaStream_t s);
 // The side stream and its events are shared by every caller on a device: the host-side ENQUEUE of a factorisation holds
 // this lock (event record / wait pairs are resolved at enqueue time, so serialising the enqueues is sufficient).
 struct GpbDeviceLock {

@@ -56,6 +56,40 @@ GpbSideStream* gpb_side_stream() {
     return g_side_state[dev] == 1 ? &g_side[dev] : nullptr;
 }
 
+// Scratch allocations of the entry points (flags, scan counts, the inverse diagonal blocks of the symmetric solve): a
+// per-device stream-ordered pool that KEEPS its memory.  The default pool hands freed memory back to the driver at the next
+// synchronisation (release threshold 0), so every call re-mapped a few megabytes; on a shared host that unmap / map pair was
+// measured to stall the solve for 50-700 ms in one step out of four (scripts/probes/e2e_breakdown.py).
+namespace {
+std::mutex g_pool_mutex;
+cudaMemPool_t g_pool[GPB_MAX_DEVICES] = {nullptr};
+int g_pool_state[GPB_MAX_DEVICES] = {0};      // 0: not tried, 1: ok, -1: failed (fall back to the default pool)
+constexpr size_t kPoolMaxBytes = 64u << 20;   // larger requests (a whole system matrix) are not worth keeping
+}  // namespace
+
+cudaError_t gpb_malloc_async(void** p, size_t bytes, cudaStream_t s) {
+    const int dev = gpb_current_device();
+    cudaMemPool_t pool = nullptr;
+    if (bytes <= kPoolMaxBytes) {
+        std::lock_guard<std::mutex> g(g_pool_mutex);
+        if (g_pool_state[dev] == 0 && getenv("GPB_SCRATCH_POOL") && atoi(getenv("GPB_SCRATCH_POOL")) == 0) g_pool_state[dev] = -1;
+        if (g_pool_state[dev] == 0) {
+            cudaMemPoolProps props = {};
+            props.allocType = cudaMemAllocationTypePinned;
+            props.handleTypes = cudaMemHandleTypeNone;
+            props.location.type = cudaMemLocationTypeDevice;
+            props.location.id = dev;
+            unsigned long long keep = ~0ULL;
+            const bool ok = cudaMemPoolCreate(&g_pool[dev], &props) == cudaSuccess &&
+                            cudaMemPoolSetAttribute(g_pool[dev], cudaMemPoolAttrReleaseThreshold, &keep) == cudaSuccess;
+            cudaGetLastError();
+            g_pool_state[dev] = ok ? 1 : -1;
+        }
+        if (g_pool_state[dev] == 1) pool = g_pool[dev];
+    }
+    return pool ? cudaMallocFromPoolAsync(p, bytes, pool, s) : cudaMallocAsync(p, bytes, s);
+}
+
 GpbDeviceLock::GpbDeviceLock() : dev(gpb_current_device()) { g_dev_mutex[dev].lock(); }
 GpbDeviceLock::~GpbDeviceLock() { g_dev_mutex[dev].unlock(); }
 

@@ -1106,7 +1106,7 @@ int factor_outer(int n, double* A, int lda, int* ipiv, int* info, double* B, int
 int backward_blocked(int n, const double* LU, int lda, double* B, int nrhs, int ldb, cudaStream_t s) {
     const int nblk = (n + kNB - 1) / kNB;
     int* flags = nullptr;
-    GPB_CHECK_CUDA(cudaMallocAsync((void**)&flags, sizeof(int) * nblk, s));
+    GPB_CHECK_CUDA(gpb_malloc_async((void**)&flags, sizeof(int) * nblk, s));
     for (int r = 0; r < nrhs; ++r) {
         GPB_CHECK_CUDA(cudaMemsetAsync(flags, 0, sizeof(int) * nblk, s));
         trsv_upper_kernel<<<nblk, 128, 0, s>>>(n, LU, lda, B + (long long)r * ldb, flags);

@@ -204,7 +204,7 @@ extern "C" int gpb_model_solve_stack(gpb_model* m, int i, const gpb_level* level
     // the caller's workspace when it is large enough (a 9.8 GB stream-ordered allocation costs more than the solve it is
     // for: the pool gives the memory back at every synchronisation), else a stream-ordered allocation
     const bool own_ws = !(workspace != nullptr && (size_t)workspace_bytes >= a_bytes + sizeof(int) * (size_t)(n + 4));
-    if (own_ws) GPB_CHECK_CUDA(cudaMallocAsync((void**)&ws, a_bytes + sizeof(int) * (size_t)(n + 4), s));
+    if (own_ws) GPB_CHECK_CUDA(gpb_malloc_async((void**)&ws, a_bytes + sizeof(int) * (size_t)(n + 4), s));
     else ws = (char*)workspace;
     double* A = reinterpret_cast<double*>(ws);
     int* ipiv = reinterpret_cast<int*>(ws + a_bytes);

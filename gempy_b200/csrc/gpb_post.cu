@@ -174,6 +174,11 @@ __global__ void mark_kernel(const double* __restrict__ lith, const double* __res
     }
 }
 
+__global__ void rint_kernel(const double* __restrict__ in, long long n, double* __restrict__ out) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        out[i] = rint(in[i]);
+}
+
 __global__ void any8_kernel(const unsigned char* __restrict__ in, long long nvox, unsigned char* __restrict__ out) {
     for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < nvox; v += (long long)gridDim.x * blockDim.x) {
         unsigned w = 0;
@@ -418,7 +423,7 @@ extern "C" int gpb_emit_children(const double* centers, long long ld_c, long lon
     cudaStream_t s = (cudaStream_t)stream;
     const long long nblocks = (nvox + kScanBlock - 1) / kScanBlock;
     long long* counts = nullptr;
-    GPB_CHECK_CUDA(cudaMallocAsync((void**)&counts, sizeof(long long) * (nblocks + 1), s));
+    GPB_CHECK_CUDA(gpb_malloc_async((void**)&counts, sizeof(long long) * (nblocks + 1), s));
     count_kernel<<<(unsigned)nblocks, kScanBlock, 0, s>>>(mark, nvox, counts);
     GPB_LAUNCH_CHECK();
     scan_counts_kernel<<<1, 1024, 0, s>>>(counts, nblocks, counts + nblocks);
@@ -513,6 +518,14 @@ extern "C" int gpb_copy_2d(double* dst, long long ld_dst, const double* src, lon
     if (rows == 0 || cols == 0) return GPB_OK;
     GPB_CHECK_CUDA(cudaMemcpy2DAsync(dst, sizeof(double) * ld_dst, src, sizeof(double) * ld_src, sizeof(double) * cols, rows,
                                      cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return GPB_OK;
+}
+
+extern "C" int gpb_rint(const double* in, long long n, double* out, void* stream) {
+    GPB_REQUIRE(in && out && n >= 0, "bad arguments");
+    if (n == 0) return GPB_OK;
+    rint_kernel<<<blocks_for(n), kT, 0, (cudaStream_t)stream>>>(in, n, out);
+    GPB_LAUNCH_CHECK();
     return GPB_OK;
 }
 

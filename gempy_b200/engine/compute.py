@@ -641,6 +641,18 @@ def _np(t: Optional[torch.Tensor]) -> Optional[np.ndarray]:
     return t.cpu().numpy()
 
 
+def _np_rint(t: torch.Tensor) -> np.ndarray:
+    """numpy.rint of a contiguous device vector, rounded on the device first (a host rint of a 512^3 block costs more than
+    its read-back)."""
+    if not t.is_cuda or t.numel() == 0:
+        return np.rint(_np(t))
+    t = t.detach().contiguous()
+    out = torch.empty_like(t)
+    with torch.cuda.device(t.device):
+        _lib.check(_lib.lib().gpb_rint(_ptr(t), t.numel(), _ptr(out), torch.cuda.current_stream(t.device).cuda_stream))
+    return _np(out)
+
+
 def _level_outputs(f: FieldsOnDevice, grid: EngineGrid, rel_enum: Sequence, iso_host=None) -> List[InterpOutput]:
     """Host containers over the device results; every array is copied on first access only."""
     D = Deferred
@@ -1017,18 +1029,21 @@ def _raw_arrays(eng: B200Engine, sol: Solutions, levels_dev, grid: EngineGrid, o
     sl = None
     if options.block_solutions_type == BlockSolutionType.DENSE_GRID and grid.dense_grid is not None:
         sl = g0.dense_grid_slice
-        ra.set_lazy("lith_block", lambda: np.rint(fb()[sl]))
-        ra.set_lazy("fault_block", lambda: np.rint(fa()[sl]))
+        f0 = levels_dev[0][2]                         # rounded on the device, only the dense-grid slice is read back
+        ra.set_lazy("lith_block", lambda: _np_rint(f0.final_block[sl]))
+        ra.set_lazy("fault_block", lambda: _np_rint(f0.faults_block[sl]))
     elif options.block_solutions_type == BlockSolutionType.OCTREE:
         root = grid.octree_grid
         sl = slice(0, int(np.prod(root.regular_grid_shape)))
         ra.set_lazy("lith_block", lambda: _fill_regular_from_octree(eng, levels_dev, root, "lith"))
         ra.set_lazy("fault_block", lambda: _fill_regular_from_octree(eng, levels_dev, root, "faults"))
     if sl is not None:
-        ra.set_lazy("scalar_field_matrix", lambda: np.stack([o.exported_fields.scalar_field_everywhere[sl] for o in outs]))
-        ra.set_lazy("block_matrix", lambda: np.stack([o.scalar_fields.values_block[0, sl] for o in outs]))
-        ra.set_lazy("mask_matrix", lambda: np.stack([o.scalar_fields.mask_components[sl] for o in outs]))
-        ra.set_lazy("mask_matrix_squeezed", lambda: np.stack([o.combined_scalar_field.squeezed_mask_array[sl] for o in outs]))
+        # [n_stacks, points] matrices: the slice is packed on the device and read back once (no host-side stack / copy)
+        fd = levels_dev[0][2]
+        ra.set_lazy("scalar_field_matrix", lambda: _np(fd.Z[:, sl]))
+        ra.set_lazy("block_matrix", lambda: _np(fd.block[:, sl]))
+        ra.set_lazy("mask_matrix", lambda: _np(fd.mask[:, sl]).astype(bool))
+        ra.set_lazy("mask_matrix_squeezed", lambda: _np(fd.squeezed[:, sl]).astype(bool))
 
         ra_ref = weakref.ref(ra)          # no strong self-reference: a cycle would keep the level's device buffers alive
                                           # until the cyclic garbage collector runs (4.6 GB per octree-8 solution)

@@ -272,6 +272,10 @@ int gpb_expand_rows(const double* src, long long ld_src, const int* map, int n_r
 /* dst[r][0..cols) = src[r][0..cols) for r < rows (device to device, on the copy engine). */
 int gpb_copy_2d(double* dst, long long ld_dst, const double* src, long long ld_src, long long rows, long long cols, void* stream);
 
+/* out[i] = rint(in[i]) (round half to even, as numpy.rint): the id blocks are rounded on the device before they are read
+ * back (the reference rounds on the host: RawArraysSolution.lith_block = rint(final_block)). in may equal out. */
+int gpb_rint(const double* in, long long n, double* out, void* stream);
+
 /* ---- (4b) octree refinement  [engine stage "octrees_topology"] ----------------------------------- */
 /* Corners of voxels (8 per voxel, sign pattern x:----++++ y:--++--++ z:-+-+-+-+), voxel-major:
  * corner = centre +- (hx, hy, hz); pass the half cell size. */

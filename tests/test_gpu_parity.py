@@ -536,6 +536,19 @@ def test_dense_grid_solution_shape_and_ids():
     ii, opt, desc = ex.combination(resolution=(20, 10, 10)).args()
     f = orc.interpolate_all_fields(ii, opt, desc, ii.grid.dense_grid.values + orc.GRID_SHIFT)
     np.testing.assert_array_equal(sol.raw_arrays.lith_block, f.lith_ids)
+    # the raw-array matrices are device-side slices of the same rows the per-stack outputs expose
+    ra, outs = sol.raw_arrays, sol.octrees_output[0].outputs_centers
+    sl = sol.octrees_output[0].grid_centers.dense_grid_slice
+    assert ra.block_matrix.shape == ra.mask_matrix.shape == ra.mask_matrix_squeezed.shape == (3, 2000)
+    for i, o in enumerate(outs):
+        np.testing.assert_array_equal(ra.scalar_field_matrix[i], o.exported_fields.scalar_field_everywhere[sl])
+        np.testing.assert_array_equal(ra.block_matrix[i], o.scalar_fields.values_block[0, sl])
+        np.testing.assert_array_equal(ra.mask_matrix[i], o.scalar_fields.mask_components[sl])
+        np.testing.assert_array_equal(ra.mask_matrix_squeezed[i], o.combined_scalar_field.squeezed_mask_array[sl])
+        assert _rel_err(ra.scalar_field_matrix[i], f.stacks[i].Z[:2000]) < RTOL
+    np.testing.assert_array_equal(ra.lith_block, np.rint(outs[-1].combined_scalar_field.final_block[sl]))
+    np.testing.assert_array_equal(ra.fault_block, np.rint(outs[-1].combined_scalar_field.faults_block[sl]))
+    assert ra.mask_matrix.dtype == bool and ra.lith_block.dtype == np.float64
 
 
 @pytest.mark.parametrize("build,n_meshes", [(lambda: ex.anticline(refinement=4), 2), (lambda: ex.combination(refinement=4), 4),
