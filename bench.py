@@ -434,7 +434,7 @@ def run_gpu(args):
             lb = sol.raw_arrays.lith_block
             sf = sol.raw_arrays.scalar_field_matrix
             return {"lith_block_points": int(lb.shape[0]), "scalar_field_matrix": list(sf.shape),
-                    "n_units": int(np.unique(lb[:: max(1, lb.shape[0] // 65536)]).shape[0])}
+                    "n_units": int(np.unique(lb[:: max(1, lb.shape[0] // 65536) | 1]).shape[0])}
 
         def build3():
             m3 = build_workload(args)

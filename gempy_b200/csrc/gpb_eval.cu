@@ -955,6 +955,8 @@ int launch_eval(const EvalParams& prm, cudaStream_t stream) {
         // regular grids: z-run kernel whenever the range is made of whole runs (variant 100 forces the generic one)
         // measured on B200 (512^3-class grids, cubic, gradient): P=8/T=256 0.751 of the DFMA peak, P=8/T=128x2 0.734,
         // P=4/T=384 0.726, P=4/T=256 0.705, generic strided kernel 0.633
+        // round 2, 16.5-instruction pair loop, 512^3: P=8/T=256 (226 registers) 779 ms; P=8 with T = 288 / 320 / 384 (ptxas
+        // drops to 168 registers) 1108 / 993 / 826 ms; source loop unrolled by 1 / 4 instead of 2: 795 / 784 ms
         if (variant == 9 && zrun_ok<8>(prm)) return launch_zrun_cfg<KERNEL, GRAD, 8, 128, 2>(prm, stream);
         if (variant == 10 && zrun_ok<4>(prm)) return launch_zrun_cfg<KERNEL, GRAD, 4, 384, 1>(prm, stream);
         if (variant == 11 && zrun_ok<4>(prm)) return launch_zrun_cfg<KERNEL, GRAD, 4, 256, 1>(prm, stream);
