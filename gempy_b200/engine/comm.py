@@ -9,6 +9,8 @@ slice of the regular grid / of the octree level's voxel list.  The only exchange
   * all-gather of the per-level refine marks (1 byte per voxel), so that every rank builds the identical child
     list -- the leaf order, and therefore every output, is independent of the number of GPUs,
   * all-gather of the output slices when the host asks for whole arrays.
+Levels that do not pay for these exchanges (compute._shard_pays: evaluation time saved against the all-gather of the level's
+outputs) are not sharded: every rank evaluates them whole (`Comm.solo()`), which leaves the ranks in the identical state.
 """
 from __future__ import annotations
 
@@ -37,6 +39,14 @@ class Comm:
         self.enabled = dist.is_available() and dist.is_initialized()
         self.rank = dist.get_rank(group) if self.enabled else 0
         self.world = dist.get_world_size(group) if self.enabled else 1
+
+    @classmethod
+    def solo(cls) -> "Comm":
+        """A Comm of one rank whatever the process group: used for work too small to shard (every rank repeats it and
+        holds the identical result, nothing is exchanged)."""
+        c = cls.__new__(cls)
+        c.group, c.enabled, c.rank, c.world = None, False, 0, 1
+        return c
 
     def shard(self, n: int) -> Tuple[int, int]:
         return shard_range(n, self.rank, self.world)

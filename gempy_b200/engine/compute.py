@@ -752,6 +752,21 @@ def compute_model_at(interpolation_input: InterpolationInput, options: Interpola
     return sol.raw_arrays.custom
 
 
+def _shard_pays(n_pts: int, n_src_total: int, n_stacks: int, world: int) -> bool:
+    """Is a level worth sharding over `world` ranks?  Evaluation time saved (1e-12 s per point-source pair: 17 FP64
+    instructions at the measured issue rate) against twice the cost of the exchanges it brings (the level's outputs --
+    about 20 bytes per point and stack -- all-gathered at ~100 GB/s effective, plus 2 ms of per-stack launch sequences and
+    small collectives).  Config 3 (5000 sources, one stack) and config 5 (25 000) shard; the 15-stack multi-fault model
+    (125 sources per stack) does not -- sharded it ran 38 ms on 2 GPUs and 47 ms on 8 against 31 ms on one.
+    GPB_SHARD_MIN_PAIRS=<pairs> replaces the model by a plain threshold (tests: 0 shards everything)."""
+    env = os.environ.get("GPB_SHARD_MIN_PAIRS")
+    if env is not None:
+        return float(n_pts) * n_src_total >= float(env)
+    t_eval = float(n_pts) * n_src_total * 1.0e-12
+    t_xchg = float(n_pts) * n_stacks * 20.0 / 1.0e11 + 2.0e-3
+    return t_eval * (1.0 - 1.0 / world) > 2.0 * t_xchg
+
+
 def _compute_model(eng: B200Engine, interpolation_input, options, data_descriptor, geophysics_input, comm: Comm) -> Solutions:
     ii, desc = interpolation_input, data_descriptor
     eo = options.evaluation_options
@@ -788,8 +803,19 @@ def _compute_model(eng: B200Engine, interpolation_input, options, data_descripto
     dedupe = os.environ.get("GPB_NO_CORNER_DEDUPE") is None
     pending = None                                      # (parent centres, nv_parent, d_parent, mark, offsets) of the next emission
     nv = int(np.prod(root.regular_grid_shape))
+    world_comm = comm
+    n_src_total = sum(int(st.n_ori + st.n_rest + st.n_surf) for st in tables)
     for lvl in range(n_levels):
         need_corners = (lvl < n_levels - 1) or (lvl == dc_level)
+        # a level is sharded over the ranks only when it is worth the exchanges (fault-minimum all-reduces, mark and output
+        # all-gathers, one launch sequence per stack instead of one native call): otherwise every rank evaluates it whole
+        comm = world_comm
+        if world_comm.world > 1:
+            n_pts = nv * (9 if need_corners else 1) + n_sp
+            if lvl == 0:
+                n_pts += (grid.dense_grid.n_points if grid.dense_grid is not None else 0) + sum(v.shape[1] for _, v in extras_host)
+            if not _shard_pays(n_pts, n_src_total, n_st, world_comm.world):
+                comm = Comm.solo()
         v0, v1 = comm.shard(nv)
         nvl = v1 - v0
         # ---- this level's voxel centres: [3, nv], the whole list on every rank (children are emitted by every rank)

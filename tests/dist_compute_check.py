@@ -24,8 +24,13 @@ def main():
     comm = Comm()
     eng = gc.B200Engine(local)
     worst = 0.0
-    # greenstone: three fault-free series -> the per-stack solves are dealt out over the ranks
-    for build in (ex.combination, ex.one_fault, lambda: ex.combination(resolution=(21, 10, 9)), lambda: ex.greenstone(refinement=4)):
+    builds = (ex.combination, ex.one_fault, lambda: ex.combination(resolution=(21, 10, 9)), lambda: ex.greenstone(refinement=4))
+    # every level sharded ("0"), only the deeper levels sharded, and the default threshold (these models: nothing sharded)
+    for build, min_pairs in [(b, t) for b in builds for t in ("0", "2e5", None)]:
+        if min_pairs is None:
+            os.environ.pop("GPB_SHARD_MIN_PAIRS", None)
+        else:
+            os.environ["GPB_SHARD_MIN_PAIRS"] = min_pairs
         sol_d = gc.compute_model(*build().args(), engine=eng, comm=comm)
         sol_1 = gc.compute_model(*build().args(), engine=eng, comm=None if False else _Single())
         assert len(sol_d.octrees_output) == len(sol_1.octrees_output)

@@ -135,3 +135,18 @@ def test_engine_inputs_npz_round_trip(tmp_path):
     assert opt.number_octree_levels == 3 and opt.number_octree_levels_surface == 3
     assert [r.name for r in desc.stack_structure.masking_descriptor] == ["FAULT", "ERODE", "BASEMENT"]
     np.testing.assert_array_equal(desc.stack_structure.faults_relations, m.descriptor.stack_structure.faults_relations)
+
+
+def test_shard_decision_cost_model(monkeypatch):
+    """Per-level sharding policy (engine/compute.py:_shard_pays): BASELINE configs 3 and 5 shard their big levels over the
+    ranks, the 15-stack multi-fault model and every shallow level are evaluated whole on each rank."""
+    from gempy_b200.engine.compute import _shard_pays
+    monkeypatch.delenv("GPB_SHARD_MIN_PAIRS", raising=False)
+    assert _shard_pays(134_217_728, 5000, 1, 8) and _shard_pays(134_217_728, 5000, 1, 2)        # config 3, dense 512^3
+    assert _shard_pays(10_500_000, 25_000, 1, 8)                                                # config 5, level 10
+    assert not _shard_pays(6_000_000, 1870, 15, 8)                                              # config 4, level 8
+    assert not _shard_pays(8 * 9 + 100, 25_000, 1, 8)                                           # any root level
+    monkeypatch.setenv("GPB_SHARD_MIN_PAIRS", "0")
+    assert _shard_pays(1, 1, 1, 2)
+    monkeypatch.setenv("GPB_SHARD_MIN_PAIRS", "1e30")
+    assert not _shard_pays(134_217_728, 5000, 1, 8)

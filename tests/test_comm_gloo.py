@@ -58,6 +58,12 @@ def _worker(rank, world, port, q):
         m = torch.tensor([float(3 - rank)])
         comm.all_reduce_min(m)
         assert m.item() == 3.0 - (world - 1)
+        # a level too small to shard: every rank keeps the whole range and nothing is exchanged
+        solo = Comm.solo()
+        assert (solo.world, solo.rank, solo.enabled) == (1, 0, False) and solo.shard(nv) == (0, nv)
+        assert solo.all_gather_cat(marks_global, nv) is marks_global
+        m = torch.tensor([float(rank)])
+        assert solo.all_reduce_min(m).item() == float(rank)
         q.put((rank, "ok"))
     except Exception as exc:          # pragma: no cover
         q.put((rank, repr(exc)))
