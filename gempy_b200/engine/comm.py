@@ -66,6 +66,28 @@ class Comm:
             dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
         return t
 
+    def all_gather_rows_into(self, out: torch.Tensor, local: torch.Tensor, n_total: int) -> None:
+        """out[..., :n_total] = the ranks' shards of `local` (range(n_total)-sharded along the LAST dimension) in rank
+        order.  With equal shards on CUDA tensors every leading-index row is gathered by NCCL straight into its place
+        (no padded staging copy, no concatenation); otherwise all_gather_cat + one copy."""
+        if not (self.enabled and self.world > 1):
+            out[..., :n_total].copy_(local)
+            return
+        if n_total == 0:
+            return
+        if n_total % self.world == 0 and local.is_cuda and hasattr(dist, "all_gather_into_tensor"):
+            m = n_total // self.world
+            assert local.shape[-1] == m, (local.shape, n_total, self.world)
+            try:                                  # views only: a reshape that copies would swallow the gathered rows
+                o2, l2 = out.view(-1, out.shape[-1]), local.view(-1, local.shape[-1])
+            except RuntimeError:
+                o2 = l2 = None
+            if o2 is not None and o2.stride(-1) == 1 and l2.stride(-1) == 1 and o2.shape[0] == l2.shape[0]:
+                for r in range(o2.shape[0]):
+                    dist.all_gather_into_tensor(o2[r, :n_total], l2[r], group=self.group)
+                return
+        out[..., :n_total].copy_(self.all_gather_cat(local.contiguous(), n_total))
+
     def all_gather_cat(self, local: torch.Tensor, n_total: int) -> torch.Tensor:
         """Concatenate the ranks' shards of a range(n_total)-sharded tensor along its LAST dimension.
         Shard sizes follow shard_range, so no size exchange is needed."""

@@ -532,15 +532,19 @@ class B200Engine:
             return f
         n_sp = f.Z.shape[1] - f.grid_size
 
+        L_tot = int(sum(totals)) + n_sp
+
         def full(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
             if t is None:
                 return None
-            parts, off = [], 0
-            for seg, tot in zip(f.segments, totals):
-                parts.append(comm.all_gather_cat(t[..., off:off + seg.m].contiguous(), tot))
+            out = torch.empty(*t.shape[:-1], L_tot, dtype=t.dtype, device=t.device)
+            off = o_t = 0
+            for seg, tot in zip(f.segments, totals):          # each segment's shards land in place, row by row
+                comm.all_gather_rows_into(out[..., o_t:o_t + int(tot)], t[..., off:off + seg.m], int(tot))
                 off += seg.m
-            parts.append(t[..., off:off + n_sp])
-            return torch.cat(parts, dim=-1).contiguous()
+                o_t += int(tot)
+            out[..., o_t:].copy_(t[..., off:off + n_sp])
+            return out
 
         segs = [Segment(sg.name, int(tot)) for sg, tot in zip(f.segments, totals)]
         return FieldsOnDevice(segs, int(sum(totals)), full(f.Z), full(f.G), full(f.block), full(f.final_block),

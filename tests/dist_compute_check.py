@@ -24,7 +24,8 @@ def main():
     comm = Comm()
     eng = gc.B200Engine(local)
     worst = 0.0
-    builds = (ex.combination, ex.one_fault, lambda: ex.combination(resolution=(21, 10, 9)), lambda: ex.greenstone(refinement=4))
+    builds = (ex.combination, ex.one_fault, lambda: ex.combination(resolution=(21, 10, 9)), lambda: ex.combination(resolution=(7, 5, 3)),
+              lambda: ex.greenstone(refinement=4))          # (7, 5, 3): 105 dense points, ragged shards
     # every level sharded ("0"), only the deeper levels sharded, and the default threshold (these models: nothing sharded)
     for build, min_pairs in [(b, t) for b in builds for t in ("0", "2e5", None)]:
         if min_pairs is None:

@@ -46,6 +46,12 @@ def _worker(rank, world, port, q):
         c0, c1 = comm.shard(7)
         got = comm.all_gather_cat(ref[:, c0:c1].contiguous(), 7)
         assert torch.equal(got, ref)
+        # level outputs gathered in place (CPU tensors take the all_gather_cat + copy route; NCCL rows land directly)
+        ref3 = torch.arange(2 * 3 * 8, dtype=torch.float64).reshape(2, 3, 8)
+        out3 = torch.zeros(2, 3, 11, dtype=torch.float64)
+        c0, c1 = comm.shard(8)
+        comm.all_gather_rows_into(out3[..., 2:10], ref3[..., c0:c1], 8)
+        assert torch.equal(out3[..., 2:10], ref3) and out3[..., :2].abs().sum() == 0 and out3[..., 10:].abs().sum() == 0
         # an empty shard on one rank
         e0, e1 = comm.shard(1)
         got = comm.all_gather_cat(torch.full((e1 - e0,), 5.0), 1)
