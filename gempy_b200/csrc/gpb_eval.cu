@@ -27,6 +27,11 @@
 #define EVAL_SQRT gpb_fast_sqrt2
 #define EVAL_RCP gpb_fast_rcp2
 #endif
+#ifdef GPB_EVAL_LIBM_EXP
+#define EVAL_EXP exp
+#else
+#define EVAL_EXP gpb_fast_exp_neg
+#endif
 
 namespace {
 
@@ -91,12 +96,12 @@ __device__ __forceinline__ void cov_sp(double u, double t, double& c, double& kp
         kp = fma(u, fma(5.25, u, -17.5), 26.25);
         c = u * P;
     } else if constexpr (KERNEL == GPB_KERNEL_EXPONENTIAL) {
-        const double e = exp(-0.5 * u);
+        const double e = EVAL_EXP(-0.5 * u);
         c = e;
         kp = -e;
     } else {
         const double s = 2.23606797749978969641 * t;
-        const double e = exp(-s);
+        const double e = EVAL_EXP(-s);
         c = fma(s, fma(s, 1.0 / 3.0, 1.0), 1.0) * e;
         kp = (-5.0 / 3.0) * (1.0 + s) * e;
     }
@@ -111,12 +116,12 @@ __device__ __forceinline__ void cov_ori(double u, double t, double& kp, double& 
         const double om = fma(-5.12347538297979853, u, 5.12347538297979853);
         dd = -(om * om) * t;
     } else if constexpr (KERNEL == GPB_KERNEL_EXPONENTIAL) {
-        const double e = exp(-0.5 * u);
+        const double e = EVAL_EXP(-0.5 * u);
         kp = -e;
         dd = -e * u;
     } else {
         const double s = 2.23606797749978969641 * t;
-        const double e = exp(-s);
+        const double e = EVAL_EXP(-s);
         kp = (-5.0 / 3.0) * (1.0 + s) * e;
         dd = (-5.0 / 3.0) * e * s * s;
     }
