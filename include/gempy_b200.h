@@ -6,7 +6,9 @@
  * GPB_E_* code, in which case gpb_last_error() holds a message.  Launches are asynchronous on
  * `stream` unless stated otherwise.  Entries act on the CURRENT CUDA device (cudaSetDevice before calling; the host
  * mirror does).  Process-wide state: the launch counter (atomic); the tuning setters gpb_lu_set_outer_*; per DEVICE:
- * kernel attributes and one high-priority side stream + two events used by the factorisations' look-ahead -- the
+ * kernel attributes, one high-priority side stream + two events used by the factorisations' look-ahead, and one
+ * stream-ordered memory pool for the entries' own scratch (flags, scan counts, inverse diagonal blocks: a few MB; the pool
+ * keeps what it has allocated until the process ends, GPB_SCRATCH_POOL=0 reverts to the device's default pool) -- the
  * enqueue of a factorisation is serialised per device by a mutex inside the library, so calls are thread-safe, but a
  * factor and the gpb_lu_apply calls that replay it must see the same gpb_lu_set_outer_* settings.
  *
