@@ -331,6 +331,32 @@ def test_eval_points_field_and_gradient(eng, name, kernel):
     assert _rel_err(G, Gr) < RTOL
 
 
+@pytest.mark.parametrize("kernel", [K.exponential, K.matern_5_2])
+def test_eval_exp_argument_range(eng, kernel):
+    """The pair loops' own exp (gpb_fast_exp_neg): a range 400x smaller than the model makes the arguments run from 0 (points
+    on the data) to about -900 (Matern) / -80 000 (exponential), far below the clamp at -700, where libm underflows to 0."""
+    m = MODELS["synthetic_300"]()
+    ii, opt, desc = m.args()
+    ko = opt.kernel_options
+    ko.kernel_function = kernel
+    ko.range = ko.range / 400.0
+    so = _oracle_stack(m)
+    rng = np.random.default_rng(5)
+    w = rng.standard_normal(orc.system_size(so, ko))
+    sp = ii.surface_points.sp_coords
+    xyz = np.vstack([rng.uniform(-0.5, 0.5, size=(2000, 3)), sp, sp + rng.normal(0, ko.range, size=sp.shape),
+                     ii.orientations.dip_positions + rng.normal(0, 3 * ko.range, size=ii.orientations.dip_positions.shape)])
+    st = gc.StackTables(ii, desc, 0, ko, eng.device)
+    src = eng.pack(st, torch.as_tensor(w, device=eng.device))
+    Z, G = eng.empty(xyz.shape[0]), eng.empty(3, xyz.shape[0])
+    seg = gc.Segment("p", xyz.shape[0], xyz=torch.as_tensor(np.ascontiguousarray(xyz.T), device=eng.device))
+    eng.evaluate_segment(st, src, seg, 0, Z, G, None)
+    Zr, Gr = orc.evaluate(so, ko, w, xyz, gradient=True)
+    Zh, Gh = Z.cpu().numpy(), G.cpu().numpy().T
+    assert np.isfinite(Zh).all() and np.isfinite(Gh).all()
+    assert _rel_err(Zh, Zr) < RTOL and _rel_err(Gh, Gr) < RTOL
+
+
 def test_eval_degree2_drift(eng):
     m = MODELS["synthetic_300"]()
     rng = np.random.default_rng(2)
