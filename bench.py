@@ -204,7 +204,7 @@ def fp64_peaks(eng):
         best = 0.0
         for _ in range(3):
             v = C.c_double(0.0)
-            _lib.check(fn(20000, C.byref(v), eng.stream))
+            _lib.check(fn(100000, C.byref(v), eng.stream))
             best = max(best, v.value)
         out[name] = best
     return out
@@ -473,7 +473,10 @@ def run_gpu(args):
         sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
         nominal_peak = eng.sm_count * 64 * 2 * 1.965e9 / 1e12       # 148 SM x 64 FP64 lanes x 2 x 1.965 GHz
         peak_at_clock = eng.sm_count * 64 * 2 * sm_mhz * 1e6 / 1e12
+        pcs = ClockSampler(local)                   # the probes' own clock record (they run for ~0.5 s in total)
+        pcs.start()
         peaks = fp64_peaks(eng)
+        peaks["clocks"] = pcs.stop()
         measured_peak = peaks["dfma_tflops"]
         # DRAM traffic of one launch of the dominant kernel: from the committed ncu --set full capture of this command
         # (profiles/ncu_traffic.json, written by scripts/ncu_traffic.py), never a constant in this file
@@ -490,7 +493,7 @@ def run_gpu(args):
                 "peak_nominal": nominal_peak, "frac_of_nominal": achieved_tf / nominal_peak,
                 "peak_at_measured_clock": peak_at_clock, "frac_at_measured_clock": achieved_tf / peak_at_clock,
                 "flops_per_point": F, "kernel": "eval_zrun_kernel<cubic, grad, P=8, T=256>",
-                "bound_note": "neither HBM (0.06 % DRAM utilisation) nor tensor: the FP64 FMA pipe is the binding resource (ncu: 89 % pipe-active)",
+                "bound_note": "neither HBM (0.06 % DRAM utilisation) nor tensor: the FP64 FMA pipe is the binding resource (ncu: 85 % pipe-active, profiles/r2_eval_zrun_kernel_ncu_full_512.txt)",
                 "hbm": {"achieved_gbs": value / world * 32 / 1e9, "algorithmic_bytes_per_point": 32}}
         cpu = None
         if not args.no_cpu and world == 1:
