@@ -256,3 +256,33 @@ def test_oracle_invariances():
     Z2, G2 = fields(sp[perm], op[po], og[po], xyz, nug_s[perm], nug_o[po])
     np.testing.assert_allclose(Z2, Z0, rtol=0, atol=1e-8 * np.abs(Z0).max())
     np.testing.assert_allclose(G2, G0, rtol=0, atol=1e-8 * np.abs(G0).max())
+
+
+@pytest.mark.parametrize("kind", ["cubic", "exponential", "matern_5_2"])
+def test_kernel_terms_are_self_consistent(kind):
+    """The three covariance terms the assembly and the evaluation use, C, C'/r and C'', agree with numerical derivatives of
+    C for every kernel (the exponential and Matern forms have no reference fixture: this at least ties their derivative
+    terms to their own C), C(0) = 1, and the cubic kernel and its first two derivatives vanish at the range."""
+    a = 1.7
+    r = np.linspace(0.05, 1.6, 200)
+    h = 1e-5
+    C, Cp_r, Cpp = orc.kernel_terms(r, a, kind)
+    Cp, _, _ = orc.kernel_terms(r + h, a, kind)
+    Cm, _, _ = orc.kernel_terms(r - h, a, kind)
+    np.testing.assert_allclose(Cp_r * r, (Cp - Cm) / (2 * h), rtol=1e-7, atol=1e-9)
+    np.testing.assert_allclose(Cpp, (Cp - 2 * C + Cm) / h ** 2, rtol=1e-4, atol=1e-5)
+    assert abs(float(orc.kernel_terms(np.array([0.0]), a, kind)[0][0]) - 1.0) < 1e-15
+    if kind == "cubic":
+        Ca, Cpa, Cppa = orc.kernel_terms(np.array([a]), a, kind)
+        assert abs(Ca[0]) < 1e-14 and abs(Cpa[0]) < 1e-14 and abs(Cppa[0]) < 1e-13
+
+
+def test_matern_52_is_the_published_matern():
+    """Matern covariance of smoothness nu = 5/2 in its general (Bessel) form, 2^(1-nu)/Gamma(nu) x^nu K_nu(x) with
+    x = sqrt(2 nu) r / a, against the closed form the oracle (and the CUDA kernels) use."""
+    from scipy.special import gamma, kv
+    a, nu = 1.7, 2.5
+    r = np.linspace(1e-3, 6.0, 400)
+    x = np.sqrt(2 * nu) * r / a
+    general = 2.0 ** (1 - nu) / gamma(nu) * x ** nu * kv(nu, x)
+    np.testing.assert_allclose(orc.kernel_terms(r, a, "matern_5_2")[0], general, rtol=1e-12, atol=1e-15)
